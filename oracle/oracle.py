@@ -1,0 +1,388 @@
+"""Python face of the parity oracle (TEST INFRASTRUCTURE ONLY -- never imported by the
+product package `rlobjectdetection_b200`; only tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs may import this module).
+
+Heavy loops live in rlod_oracle.c (liboracle.so, built by `make -C oracle`); the small
+pieces (anchor table, action table, move_from_act) are restated in numpy here.  Every
+function cites the reference file:line it follows (paths relative to the reference
+checkout jbr97/RLObjectDetection).
+
+Pinning status: PINNED -- see oracle/README.md.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+c_f = ctypes.POINTER(ctypes.c_float)
+c_d = ctypes.POINTER(ctypes.c_double)
+c_i = ctypes.POINTER(ctypes.c_int)
+c_u8 = ctypes.POINTER(ctypes.c_ubyte)
+
+
+def build(verbose=False):
+    """make -C oracle (liboracle.so always; _ref/*.so only when /root/reference exists)."""
+    r = subprocess.run(["make", "-C", _HERE], capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        print(r.stdout, r.stderr)
+    if r.returncode != 0:
+        raise RuntimeError("oracle build failed")
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(path):
+            build()
+        _LIB = ctypes.CDLL(path)
+        _LIB.orc_nms.restype = ctypes.c_int
+        _LIB.orc_nms_iou.restype = ctypes.c_float
+        _LIB.orc_max_threads.restype = ctypes.c_int
+        _LIB.orc_roi_pool_fwd_cpu_nhwc.restype = ctypes.c_int
+    return _LIB
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t) if a is not None else None
+
+
+def max_threads():
+    return int(lib().orc_max_threads())
+
+
+def set_threads(n):
+    lib().orc_set_threads(int(n))
+
+
+# ----------------------------------------------------------------------------------------
+# anchors: lib/model/rpn/generate_anchors.py:45-105
+# ----------------------------------------------------------------------------------------
+def generate_anchors(base_size=16, ratios=(0.5, 1, 2), scales=(8, 16, 32)):
+    ratios = np.asarray(ratios, dtype=np.float64)
+    scales = np.asarray(scales, dtype=np.float64)
+
+    def whctrs(a):  # :58-67
+        w = a[2] - a[0] + 1
+        h = a[3] - a[1] + 1
+        return w, h, a[0] + 0.5 * (w - 1), a[1] + 0.5 * (h - 1)
+
+    def mk(ws, hs, xc, yc):  # :69-81
+        ws = ws[:, None]
+        hs = hs[:, None]
+        return np.hstack((xc - 0.5 * (ws - 1), yc - 0.5 * (hs - 1), xc + 0.5 * (ws - 1), yc + 0.5 * (hs - 1)))
+
+    base = np.array([1, 1, base_size, base_size], dtype=np.float64) - 1
+    w, h, xc, yc = whctrs(base)
+    size_ratios = (w * h) / ratios  # :88-90
+    ws = np.round(np.sqrt(size_ratios))  # :91 (np.round = half to even)
+    hs = np.round(ws * ratios)  # :92
+    ratio_anchors = mk(ws, hs, xc, yc)
+    out = []
+    for i in range(ratio_anchors.shape[0]):  # :53-54 ratio-major, scale-minor
+        w, h, xc, yc = whctrs(ratio_anchors[i])
+        out.append(mk(w * scales, h * scales, xc, yc))
+    return np.vstack(out)
+
+
+# ----------------------------------------------------------------------------------------
+# NMS: lib/model/nms/src/nms_cuda_kernel.cu:31-39,77-81,123-144
+# ----------------------------------------------------------------------------------------
+def nms(dets, thresh, max_keep=0):
+    dets = _f32(dets)
+    n, stride = dets.shape if dets.ndim == 2 else (0, 5)
+    keep = np.empty(max(n, 1), dtype=np.int32)
+    num = lib().orc_nms(_p(dets, c_f), n, stride, ctypes.c_float(thresh), int(max_keep), _p(keep, c_i))
+    return keep[:num].copy()
+
+
+def nms_batched(dets, seg_offsets, thresh, max_keep=0):
+    dets = _f32(dets)
+    seg = np.ascontiguousarray(seg_offsets, dtype=np.int32)
+    nseg = seg.shape[0] - 1
+    keep = np.full(max(dets.shape[0], 1), -1, dtype=np.int32)
+    num = np.zeros(max(nseg, 1), dtype=np.int32)
+    lib().orc_nms_batched(_p(dets, c_f), dets.shape[1], _p(seg, c_i), nseg, ctypes.c_float(thresh),
+                          int(max_keep), _p(keep, c_i), _p(num, c_i))
+    return keep, num[:nseg]
+
+
+def nms_iou(a, b):
+    a = _f32(a)
+    b = _f32(b)
+    return float(lib().orc_nms_iou(_p(a, c_f), _p(b, c_f)))
+
+
+# ----------------------------------------------------------------------------------------
+# RoIAlign: lib/model/roi_align/src/roi_align_kernel.cu:15-70,94-143 + modules/roi_align.py
+# ----------------------------------------------------------------------------------------
+POOL_NONE, POOL_AVG, POOL_MAX = 0, 1, 2
+
+
+def roi_align_grid(feat, rois, ah, aw, scale):
+    """RoIAlignFunction.forward: (R,C,ah,aw) bilinear samples."""
+    feat = _f32(feat)
+    rois = _f32(rois)
+    B, C, H, W = feat.shape
+    R = rois.shape[0]
+    out = np.zeros((R, C, ah, aw), dtype=np.float32)
+    lib().orc_roi_align_fwd(_p(feat, c_f), _p(rois, c_f), B, C, H, W, R, ah, aw, ctypes.c_float(scale), _p(out, c_f))
+    return out
+
+
+def pool2x2(x, is_max):
+    x = _f32(x)
+    R, C, ah, aw = x.shape
+    y = np.empty((R, C, ah - 1, aw - 1), dtype=np.float32)
+    lib().orc_pool2x2(_p(x, c_f), ctypes.c_long(R * C), ah, aw, int(is_max), _p(y, c_f))
+    return y
+
+
+def roi_align(feat, rois, ph, pw, scale, pool_mode=POOL_AVG):
+    """RoIAlign (pool_mode NONE: ph x pw grid), RoIAlignAvg / RoIAlignMax ((ph+1)x(pw+1) grid
+    then 2x2 stride-1 pool) -- modules/roi_align.py:14-16, 26-29, 39-42."""
+    if pool_mode == POOL_NONE:
+        return roi_align_grid(feat, rois, ph, pw, scale)
+    g = roi_align_grid(feat, rois, ph + 1, pw + 1, scale)
+    return pool2x2(g, pool_mode == POOL_MAX)
+
+
+def roi_align_bwd(grad_out, feat, rois, ph, pw, scale, pool_mode=POOL_AVG):
+    """d(features) of roi_align(); returns fp64 (B,C,H,W).  `feat` is needed for MAX only."""
+    grad_out = _f32(grad_out)
+    rois = _f32(rois)
+    feat = _f32(feat)
+    B, C, H, W = feat.shape
+    R = rois.shape[0]
+    if pool_mode == POOL_NONE:
+        ah, aw, gx = ph, pw, grad_out
+    else:
+        ah, aw = ph + 1, pw + 1
+        x = roi_align_grid(feat, rois, ah, aw, scale) if pool_mode == POOL_MAX else None
+        gx = np.empty((R, C, ah, aw), dtype=np.float32)
+        lib().orc_pool2x2_bwd(_p(grad_out, c_f), _p(x, c_f), ctypes.c_long(R * C), ah, aw,
+                              int(pool_mode == POOL_MAX), _p(gx, c_f))
+    gin = np.zeros((B, C, H, W), dtype=np.float64)
+    lib().orc_roi_align_bwd(_p(gx, c_f), _p(rois, c_f), B, C, H, W, R, ah, aw, ctypes.c_float(scale), _p(gin, c_d))
+    return gin
+
+
+# ----------------------------------------------------------------------------------------
+# RoIPool: lib/model/roi_pooling/src/roi_pooling_kernel.cu:24-93,128-203; roi_pooling.c:4-104
+# ----------------------------------------------------------------------------------------
+def roi_pool(feat, rois, ph, pw, scale):
+    feat = _f32(feat)
+    rois = _f32(rois)
+    B, C, H, W = feat.shape
+    R = rois.shape[0]
+    out = np.zeros((R, C, ph, pw), dtype=np.float32)
+    arg = np.zeros((R, C, ph, pw), dtype=np.int32)
+    lib().orc_roi_pool_fwd(_p(feat, c_f), _p(rois, c_f), B, C, H, W, R, ph, pw, ctypes.c_float(scale),
+                           _p(out, c_f), _p(arg, c_i))
+    return out, arg
+
+
+def roi_pool_bwd(grad_out, argmax, feat_shape):
+    grad_out = _f32(grad_out)
+    argmax = np.ascontiguousarray(argmax, dtype=np.int32)
+    gin = np.zeros(feat_shape, dtype=np.float64)
+    lib().orc_roi_pool_bwd(_p(grad_out, c_f), _p(argmax, c_i), ctypes.c_long(grad_out.size),
+                           ctypes.c_long(gin.size), _p(gin, c_d))
+    return gin
+
+
+def roi_pool_cpu_nhwc(feat_nhwc, rois, ph, pw, scale):
+    """roi_pooling.c semantics (the reference's only CPU pooling path): NHWC, batch 1."""
+    feat_nhwc = _f32(feat_nhwc)
+    rois = _f32(rois)
+    B, H, W, C = feat_nhwc.shape
+    R = rois.shape[0]
+    out = np.zeros((R, C, ph, pw), dtype=np.float32)
+    ok = lib().orc_roi_pool_fwd_cpu_nhwc(_p(feat_nhwc, c_f), _p(rois, c_f), B, H, W, C, R, ph, pw,
+                                         ctypes.c_float(scale), _p(out, c_f))
+    return out, int(ok)
+
+
+# ----------------------------------------------------------------------------------------
+# box algebra: lib/model/rpn/bbox_transform.py:77-103,125-133,136-166,168-257
+# ----------------------------------------------------------------------------------------
+def bbox_transform_inv(boxes, deltas):
+    boxes = _f32(boxes)
+    deltas = _f32(deltas)
+    B, N, _ = boxes.shape
+    k = deltas.shape[2] // 4
+    out = np.empty_like(deltas)
+    lib().orc_bbox_transform_inv(_p(boxes, c_f), _p(deltas, c_f), ctypes.c_long(B * N), k, _p(out, c_f))
+    return out
+
+
+def clip_boxes(boxes, im_info):
+    boxes = _f32(boxes).copy()
+    im_info = _f32(im_info)
+    B, N, k4 = boxes.shape
+    lib().orc_clip_boxes(_p(boxes, c_f), _p(im_info, c_f), B, ctypes.c_long(N), k4 // 4)
+    return boxes
+
+
+def bbox_overlaps(anchors, gt):
+    anchors = _f32(anchors)
+    gt = _f32(gt)
+    N, K = anchors.shape[0], gt.shape[0]
+    out = np.empty((N, K), dtype=np.float32)
+    lib().orc_bbox_overlaps(_p(anchors, c_f), _p(gt, c_f), N, K, _p(out, c_f))
+    return out
+
+
+def bbox_overlaps_batch(anchors, gt_boxes):
+    """anchors (N,4) | (B,N,4) | (B,N,5: cols 1:5); gt (B,K,>=4)."""
+    gt = _f32(np.asarray(gt_boxes)[:, :, :4])
+    B, K = gt.shape[:2]
+    a = np.asarray(anchors, dtype=np.float32)
+    if a.ndim == 2:
+        a = np.broadcast_to(a[None, :, :4], (B, a.shape[0], 4))
+    elif a.shape[2] != 4:
+        a = a[:, :, 1:5]
+    a = _f32(a)
+    N = a.shape[1]
+    out = np.empty((B, N, K), dtype=np.float32)
+    lib().orc_bbox_overlaps_batch(_p(a, c_f), _p(gt, c_f), B, N, K, _p(out, c_f))
+    return out
+
+
+# ----------------------------------------------------------------------------------------
+# proposal layer: lib/model/rpn/proposal_layer.py:49-161
+# ----------------------------------------------------------------------------------------
+def proposal_layer(scores, deltas, im_info, anchors, feat_stride, pre_nms_topN, post_nms_topN,
+                   nms_thresh, boxes_override=None, return_taps=False):
+    scores = _f32(scores)
+    deltas = _f32(deltas)
+    im_info = _f32(im_info)
+    anchors = _f32(anchors)
+    B, A2, H, W = scores.shape
+    A = A2 // 2
+    KA = H * W * A
+    pre = pre_nms_topN if 0 < pre_nms_topN < KA else KA
+    out = np.zeros((B, post_nms_topN, 5), dtype=np.float32)
+    order = np.zeros((B, pre), dtype=np.int32)
+    props = np.zeros((B, pre, 4), dtype=np.float32)
+    keep = np.zeros((B, post_nms_topN), dtype=np.int32)
+    nkeep = np.zeros((B,), dtype=np.int32)
+    bo = _f32(boxes_override) if boxes_override is not None else None
+    lib().orc_proposal_layer(_p(scores, c_f), _p(deltas, c_f), _p(im_info, c_f), _p(anchors, c_f),
+                             B, A, H, W, int(feat_stride), int(pre_nms_topN), int(post_nms_topN),
+                             ctypes.c_float(nms_thresh), _p(out, c_f), _p(order, c_i), _p(props, c_f),
+                             _p(keep, c_i), _p(nkeep, c_i), _p(bo, c_f))
+    if return_taps:
+        return out, order, props, keep, nkeep
+    return out
+
+
+# ----------------------------------------------------------------------------------------
+# RL refinement: lib/model/Reinforcement/action.py:6-59, lib/datasets/RL_coco_dataset.py:119-137,
+# lib/pycocotools/maskApi.c:98-109
+# ----------------------------------------------------------------------------------------
+def action_table(delta, alpha=1.0):
+    """Action.__init__ (action.py:11-22): idx = (dim*len(delta)+j)*2 + sign."""
+    num = 4 * len(delta) * 2
+    t = np.zeros((num, 4), dtype=np.float32)
+    idx = 0
+    for i in range(4):
+        for j in range(len(delta)):
+            t[idx, i] = delta[j] * alpha
+            idx += 1
+            t[idx, i] = -delta[j] * alpha
+            idx += 1
+    return t
+
+
+def bbiou(dt, gt, iscrowd=None):
+    """maskApi.c:98-109; returns (m, n) like pycocotools' mask.iou (o is column-major n x m)."""
+    dt = np.ascontiguousarray(dt, dtype=np.float64).reshape(-1, 4)
+    gt = np.ascontiguousarray(gt, dtype=np.float64).reshape(-1, 4)
+    m, n = dt.shape[0], gt.shape[0]
+    cr = np.ascontiguousarray(iscrowd, dtype=np.uint8) if iscrowd is not None else None
+    o = np.zeros((n, m), dtype=np.float64)
+    lib().orc_bbiou(_p(dt, c_d), _p(gt, c_d), ctypes.c_long(m), ctypes.c_long(n), _p(cr, c_u8), _p(o, c_d))
+    return o.T.copy()
+
+
+MODE_COCO, MODE_RCNN = 0, 1
+
+
+def action_reward(boxes, gt, act, crowd=None, ngt=None, mode=MODE_COCO, iou_thres=0.0,
+                  pos_wratio=1.0, neg_wratio=1.0):
+    boxes = _f32(boxes)
+    gt = _f32(gt)
+    act = _f32(act)
+    B, N, _ = boxes.shape
+    G = gt.shape[1]
+    A = act.shape[0]
+    cr = np.ascontiguousarray(crowd, dtype=np.uint8) if crowd is not None else None
+    ng = np.ascontiguousarray(ngt, dtype=np.int32) if ngt is not None else None
+    reward = np.empty((B, N, A), dtype=np.float32)
+    label = np.empty((B, N, A), dtype=np.float32)
+    weight = np.empty((B, N, A), dtype=np.float32)
+    lib().orc_action_reward(_p(boxes, c_f), _p(gt, c_f), _p(cr, c_u8), _p(ng, c_i), _p(act, c_f), B, N, A, G,
+                            int(mode), ctypes.c_float(iou_thres), ctypes.c_float(pos_wratio),
+                            ctypes.c_float(neg_wratio), _p(reward, c_f), _p(label, c_f), _p(weight, c_f))
+    return reward, label, weight
+
+
+def move_from_act(bboxes, preds, targets, act, maxk):
+    """Action.move_from_act (action.py:25-59) with the documented tie rule: descending by
+    pred, ties -> lower flat index first (numpy's quicksort tie order is unpinned)."""
+    bboxes = np.array(bboxes, dtype=np.float32, copy=True)
+    b, n, _ = bboxes.shape
+    A = act.shape[0]
+    correct = 0
+    for bid in range(b):
+        flat = preds[bid].reshape(-1)
+        inds = np.argsort(-flat.astype(np.float64), kind="stable")
+        cnt = 0
+        vis = np.zeros(n, dtype=bool)
+        for num in inds:
+            idx, act_id = num // A, num % A
+            if not vis[idx]:
+                cnt += 1
+                vis[idx] = True
+                if targets[bid, idx, act_id] == 1:
+                    correct += 1
+                    x, y, w, h = bboxes[bid, idx]
+                    bboxes[bid, idx] += act[act_id] * np.array([w, h, w, h], dtype=np.float32)
+            if cnt >= maxk:
+                break
+    return bboxes, correct * 100.0 / (b * maxk)
+
+
+# ----------------------------------------------------------------------------------------
+# the compiled reference itself (oracle/_ref, built from /root/reference in place)
+# ----------------------------------------------------------------------------------------
+def ref_maskapi():
+    path = os.path.join(_HERE, "_ref", "libmaskapi.so")
+    return ctypes.CDLL(path) if os.path.exists(path) else None
+
+
+def ref_bbiou(dt, gt, iscrowd=None):
+    """The reference's own bbIou (maskApi.c compiled unchanged)."""
+    l = ref_maskapi()
+    dt = np.ascontiguousarray(dt, dtype=np.float64).reshape(-1, 4)
+    gt = np.ascontiguousarray(gt, dtype=np.float64).reshape(-1, 4)
+    m, n = dt.shape[0], gt.shape[0]
+    cr = np.ascontiguousarray(iscrowd, dtype=np.uint8) if iscrowd is not None else None
+    o = np.zeros((n, m), dtype=np.float64)
+    l.bbIou(_p(dt, c_d), _p(gt, c_d), ctypes.c_size_t(m), ctypes.c_size_t(n), _p(cr, c_u8), _p(o, c_d))
+    return o.T.copy()
+
+
+def ref_legacy():
+    """The reference's legacy CUDA kernels compiled unchanged for sm_100a (GPU box only)."""
+    path = os.path.join(_HERE, "_ref", "libref_legacy.so")
+    return ctypes.CDLL(path) if os.path.exists(path) else None

@@ -1,0 +1,84 @@
+"""CPU: the oracle (oracle/) against the golden vectors produced by executing the reference's own
+Python and its vendored maskApi.c (tests/golden/make_golden.py).  This is what pins the oracle."""
+import numpy as np
+import pytest
+
+
+def test_anchor_known_answer(orc, golden):
+    # the actual output of generate_anchors (0-based; the MATLAB comment at
+    # generate_anchors.py:12-37 is the 1-based version), SURVEY.md section 4
+    kat = np.array([[-84, -40, 99, 55], [-176, -88, 191, 103], [-360, -184, 375, 199],
+                    [-56, -56, 71, 71], [-120, -120, 135, 135], [-248, -248, 263, 263],
+                    [-36, -80, 51, 95], [-80, -168, 95, 183], [-168, -344, 183, 359]], dtype=np.float64)
+    a9 = orc.generate_anchors(16, (0.5, 1, 2), (8, 16, 32))
+    assert np.array_equal(a9, kat)
+    assert np.array_equal(a9, golden["anchors9"])
+    assert np.array_equal(orc.generate_anchors(16, (0.5, 1, 2), (4, 8, 16, 32)), golden["anchors12"])
+
+
+def test_decode_clip(orc, golden):
+    dec = orc.bbox_transform_inv(golden["dec_boxes"], golden["dec_deltas"])
+    ref = golden["dec_out"]
+    fin = np.isfinite(ref)
+    assert np.array_equal(np.isfinite(dec), fin)
+    # torch's vectorised expf (sleef) and glibc expf may differ by an ulp
+    np.testing.assert_allclose(dec[fin], ref[fin], rtol=3e-6, atol=1e-4)
+    clp = orc.clip_boxes(golden["dec_out"], golden["clip_im_info"])
+    assert np.array_equal(clp, golden["clip_out"])  # clamp is exact, inf -> border
+
+
+def test_overlaps(orc, golden):
+    o = orc.bbox_overlaps(golden["ovl_anchors"], golden["ovl_gt"])
+    np.testing.assert_array_equal(o, golden["ovl_out"])
+    o3 = orc.bbox_overlaps_batch(golden["ovlb_anchors"], golden["ovlb_gt"])
+    np.testing.assert_array_equal(o3, golden["ovlb_out3"])
+    assert (o3[0, 5] == -1).all() and (o3[:, :, 4:] [o3[:, :, 4:] != -1] == 0).all()
+    o2 = orc.bbox_overlaps_batch(golden["ovlb_anchors"][0], golden["ovlb_gt"])
+    np.testing.assert_array_equal(o2, golden["ovlb_out2"])
+
+
+@pytest.mark.parametrize("tag", ["test", "train", "all"])
+def test_proposal_layer(orc, golden, tag):
+    stride, pre, post, A = [int(v) for v in golden[f"prop_{tag}_cfg"]]
+    rois = orc.proposal_layer(golden[f"prop_{tag}_scores"], golden[f"prop_{tag}_deltas"],
+                              golden[f"prop_{tag}_im_info"], golden[f"prop_{tag}_anchors"],
+                              stride, pre, post, 0.7)
+    ref = golden[f"prop_{tag}_rois"]
+    assert rois.shape == ref.shape
+    # identical keep sets and order; coordinates up to the expf ulp
+    assert np.array_equal(rois[:, :, 0], ref[:, :, 0])
+    assert np.array_equal(rois[:, :, 1:].any(axis=2), ref[:, :, 1:].any(axis=2))
+    np.testing.assert_allclose(rois, ref, rtol=3e-6, atol=2e-4)
+
+
+def test_action_table_and_move(orc, golden):
+    assert np.array_equal(orc.action_table([0.5, 0.25]), golden["act16"])
+    assert np.array_equal(orc.action_table([.5, .25, .125, .0625, .03125, .015625, .008]), golden["act56"])
+    for k in (1, 5):
+        moved, prec = orc.move_from_act(golden["move_in_boxes"], golden["move_preds"],
+                                        golden["move_targets"], golden["act16"], k)
+        np.testing.assert_array_equal(moved, golden[f"move_k{k}_boxes"])
+        assert prec == float(golden[f"move_k{k}_prec"])
+
+
+def test_bbiou_and_reward(orc, golden):
+    o = orc.bbiou(golden["iou_dt"], golden["iou_gt"], golden["iou_crowd"])
+    np.testing.assert_array_equal(o, golden["iou_out"])  # bit-exact fp64 vs maskApi.c
+    assert abs(orc.bbiou([[10, 10, 20, 20]], [[12, 12, 20, 20]], [0])[0, 0] - 324.0 / 476.0) < 1e-15
+    assert orc.bbiou([[0, 0, 5, 5]], [[0, 0, 10, 10]], [1])[0, 0] == 1.0  # crowd: union = dt area
+    r, l, w = orc.action_reward(golden["iou_dt"][None], golden["iou_gt"][None], golden["act16"],
+                                crowd=golden["iou_crowd"][None], mode=orc.MODE_COCO, iou_thres=0.0,
+                                pos_wratio=2.0, neg_wratio=0.5)
+    np.testing.assert_array_equal(r[0], golden["reward_out"].astype(np.float32))
+    np.testing.assert_array_equal(l[0], golden["reward_label"].astype(np.float32))
+    np.testing.assert_allclose(w[0], golden["reward_weight"], rtol=1e-6)
+
+
+def test_ref_maskapi_when_present(orc, golden):
+    if orc.ref_maskapi() is None:
+        pytest.skip("oracle/_ref/libmaskapi.so not built (needs /root/reference)")
+    rng = np.random.default_rng(0)
+    dt = np.concatenate([rng.random((200, 2)) * 300, rng.random((200, 2)) * 100], 1)
+    gt = np.concatenate([rng.random((50, 2)) * 300, rng.random((50, 2)) * 100], 1)
+    cr = (rng.random(50) < 0.2).astype(np.uint8)
+    np.testing.assert_array_equal(orc.bbiou(dt, gt, cr), orc.ref_bbiou(dt, gt, cr))
