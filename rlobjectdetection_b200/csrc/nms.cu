@@ -1,0 +1,343 @@
+// Bitmask NMS for sm_100a, fully on device.
+//
+// Arithmetic is bit-identical to the reference's devIoU + strict '>' + greedy scan
+// (lib/model/nms/src/nms_cuda_kernel.cu:31-39, 77-81, 123-144) as nvcc 12.9 compiles it for
+// sm_100a: Sa = w_a*h_a (FMUL), S = fma(w_b, h_b, Sa), inter = w*h (FMUL),
+// iou = inter / (S - inter) (IEEE division), bit = iou > thresh.
+//
+// What differs is everything around it:
+//   - k_nms_mask computes only the upper-triangular 64x64 tiles, for all segments (images /
+//     (image,class) pairs) in one launch, and stores the mask column-block-major
+//     ([col_block][row]) so both the tile write (512 B) and the scan's reads are coalesced.
+//     A division-free interval test decides all but the razor-edge pairs; those fall through
+//     to the exact IEEE division, so the bits never differ from the reference's.
+//   - k_nms_scan resolves the serial greedy dependency ON THE DEVICE, one CTA per segment:
+//     per 64-box block one thread walks the diagonal tile, then 8 warps OR the kept rows
+//     into the running removed-bitmap with warp-wide OR reductions.  It stops as soon as
+//     max_keep boxes are kept (the proposal layer only uses the first post_nms_topN) and
+//     can emit the padded (B, post, 5) roi tensor directly.
+//   - k_nms_small handles short segments (<= 512 boxes, e.g. per-class test-time NMS) in
+//     one CTA each with the mask in shared memory: one launch for thousands of segments.
+// No cudaMalloc, no mask D2H (18 MB per call at n=12000 in the reference), no host loop,
+// no default-stream sync.
+#include "nms_device.cuh"
+
+namespace rlod {
+
+// ----------------------------------------------------------------------------------------
+// tile kernel: grid = (n_tiles_upper_triangular(max_blk), nseg), block = 64 threads.
+// thread t owns row rb*64+t and tests it against the 64 boxes of column block cb.
+// ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64)
+    k_nms_mask(NmsSegs segs, float thresh, int max_blk, unsigned long long *__restrict__ mask,
+               size_t mask_seg_stride) {
+  const int seg = blockIdx.y;
+  int off, n;
+  segs.get(seg, off, n);
+  const int nblk = (n + 63) >> 6;
+  // decode the upper-triangular tile index -> (rb, cb), cb >= rb, over max_blk blocks
+  int rb, cb;
+  tri_decode(blockIdx.x, max_blk, rb, cb);
+  if (cb >= nblk) return;  // also covers rb >= nblk
+  const int npad = nblk << 6;
+  __shared__ float4 cbox[64];
+  __shared__ float2 cwh[64];
+  const int t = threadIdx.x;
+  {
+    const int j = cb * 64 + t;
+    float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j < n) bx = segs.load_box(off + j);
+    cbox[t] = bx;
+    cwh[t] = make_float2(__fadd_rn(__fsub_rn(bx.z, bx.x), 1.f), __fadd_rn(__fsub_rn(bx.w, bx.y), 1.f));
+  }
+  __syncthreads();
+  const int i = rb * 64 + t;
+  unsigned long long bits = 0ull;
+  if (i < n) {
+    const float4 a = segs.load_box(off + i);
+    const float Sa = __fmul_rn(__fadd_rn(__fsub_rn(a.z, a.x), 1.f), __fadd_rn(__fsub_rn(a.w, a.y), 1.f));
+    const int jn = min(64, n - cb * 64);
+    const int j0 = (rb == cb) ? t + 1 : 0;
+    const bool fast = thresh >= 0.f && thresh < 1e30f;
+    for (int j = j0; j < jn; ++j)
+      if (iou_gt(a, Sa, cbox[j], cwh[j], thresh, fast)) bits |= 1ull << j;
+  }
+  mask[(size_t)seg * mask_seg_stride + (size_t)cb * npad + i] = bits;
+}
+
+// ----------------------------------------------------------------------------------------
+// scan kernel: one CTA (256 threads) per segment.
+// ----------------------------------------------------------------------------------------
+constexpr int kScanThreads = 256;
+
+__global__ void __launch_bounds__(kScanThreads)
+    k_nms_scan(NmsSegs segs, int max_keep, const unsigned long long *__restrict__ mask,
+               size_t mask_seg_stride, NmsOut o) {
+  extern __shared__ unsigned long long remv[];  // [nblk]
+  __shared__ unsigned long long diag[64];
+  __shared__ unsigned long long s_kept;
+  __shared__ int s_base, s_total;
+  const int seg = blockIdx.x;
+  int off, n;
+  segs.get(seg, off, n);
+  const int nblk = (n + 63) >> 6, npad = nblk << 6;
+  const unsigned long long *m = mask + (size_t)seg * mask_seg_stride;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  for (int w = t; w < nblk; w += kScanThreads) remv[w] = 0ull;
+  if (t == 0) s_total = 0;
+  __syncthreads();
+  for (int k = 0; k < nblk; ++k) {
+    if (t < 64) diag[t] = m[(size_t)k * npad + k * 64 + t];
+    __syncthreads();
+    if (t == 0) {
+      unsigned long long r = remv[k];
+      const int valid = min(64, n - k * 64);
+      if (valid < 64) r |= ~0ull << valid;
+      unsigned long long kb = 0ull;
+#pragma unroll 8
+      for (int i = 0; i < 64; ++i) {
+        if (!((r >> i) & 1ull)) {
+          kb |= 1ull << i;
+          r |= diag[i];
+        }
+      }
+      int total = s_total;
+      int cnt = __popcll(kb);
+      if (max_keep > 0 && total + cnt > max_keep) {
+        // keep only the first (max_keep - total) set bits
+        int need = max_keep - total;
+        unsigned long long trimmed = 0ull, rest = kb;
+        while (need-- > 0) {
+          const unsigned long long low = rest & (~rest + 1ull);
+          trimmed |= low;
+          rest ^= low;
+        }
+        kb = trimmed;
+        cnt = __popcll(kb);
+      }
+      s_kept = kb;
+      s_base = total;
+      s_total = total + cnt;
+    }
+    __syncthreads();
+    const unsigned long long kb = s_kept;
+    const int base = s_base, total = s_total;
+    if (t < 64 && ((kb >> t) & 1ull)) {
+      const int rank = base + __popcll(kb & ((1ull << t) - 1ull));
+      o.emit(seg, off, rank, k * 64 + t, segs);
+    }
+    if (max_keep > 0 && total >= max_keep) break;  // CTA-uniform
+    // OR the kept rows of this block into the removed-bitmap of all later blocks
+    const bool k0 = (kb >> lane) & 1ull, k1 = (kb >> (lane + 32)) & 1ull;
+    for (int w = k + 1 + warp; w < nblk; w += kScanThreads / 32) {
+      const unsigned long long *row = m + (size_t)w * npad + k * 64;
+      unsigned long long v = 0ull;
+      if (k0) v = row[lane];
+      if (k1) v |= row[lane + 32];
+      unsigned lo = (unsigned)v, hi = (unsigned)(v >> 32);
+      lo = __reduce_or_sync(0xffffffffu, lo);
+      hi = __reduce_or_sync(0xffffffffu, hi);
+      if (lane == 0) remv[w] |= ((unsigned long long)hi << 32) | lo;
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  o.finish(seg, off, n, s_total, t, kScanThreads);
+}
+
+// ----------------------------------------------------------------------------------------
+// small segments: one CTA (128 threads) per segment, mask in shared memory.
+// smem: float4 box[npad]; float2 wh[npad]; u64 mask[nblk][npad + 1]
+// ----------------------------------------------------------------------------------------
+constexpr int kSmallThreads = 128;
+constexpr int kSmallMaxN = 512;
+
+__global__ void __launch_bounds__(kSmallThreads)
+    k_nms_small(NmsSegs segs, float thresh, int max_keep, int max_pad, NmsOut o) {
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  const int seg = blockIdx.x;
+  int off, n;
+  segs.get(seg, off, n);
+  const int nblk = (n + 63) >> 6, npad = nblk << 6;
+  float4 *box = reinterpret_cast<float4 *>(sm_raw);
+  float2 *wh = reinterpret_cast<float2 *>(box + max_pad);
+  unsigned long long *mk = reinterpret_cast<unsigned long long *>(wh + max_pad);
+  const int mstride = npad + 1;
+  __shared__ int s_total;
+  const int t = threadIdx.x;
+  for (int i = t; i < npad; i += kSmallThreads) {
+    float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < n) bx = segs.load_box(off + i);
+    box[i] = bx;
+    wh[i] = make_float2(__fadd_rn(__fsub_rn(bx.z, bx.x), 1.f), __fadd_rn(__fsub_rn(bx.w, bx.y), 1.f));
+  }
+  if (t == 0) s_total = 0;
+  __syncthreads();
+  const bool fast = thresh >= 0.f && thresh < 1e30f;
+  // items = (cb, row) with cb >= row/64
+  for (int it = t; it < nblk * npad; it += kSmallThreads) {
+    const int cb = it / npad, i = it - cb * npad;
+    const int rb = i >> 6;
+    if (cb < rb) continue;
+    unsigned long long bits = 0ull;
+    if (i < n) {
+      const float4 a = box[i];
+      const float Sa = __fmul_rn(wh[i].x, wh[i].y);
+      const int jn = min(64, n - cb * 64);
+      const int j0 = (rb == cb) ? (i & 63) + 1 : 0;
+      for (int j = j0; j < jn; ++j)
+        if (iou_gt(a, Sa, box[cb * 64 + j], wh[cb * 64 + j], thresh, fast)) bits |= 1ull << j;
+    }
+    mk[(size_t)cb * mstride + i] = bits;
+  }
+  __syncthreads();
+  if (t < 32) {
+    // warp 0: lane w owns the removed-bitmap word of column block w (nblk <= 8)
+    const int lane = t;
+    unsigned long long rem = 0ull;
+    int total = 0;
+    for (int k = 0; k < nblk; ++k) {
+      unsigned long long r = __shfl_sync(0xffffffffu, rem, k);
+      const int valid = min(64, n - k * 64);
+      if (valid < 64) r |= ~0ull << valid;
+      unsigned long long kb = 0ull;
+      const unsigned long long *dg = mk + (size_t)k * mstride + k * 64;
+      for (int i = 0; i < valid; ++i) {
+        if (!((r >> i) & 1ull)) {
+          kb |= 1ull << i;
+          r |= dg[i];  // broadcast read, every lane runs the same chain
+        }
+      }
+      int cnt = __popcll(kb);
+      if (max_keep > 0 && total + cnt > max_keep) {
+        int need = max_keep - total;
+        unsigned long long trimmed = 0ull, rest = kb;
+        while (need-- > 0) {
+          const unsigned long long low = rest & (~rest + 1ull);
+          trimmed |= low;
+          rest ^= low;
+        }
+        kb = trimmed;
+        cnt = __popcll(kb);
+      }
+      for (int q = lane; q < 64; q += 32)
+        if ((kb >> q) & 1ull)
+          o.emit(seg, off, total + __popcll(kb & ((1ull << q) - 1ull)), k * 64 + q, segs);
+      total += cnt;
+      if (max_keep > 0 && total >= max_keep) break;
+      if (lane > k && lane < nblk) {
+        const unsigned long long *row = mk + (size_t)lane * mstride + k * 64;
+        unsigned long long kk = kb;
+        while (kk) {
+          const int i = __ffsll((long long)kk) - 1;
+          kk &= kk - 1ull;
+          rem |= row[i];
+        }
+      }
+    }
+    if (lane == 0) s_total = total;
+  }
+  __syncthreads();
+  o.finish(seg, off, n, s_total, t, kSmallThreads);
+}
+
+static size_t small_smem(int max_pad) {
+  const int nblk = max_pad / 64;
+  return (size_t)max_pad * (sizeof(float4) + sizeof(float2)) +
+         (size_t)nblk * (max_pad + 1) * sizeof(unsigned long long);
+}
+
+size_t nms_mask_bytes(int nseg, int max_seg) {
+  if (nseg <= 0 || max_seg <= 0) return 0;
+  const size_t nblk = (size_t)(max_seg + 63) / 64;
+  return (size_t)nseg * nblk * nblk * 64 * sizeof(unsigned long long);
+}
+
+int nms_launch(const NmsSegs &segs, int nseg, int max_seg, float thresh, int max_keep,
+               const NmsOut &out, void *workspace, size_t workspace_bytes, cudaStream_t st,
+               int force_large) {
+  if (nseg <= 0) return RLOD_OK;
+  if (max_seg <= 0) {
+    // every segment is empty: counts = 0
+    RLOD_LAUNCH(RLOD_KERNEL_NMS_SMALL, st, k_nms_small<<<nseg, kSmallThreads, small_smem(64), st>>>(segs, thresh, max_keep, 64, out));
+    return launch_status();
+  }
+  if (max_seg <= kSmallMaxN && !force_large) {
+    const int max_pad = (max_seg + 63) / 64 * 64;
+    const size_t smem = small_smem(max_pad);
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(k_nms_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    RLOD_LAUNCH(RLOD_KERNEL_NMS_SMALL, st, k_nms_small<<<nseg, kSmallThreads, smem, st>>>(segs, thresh, max_keep, max_pad, out));
+    return launch_status();
+  }
+  const int max_blk = (max_seg + 63) / 64;
+  const size_t seg_stride = (size_t)max_blk * max_blk * 64;
+  const size_t need = (size_t)nseg * seg_stride * sizeof(unsigned long long);
+  if (!workspace || workspace_bytes < need) return RLOD_ENOSPC;
+  if (nseg > 65535) return RLOD_EUNSUPPORTED;
+  unsigned long long *mask = (unsigned long long *)workspace;
+  const unsigned tiles = (unsigned)((long long)max_blk * (max_blk + 1) / 2);
+  RLOD_LAUNCH(RLOD_KERNEL_NMS_MASK, st, k_nms_mask<<<dim3(tiles, nseg), 64, 0, st>>>(segs, thresh, max_blk, mask, seg_stride));
+  RLOD_LAUNCH(RLOD_KERNEL_NMS_SCAN, st, k_nms_scan<<<nseg, kScanThreads, (size_t)max_blk * sizeof(unsigned long long), st>>>(
+      segs, max_keep, mask, seg_stride, out));
+  return launch_status();
+}
+
+}  // namespace rlod
+
+using namespace rlod;
+
+static int g_force_large = 0;
+
+RLOD_API int rlod_debug_nms_force_large(int on) {
+  const int prev = g_force_large;
+  g_force_large = on;
+  return prev;
+}
+
+RLOD_API size_t rlod_nms_workspace_bytes(int nseg, int max_seg) {
+  if (nseg <= 0 || max_seg <= 0) return 0;
+  if (max_seg <= kSmallMaxN && !g_force_large) return 0;  // mask lives in shared memory
+  const size_t nblk = (size_t)(max_seg + 63) / 64;
+  return (size_t)nseg * nblk * nblk * 64 * sizeof(unsigned long long);
+}
+
+RLOD_API int rlod_nms(const float *dets, int n, int stride, float thresh, int max_keep, int *keep,
+                      int *num_out, void *workspace, size_t workspace_bytes,
+                      rlod_stream_t stream) {
+  if (n < 0 || stride < 4 || !num_out) return RLOD_EINVAL;
+  if (n > 0 && (!dets || !keep)) return RLOD_EINVAL;
+  NmsSegs segs;
+  segs.dets = dets;
+  segs.stride = stride;
+  segs.vec4 = (stride == 4 && ((uintptr_t)dets % 16) == 0) ? 1 : 0;
+  segs.seg_offsets = nullptr;
+  segs.uniform_n = n;
+  segs.max_n = n;
+  NmsOut o = {};
+  o.keep = keep;
+  o.num_out = num_out;
+  return nms_launch(segs, 1, n, thresh, max_keep, o, workspace, workspace_bytes,
+                    (cudaStream_t)stream, g_force_large);
+}
+
+RLOD_API int rlod_nms_batched(const float *dets, int stride, const int *seg_offsets, int nseg,
+                              int max_seg, float thresh, int max_keep, int *keep, int *num_out,
+                              void *workspace, size_t workspace_bytes, rlod_stream_t stream) {
+  if (nseg < 0 || stride < 4 || max_seg < 0) return RLOD_EINVAL;
+  if (nseg == 0) return RLOD_OK;
+  if (!seg_offsets || !num_out) return RLOD_EINVAL;
+  if (max_seg > 0 && (!dets || !keep)) return RLOD_EINVAL;
+  NmsSegs segs;
+  segs.dets = dets;
+  segs.stride = stride;
+  segs.vec4 = (stride == 4 && ((uintptr_t)dets % 16) == 0) ? 1 : 0;
+  segs.seg_offsets = seg_offsets;
+  segs.uniform_n = 0;
+  segs.max_n = max_seg;
+  NmsOut o = {};
+  o.keep = keep;
+  o.num_out = num_out;
+  return nms_launch(segs, nseg, max_seg, thresh, max_keep, o, workspace, workspace_bytes,
+                    (cudaStream_t)stream, g_force_large);
+}

@@ -1,0 +1,277 @@
+// RPN proposal layer for sm_100a: _ProposalLayer.forward (lib/model/rpn/proposal_layer.py:
+// 49-161) as three launches for the whole batch and zero host synchronisation.
+//
+//   k_proposal_sort_decode  one CTA (1024 threads) per image:
+//       1. radix-select the pre_nms_topN best anchors on a 64-bit composite key
+//          (descending-orderable score bits << 32 | anchor index) straight from the NCHW
+//          score map -- the reference's two permute().contiguous() copies
+//          (proposal_layer.py:98,102) and its full sort of all H*W*A scores (:125) vanish;
+//       2. compact the selected keys into shared memory and bitonic-sort them there (all
+//          composite keys are distinct, so the order is exactly "score descending, ties by
+//          lower anchor index" = a stable descending sort);
+//       3. decode (bbox_transform_inv, bbox_transform.py:77-103) + clip (clip_boxes,
+//          :125-133) only the selected anchors, anchors generated arithmetically from the
+//          (A,4) base table (:80-93), deltas gathered from channel 4a+k; every fp32 op rounds
+//          separately like the eager torch expression it replaces.
+//   k_nms_mask + k_nms_scan (nms.cu): batched NMS; the scan stops at post_nms_topN keeps
+//       and writes the zero-padded (B, post_nms_topN, 5) output itself (:151-159).
+#include "nms_device.cuh"
+
+namespace rlod {
+
+constexpr int kSortThreads = 1024;
+constexpr int kSortMax = 16384;  // composite keys held in shared memory (128 KB)
+
+// float -> uint32 whose ASCENDING order is the float's DESCENDING order (NaN first, like
+// torch.sort(descending=True); -0 == +0)
+__device__ __forceinline__ uint32_t desc_key(float f) {
+  uint32_t u = __float_as_uint(f);
+  if (f == 0.f) u = 0u;
+  const uint32_t asc = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  return ~asc;
+}
+
+struct PropArgs {
+  const float *scores, *deltas, *im_info, *anchors;
+  int B, A, H, W, feat_stride, pre;  // pre = min(pre_nms_topN, H*W*A), > 0
+  float4 *props;                     // (B, pre) decoded + clipped, sorted
+  int *order_out;                    // (B, pre) or NULL
+  float *props_out;                  // (B, pre, 4) or NULL
+};
+
+__global__ void __launch_bounds__(kSortThreads) k_proposal_sort_decode(PropArgs a, int mp) {
+  extern __shared__ __align__(16) unsigned long long keys[];  // [mp], mp = pow2 >= pre
+  __shared__ unsigned int hist[256];
+  __shared__ unsigned int wsum[8];
+  __shared__ unsigned long long s_prefix;
+  __shared__ unsigned int s_remaining, s_done, s_count;
+  const int b = blockIdx.x, t = threadIdx.x, lane = t & 31;
+  const int HW = a.H * a.W, KA = HW * a.A, M = a.pre;
+  const float *fg = a.scores + ((size_t)b * 2 * a.A + a.A) * HW;
+
+  // memory index e = a*HW + pix  <->  anchor index idx = pix*A + a  (proposal_layer.py:92-103)
+  auto composite = [&](int e) -> unsigned long long {
+    const int an = e / HW, pix = e - an * HW;
+    return ((unsigned long long)desc_key(__ldg(fg + e)) << 32) | (unsigned)(pix * a.A + an);
+  };
+
+  unsigned long long T = ~0ull;  // threshold: select composite <= T
+  if (M < KA) {
+    if (t == 0) {
+      s_prefix = 0ull;
+      s_remaining = (unsigned)M;
+      s_done = 0u;
+    }
+    for (int pass = 0; pass < 8; ++pass) {
+      const int shift = 56 - 8 * pass;
+      if (t < 256) hist[t] = 0u;
+      __syncthreads();
+      if (s_done) break;  // CTA-uniform (written before the previous barrier)
+      const unsigned long long prefix = s_prefix;
+      const unsigned rem = s_remaining;
+      for (int e0 = 0; e0 < KA; e0 += kSortThreads) {
+        const int e = e0 + t;
+        int digit = -1 - lane;  // unique sentinel: never matches another lane
+        if (e < KA) {
+          const unsigned long long c = composite(e);
+          if (pass == 0 || (c >> (shift + 8)) == (prefix >> (shift + 8))) digit = (int)((c >> shift) & 255ull);
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, digit);
+        if (digit >= 0 && lane == __ffs(peers) - 1) atomicAdd(&hist[digit], (unsigned)__popc(peers));
+      }
+      __syncthreads();
+      // 256 threads: inclusive scan of the histogram, find the digit holding the M-th key
+      unsigned cnt = 0, inc = 0;
+      if (t < 256) {
+        cnt = hist[t];
+        inc = cnt;
+        for (int d = 1; d < 32; d <<= 1) {
+          const unsigned v = __shfl_up_sync(0xffffffffu, inc, d);
+          if (lane >= d) inc += v;
+        }
+        if (lane == 31) wsum[t >> 5] = inc;
+      }
+      __syncthreads();
+      if (t < 256) {
+        unsigned basev = 0;
+        for (int w = 0; w < (t >> 5); ++w) basev += wsum[w];
+        inc += basev;
+        const unsigned excl = inc - cnt;
+        if (excl < rem && rem <= inc) {
+          // exactly one thread gets here
+          const unsigned long long np = prefix | ((unsigned long long)t << shift);
+          if (inc == rem || shift == 0) {
+            // the whole bin is taken: everything with this prefix qualifies
+            s_prefix = np | ((shift == 0) ? 0ull : ((1ull << shift) - 1ull));
+            s_done = 1u;
+          } else {
+            s_prefix = np;
+          }
+          s_remaining = rem - excl;
+        }
+      }
+      __syncthreads();
+    }
+    __syncthreads();
+    T = s_prefix;
+  }
+
+  // compaction (unordered; the sort below orders the distinct composite keys)
+  if (t == 0) s_count = 0u;
+  for (int i = t; i < mp; i += kSortThreads) keys[i] = ~0ull;
+  __syncthreads();
+  for (int e0 = 0; e0 < KA; e0 += kSortThreads) {
+    const int e = e0 + t;
+    bool take = false;
+    unsigned long long c = 0ull;
+    if (e < KA) {
+      c = composite(e);
+      take = c <= T;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, take);
+    unsigned wbase = 0;
+    if (lane == 0 && bal) wbase = atomicAdd(&s_count, (unsigned)__popc(bal));
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+    if (take) {
+      const unsigned pos = wbase + __popc(bal & ((1u << lane) - 1u));
+      if (pos < (unsigned)mp) keys[pos] = c;
+    }
+  }
+  __syncthreads();
+
+  // bitonic sort, ascending, mp a power of two
+  for (int k = 2; k <= mp; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int p = t; p < (mp >> 1); p += kSortThreads) {
+        const int i = ((p / j) * (j << 1)) + (p % j);
+        const int l = i + j;
+        const unsigned long long x = keys[i], y = keys[l];
+        const bool up = (i & k) == 0;
+        if ((x > y) == up) {
+          keys[i] = y;
+          keys[l] = x;
+        }
+      }
+      __syncthreads();
+    }
+  }
+
+  // decode + clip the selected anchors in sorted order
+  const float imh = a.im_info[b * 3 + 0], imw = a.im_info[b * 3 + 1];
+  const float xmax = __fsub_rn(imw, 1.f), ymax = __fsub_rn(imh, 1.f);
+  const float *dl = a.deltas + (size_t)b * 4 * a.A * HW;
+  for (int i = t; i < M; i += kSortThreads) {
+    const int idx = (int)(unsigned)(keys[i] & 0xffffffffull);
+    const int an = idx % a.A, pix = idx / a.A;
+    const int y = pix / a.W, x = pix - y * a.W;
+    const float sx = (float)(x * a.feat_stride), sy = (float)(y * a.feat_stride);
+    const float4 base = __ldg(reinterpret_cast<const float4 *>(a.anchors) + an);
+    const float bx1 = __fadd_rn(base.x, sx), by1 = __fadd_rn(base.y, sy);
+    const float bx2 = __fadd_rn(base.z, sx), by2 = __fadd_rn(base.w, sy);
+    const float d0 = __ldg(dl + (size_t)(4 * an + 0) * HW + pix);
+    const float d1 = __ldg(dl + (size_t)(4 * an + 1) * HW + pix);
+    const float d2 = __ldg(dl + (size_t)(4 * an + 2) * HW + pix);
+    const float d3 = __ldg(dl + (size_t)(4 * an + 3) * HW + pix);
+    const float w = __fadd_rn(__fsub_rn(bx2, bx1), 1.0f), h = __fadd_rn(__fsub_rn(by2, by1), 1.0f);
+    const float cx = __fadd_rn(bx1, __fmul_rn(0.5f, w)), cy = __fadd_rn(by1, __fmul_rn(0.5f, h));
+    const float pcx = __fadd_rn(__fmul_rn(d0, w), cx), pcy = __fadd_rn(__fmul_rn(d1, h), cy);
+    const float pw = __fmul_rn(expf(d2), w), ph = __fmul_rn(expf(d3), h);
+    float4 o;
+    o.x = __fsub_rn(pcx, __fmul_rn(0.5f, pw));
+    o.y = __fsub_rn(pcy, __fmul_rn(0.5f, ph));
+    o.z = __fadd_rn(pcx, __fmul_rn(0.5f, pw));
+    o.w = __fadd_rn(pcy, __fmul_rn(0.5f, ph));
+    // clamp_(0, max): min(max(v, 0), max); NaN propagates like torch
+    o.x = (o.x != o.x) ? o.x : fminf(fmaxf(o.x, 0.f), xmax);
+    o.y = (o.y != o.y) ? o.y : fminf(fmaxf(o.y, 0.f), ymax);
+    o.z = (o.z != o.z) ? o.z : fminf(fmaxf(o.z, 0.f), xmax);
+    o.w = (o.w != o.w) ? o.w : fminf(fmaxf(o.w, 0.f), ymax);
+    a.props[(size_t)b * M + i] = o;
+    if (a.order_out) a.order_out[(size_t)b * M + i] = idx;
+    if (a.props_out) reinterpret_cast<float4 *>(a.props_out)[(size_t)b * M + i] = o;
+  }
+}
+
+struct PropWs {
+  float4 *props;
+  void *mask;
+  size_t mask_bytes, bytes;
+};
+
+static PropWs carve_prop_ws(void *base, int B, int pre) {
+  PropWs w;
+  char *p = (char *)base;
+  size_t off = 0;
+  w.props = (float4 *)(p ? p + off : nullptr);
+  off += align_up((size_t)B * pre * sizeof(float4), 256);
+  w.mask = p ? p + off : nullptr;
+  w.mask_bytes = nms_mask_bytes(B, pre);
+  off += align_up(w.mask_bytes, 256);
+  w.bytes = off;
+  return w;
+}
+
+static int eff_pre(int A, int H, int W, int pre_nms_topN) {
+  const long long KA = (long long)A * H * W;
+  if (pre_nms_topN > 0 && pre_nms_topN < KA) return pre_nms_topN;
+  return (int)(KA < (1LL << 30) ? KA : (1LL << 30));
+}
+
+}  // namespace rlod
+
+using namespace rlod;
+
+RLOD_API size_t rlod_proposal_workspace_bytes(int B, int A, int H, int W, int pre_nms_topN,
+                                              int post_nms_topN) {
+  (void)post_nms_topN;
+  if (B <= 0 || A <= 0 || H <= 0 || W <= 0) return 0;
+  return carve_prop_ws(nullptr, B, eff_pre(A, H, W, pre_nms_topN)).bytes;
+}
+
+RLOD_API int rlod_proposal_forward(const float *scores, const float *deltas, const float *im_info,
+                                   const float *anchors, int B, int A, int H, int W,
+                                   int feat_stride, int pre_nms_topN, int post_nms_topN,
+                                   float nms_thresh, float *rois_out, int *order_out,
+                                   float *props_out, int *nkeep_out, void *workspace,
+                                   size_t workspace_bytes, rlod_stream_t stream) {
+  if (B < 0 || A <= 0 || H <= 0 || W <= 0 || post_nms_topN <= 0) return RLOD_EINVAL;
+  if (B == 0) return RLOD_OK;
+  if (!scores || !deltas || !im_info || !anchors || !rois_out || !workspace) return RLOD_EINVAL;
+  if (((uintptr_t)anchors % 16) != 0) return RLOD_EINVAL;
+  if (props_out && ((uintptr_t)props_out % 16) != 0) return RLOD_EINVAL;
+  if ((long long)A * H * W >= (1LL << 30)) return RLOD_EUNSUPPORTED;
+  const int pre = eff_pre(A, H, W, pre_nms_topN);
+  if (pre > kSortMax) return RLOD_EUNSUPPORTED;
+  PropWs ws = carve_prop_ws(workspace, B, pre);
+  if (workspace_bytes < ws.bytes) return RLOD_ENOSPC;
+  cudaStream_t st = (cudaStream_t)stream;
+
+  int mp = 64;
+  while (mp < pre) mp <<= 1;
+  PropArgs pa;
+  pa.scores = scores, pa.deltas = deltas, pa.im_info = im_info, pa.anchors = anchors;
+  pa.B = B, pa.A = A, pa.H = H, pa.W = W, pa.feat_stride = feat_stride, pa.pre = pre;
+  pa.props = ws.props, pa.order_out = order_out, pa.props_out = props_out;
+  const size_t smem = (size_t)mp * sizeof(unsigned long long);
+  cudaFuncSetAttribute(k_proposal_sort_decode, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)smem);
+  RLOD_LAUNCH(RLOD_KERNEL_PROPOSAL_SORT, st, k_proposal_sort_decode<<<B, kSortThreads, smem, st>>>(pa, mp));
+  int rc = launch_status();
+  if (rc) return rc;
+
+  NmsSegs segs;
+  segs.dets = reinterpret_cast<const float *>(ws.props);
+  segs.stride = 4;
+  segs.vec4 = 1;
+  segs.seg_offsets = nullptr;
+  segs.uniform_n = pre;
+  segs.max_n = pre;
+  NmsOut o = {};
+  o.keep = nullptr;
+  o.num_out = nkeep_out;
+  o.rois = rois_out;
+  o.post = post_nms_topN;
+  // proposals always take the tiled path (pre is thousands); tiny maps fall to the
+  // shared-memory kernel, which emits the same output
+  return nms_launch(segs, B, pre, nms_thresh, post_nms_topN, o, ws.mask, ws.mask_bytes, st, 0);
+}

@@ -1,0 +1,239 @@
+// RL refinement step for sm_100a.
+//
+// k_action_reward: the per-box x per-action label loop of COCODataset.__getitem__
+// (lib/datasets/RL_coco_dataset.py:119-137) -- in the reference N_boxes * num_acts separate
+// Python -> Cython -> C calls of pycocotools bbIou (lib/pycocotools/maskApi.c:98-109) per
+// image inside DataLoader workers -- as one launch: a thread per (image, box, action).
+//   RLOD_IOU_COCO: xywh boxes, fp64, every operation rounded separately exactly like the C
+//     source compiled without contraction -> bit-exact rewards.
+//   RLOD_IOU_RCNN: x1y1x2y2 boxes, fp32 bbox_overlaps (lib/model/rpn/bbox_transform.py:
+//     136-166), the action applied to (x1, y1, w, h).
+// k_move_from_act: Action.move_from_act (lib/model/Reinforcement/action.py:25-59) on the
+// device, one CTA per image: per-box best action, bitonic sort of the boxes by
+// (pred descending, flat index ascending), the first maxk boxes move if their target is 1.
+#include "rlod_common.cuh"
+
+namespace rlod {
+
+__device__ __forceinline__ double bbiou_f64(const double *D, const double *G, bool crowd) {
+  const double ga = __dmul_rn(G[2], G[3]), da = __dmul_rn(D[2], D[3]);
+  const double w = __dsub_rn(fmin(__dadd_rn(D[2], D[0]), __dadd_rn(G[2], G[0])), fmax(D[0], G[0]));
+  if (w <= 0) return 0.;
+  const double h = __dsub_rn(fmin(__dadd_rn(D[3], D[1]), __dadd_rn(G[3], G[1])), fmax(D[1], G[1]));
+  if (h <= 0) return 0.;
+  const double i = __dmul_rn(w, h);
+  const double u = crowd ? da : __dsub_rn(__dadd_rn(da, ga), i);
+  return __ddiv_rn(i, u);
+}
+
+__device__ __forceinline__ double max_bbiou(const double *D, const float *__restrict__ gt,
+                                            const unsigned char *__restrict__ crowd, int ng) {
+  if (ng <= 0) {
+    const double z[4] = {0., 0., 0., 0.};
+    return bbiou_f64(D, z, false);
+  }
+  double best = -INFINITY;
+  for (int g = 0; g < ng; ++g) {
+    const double G[4] = {(double)__ldg(gt + g * 4), (double)__ldg(gt + g * 4 + 1),
+                         (double)__ldg(gt + g * 4 + 2), (double)__ldg(gt + g * 4 + 3)};
+    const double o = bbiou_f64(D, G, crowd ? (crowd[g] != 0) : false);
+    if (o > best) best = o;
+  }
+  return best;
+}
+
+__device__ __forceinline__ float overlap_f32(const float *a, const float *g) {
+  const float aa = __fmul_rn(__fadd_rn(__fsub_rn(a[2], a[0]), 1.f), __fadd_rn(__fsub_rn(a[3], a[1]), 1.f));
+  const float ga = __fmul_rn(__fadd_rn(__fsub_rn(g[2], g[0]), 1.f), __fadd_rn(__fsub_rn(g[3], g[1]), 1.f));
+  float iw = __fadd_rn(__fsub_rn(fminf(a[2], g[2]), fmaxf(a[0], g[0])), 1.f);
+  if (iw < 0.f) iw = 0.f;
+  float ih = __fadd_rn(__fsub_rn(fminf(a[3], g[3]), fmaxf(a[1], g[1])), 1.f);
+  if (ih < 0.f) ih = 0.f;
+  const float inter = __fmul_rn(iw, ih);
+  return __fdiv_rn(inter, __fsub_rn(__fadd_rn(aa, ga), inter));
+}
+
+__device__ __forceinline__ float max_overlap_f32(const float *a, const float *__restrict__ gt, int ng) {
+  if (ng <= 0) {
+    const float z[4] = {0.f, 0.f, 0.f, 0.f};
+    return overlap_f32(a, z);
+  }
+  float best = -INFINITY;
+  for (int g = 0; g < ng; ++g) {
+    const float G[4] = {__ldg(gt + g * 4), __ldg(gt + g * 4 + 1), __ldg(gt + g * 4 + 2),
+                        __ldg(gt + g * 4 + 3)};
+    const float o = overlap_f32(a, G);
+    if (o > best) best = o;
+  }
+  return best;
+}
+
+__global__ void __launch_bounds__(256)
+    k_action_reward(const float *__restrict__ boxes, const float *__restrict__ gt,
+                    const unsigned char *__restrict__ crowd, const int *__restrict__ ngt,
+                    const float *__restrict__ act, int B, int N, int A, int G, int mode,
+                    float iou_thres, float pos_wratio, float neg_wratio, float *__restrict__ reward,
+                    float *__restrict__ label, float *__restrict__ weight) {
+  const long long total = (long long)B * N * A;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int a = (int)(idx % A);
+    const long long bn = idx / A;
+    const int b = (int)(bn / N);
+    const float *bx = boxes + bn * 4;
+    const float *gtb = gt + (size_t)b * G * 4;
+    const unsigned char *crb = crowd ? crowd + (size_t)b * G : nullptr;
+    int ng = ngt ? __ldg(ngt + b) : G;
+    if (ng > G) ng = G;
+    const float x0 = __ldg(bx), x1 = __ldg(bx + 1), x2 = __ldg(bx + 2), x3 = __ldg(bx + 3);
+    const float a0 = __ldg(act + a * 4), a1 = __ldg(act + a * 4 + 1);
+    const float a2 = __ldg(act + a * 4 + 2), a3 = __ldg(act + a * 4 + 3);
+    double r;
+    float rf;
+    if (mode == RLOD_IOU_COCO) {
+      // bbox + act_delta * np.array([w, h, w, h])  (RL_coco_dataset.py:124): fp64
+      const double w = x2, h = x3;
+      const double dt[4] = {x0, x1, x2, x3};
+      const double nb[4] = {__dadd_rn(dt[0], __dmul_rn((double)a0, w)),
+                            __dadd_rn(dt[1], __dmul_rn((double)a1, h)),
+                            __dadd_rn(dt[2], __dmul_rn((double)a2, w)),
+                            __dadd_rn(dt[3], __dmul_rn((double)a3, h))};
+      r = __dsub_rn(max_bbiou(nb, gtb, crb, ng), max_bbiou(dt, gtb, crb, ng));
+      rf = (float)r;
+    } else {
+      const float w = __fadd_rn(__fsub_rn(x2, x0), 1.f), h = __fadd_rn(__fsub_rn(x3, x1), 1.f);
+      const float nx = __fadd_rn(x0, __fmul_rn(a0, w)), ny = __fadd_rn(x1, __fmul_rn(a1, h));
+      const float nw = __fadd_rn(w, __fmul_rn(a2, w)), nh = __fadd_rn(h, __fmul_rn(a3, h));
+      const float nb[4] = {nx, ny, __fsub_rn(__fadd_rn(nx, nw), 1.f), __fsub_rn(__fadd_rn(ny, nh), 1.f)};
+      const float ob[4] = {x0, x1, x2, x3};
+      rf = __fsub_rn(max_overlap_f32(nb, gtb, ng), max_overlap_f32(ob, gtb, ng));
+      r = rf;
+    }
+    reward[idx] = rf;
+    const bool pos = r > (double)iou_thres;
+    if (label) label[idx] = pos ? 1.f : -1.f;
+    if (weight) weight[idx] = (float)(exp(fabs(r)) * (double)(pos ? pos_wratio : neg_wratio));
+  }
+}
+
+// float -> uint32 whose ascending order is the float's descending order
+__device__ __forceinline__ uint32_t desc_key32(float f) {
+  uint32_t u = __float_as_uint(f);
+  if (f == 0.f) u = 0u;
+  const uint32_t asc = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  return ~asc;
+}
+
+constexpr int kMoveThreads = 256;
+constexpr int kMoveMaxN = 4096;
+
+__global__ void __launch_bounds__(kMoveThreads)
+    k_move_from_act(float *__restrict__ boxes, int box_stride, int corners,
+                    const float *__restrict__ preds, const float *__restrict__ targets,
+                    const float *__restrict__ act, int N, int A, int maxk, int np2,
+                    int *__restrict__ correct) {
+  extern __shared__ unsigned long long mkeys[];  // [np2]
+  const int b = blockIdx.x, t = threadIdx.x;
+  const float *pr = preds + (size_t)b * N * A;
+  for (int n = t; n < np2; n += kMoveThreads) {
+    unsigned long long key = ~0ull;
+    if (n < N) {
+      // best action of the box: max pred, ties -> lowest action id (= lowest flat index)
+      int best = 0;
+      float bv = __ldg(pr + (size_t)n * A);
+      for (int a = 1; a < A; ++a) {
+        const float v = __ldg(pr + (size_t)n * A + a);
+        if (v > bv) {
+          bv = v;
+          best = a;
+        }
+      }
+      key = ((unsigned long long)desc_key32(bv) << 32) | (unsigned)(n * A + best);
+    }
+    mkeys[n] = key;
+  }
+  __syncthreads();
+  for (int k = 2; k <= np2; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int p = t; p < (np2 >> 1); p += kMoveThreads) {
+        const int i = ((p / j) * (j << 1)) + (p % j), l = i + j;
+        const unsigned long long x = mkeys[i], y = mkeys[l];
+        if ((x > y) == ((i & k) == 0)) {
+          mkeys[i] = y;
+          mkeys[l] = x;
+        }
+      }
+      __syncthreads();
+    }
+  const int take = min(maxk, N);
+  int local = 0;
+  for (int i = t; i < take; i += kMoveThreads) {
+    const unsigned flat = (unsigned)(mkeys[i] & 0xffffffffull);
+    const int n = (int)(flat / (unsigned)A), a = (int)(flat % (unsigned)A);
+    if (__ldg(targets + ((size_t)b * N + n) * A + a) == 1.f) {
+      ++local;
+      float *bx = boxes + ((size_t)b * N + n) * box_stride;
+      const float a0 = __ldg(act + a * 4 + 0), a1 = __ldg(act + a * 4 + 1);
+      const float a2 = __ldg(act + a * 4 + 2), a3 = __ldg(act + a * 4 + 3);
+      if (!corners) {
+        // bboxes[bid][idx] += delta * np.array([w, h, w, h])   (xywh, fp32, action.py:55)
+        const float w = bx[2], h = bx[3];
+        bx[0] = __fadd_rn(bx[0], __fmul_rn(a0, w));
+        bx[1] = __fadd_rn(bx[1], __fmul_rn(a1, h));
+        bx[2] = __fadd_rn(bx[2], __fmul_rn(a2, w));
+        bx[3] = __fadd_rn(bx[3], __fmul_rn(a3, h));
+      } else {
+        // x1y1x2y2 boxes (+1 convention): the same move applied to (x1, y1, w, h), identical
+        // to the arithmetic of k_action_reward's RLOD_IOU_RCNN mode
+        const float w = __fadd_rn(__fsub_rn(bx[2], bx[0]), 1.f);
+        const float h = __fadd_rn(__fsub_rn(bx[3], bx[1]), 1.f);
+        const float nx = __fadd_rn(bx[0], __fmul_rn(a0, w)), ny = __fadd_rn(bx[1], __fmul_rn(a1, h));
+        const float nw = __fadd_rn(w, __fmul_rn(a2, w)), nh = __fadd_rn(h, __fmul_rn(a3, h));
+        bx[0] = nx;
+        bx[1] = ny;
+        bx[2] = __fsub_rn(__fadd_rn(nx, nw), 1.f);
+        bx[3] = __fsub_rn(__fadd_rn(ny, nh), 1.f);
+      }
+    }
+  }
+  // block reduce of the per-thread counts
+  for (int d = 16; d > 0; d >>= 1) local += __shfl_down_sync(0xffffffffu, local, d);
+  if ((t & 31) == 0 && local && correct) atomicAdd(correct, local);
+}
+
+}  // namespace rlod
+
+using namespace rlod;
+
+RLOD_API int rlod_action_reward(const float *boxes, const float *gt, const unsigned char *crowd,
+                                const int *ngt, const float *act, int B, int N, int A, int G,
+                                int mode, float iou_thres, float pos_wratio, float neg_wratio,
+                                float *reward, float *label, float *weight, rlod_stream_t stream) {
+  if (B < 0 || N < 0 || A < 0 || G < 0) return RLOD_EINVAL;
+  if (mode != RLOD_IOU_COCO && mode != RLOD_IOU_RCNN) return RLOD_EINVAL;
+  if (B == 0 || N == 0 || A == 0) return RLOD_OK;
+  if (!boxes || !act || !reward) return RLOD_EINVAL;
+  if (G > 0 && !gt) return RLOD_EINVAL;
+  const long long total = (long long)B * N * A;
+  const long long blocks = cdiv(total, 256);
+  const unsigned grid = (unsigned)(blocks < (1LL << 30) ? blocks : (1LL << 30));
+  RLOD_LAUNCH(RLOD_KERNEL_REWARD, (cudaStream_t)stream, k_action_reward<<<grid, 256, 0, (cudaStream_t)stream>>>(boxes, gt, crowd, ngt, act, B, N, A, G,
+                                                          mode, iou_thres, pos_wratio, neg_wratio,
+                                                          reward, label, weight));
+  return launch_status();
+}
+
+RLOD_API int rlod_move_from_act(float *boxes, int box_stride, int corners, const float *preds,
+                                const float *targets, const float *act, int B, int N, int A,
+                                int maxk, int *correct, rlod_stream_t stream) {
+  if (B < 0 || N < 0 || A < 1 || maxk < 0 || box_stride < 4) return RLOD_EINVAL;
+  if (B == 0 || N == 0 || maxk == 0) return RLOD_OK;
+  if (!boxes || !preds || !targets || !act) return RLOD_EINVAL;
+  if (N > kMoveMaxN || (long long)N * A >= (1LL << 31)) return RLOD_EUNSUPPORTED;
+  int np2 = 2;
+  while (np2 < N) np2 <<= 1;
+  k_move_from_act<<<B, kMoveThreads, (size_t)np2 * sizeof(unsigned long long),
+                    (cudaStream_t)stream>>>(boxes, box_stride, corners, preds, targets, act, N, A,
+                                            maxk, np2, correct);
+  return launch_status();
+}

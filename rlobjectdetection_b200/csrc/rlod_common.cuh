@@ -1,0 +1,92 @@
+// Shared helpers for the sm_100a kernels of librlod_sm100a.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "rlod.h"
+
+#define RLOD_API extern "C" __attribute__((visibility("default")))
+
+namespace rlod {
+
+constexpr int kSmCount = 148;           // B200: 2 dies x 74 SMs
+constexpr int kMaxSmemPerCta = 232448;  // 227 KB opt-in limit per CTA on sm_100a
+
+static inline int launch_status() { return (int)cudaGetLastError(); }
+
+// every kernel launch of the library goes through a ProfScope: it counts the launch
+// (rlod_launch_count) and, when rlod_profile_enable(1) is set, brackets it with CUDA events on
+// its own stream (rlod_profile_collect).
+void note_launch(int n);
+class ProfScope {
+ public:
+  ProfScope(int kernel_id, cudaStream_t st);
+  ~ProfScope();
+
+ private:
+  int id_;
+  cudaStream_t st_;
+  bool on_;
+  cudaEvent_t a_, b_;
+};
+
+#define RLOD_LAUNCH(ID, ST, ...)        \
+  do {                                  \
+    ::rlod::ProfScope _ps((ID), (ST));  \
+    __VA_ARGS__;                        \
+  } while (0)
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static inline long long cdiv(long long a, long long b) { return (a + b - 1) / b; }
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// ---- mbarrier + 1-D bulk async copy (TMA engine, SASS: UBLKCP) --------------------------
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes,
+                                         uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+
+// streaming (evict-first) 128-bit store / load: outputs and one-shot inputs must not push
+// the feature planes out of L2
+__device__ __forceinline__ void st_stream4(float *p, float4 v) {
+  __stcs(reinterpret_cast<float4 *>(p), v);
+}
+__device__ __forceinline__ float4 ld_stream4(const float *p) {
+  return __ldcs(reinterpret_cast<const float4 *>(p));
+}
+
+}  // namespace rlod

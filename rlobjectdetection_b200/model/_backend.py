@@ -1,0 +1,329 @@
+"""ctypes binding of csrc/librlod_sm100a.so (C ABI: include/rlod.h).
+
+PyTorch is used only for device memory (tensors, the caching allocator for workspaces) and
+streams; every computation is a hand-written sm_100a kernel behind the C ABI.  There is NO
+fallback: if the shared library is missing, or a tensor is not on a CUDA device, the call
+raises.
+"""
+import ctypes
+import os
+import subprocess
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(os.path.dirname(_HERE), "csrc")
+LIB_PATH = os.path.join(CSRC, "librlod_sm100a.so")
+
+POOL_NONE, POOL_AVG, POOL_MAX = 0, 1, 2
+KERNELS = ["align_fwd", "align_bwd", "align_fwd_generic", "align_bwd_generic", "roi_plan", "nms_mask",
+           "nms_scan", "nms_small", "proposal_sort", "pool_fwd", "pool_bwd", "boxes", "reward", "move"]
+IOU_COCO, IOU_RCNN = 0, 1
+SORT_MAX = 16384  # rlod_proposal_forward: min(pre_nms_topN, H*W*A) limit
+
+_c_void_p, _c_int, _c_float, _c_size_t, _c_ll = (ctypes.c_void_p, ctypes.c_int, ctypes.c_float,
+                                                 ctypes.c_size_t, ctypes.c_longlong)
+_P, _I, _F, _Z, _L = _c_void_p, _c_int, _c_float, _c_size_t, _c_ll
+
+# name -> (restype, argtypes); mirrors include/rlod.h one to one
+SIGNATURES = {
+    "rlod_version": (_I, []),
+    "rlod_error_string": (ctypes.c_char_p, [_I]),
+    "rlod_launch_count": (_L, []),
+    "rlod_profile_enable": (_I, [_I]),
+    "rlod_profile_collect": (_I, [_I, _P, _P]),
+    "rlod_nms_workspace_bytes": (_Z, [_I, _I]),
+    "rlod_nms": (_I, [_P, _I, _I, _F, _I, _P, _P, _P, _Z, _P]),
+    "rlod_debug_nms_force_large": (_I, [_I]),
+    "rlod_nms_batched": (_I, [_P, _I, _P, _I, _I, _F, _I, _P, _P, _P, _Z, _P]),
+    "rlod_roi_align_workspace_bytes": (_Z, [_I, _I, _I, _I, _I]),
+    "rlod_roi_align_forward": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P, _P, _Z, _P]),
+    "rlod_roi_align_backward": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _I, _I, _P, _P,
+                                     _Z, _P]),
+    "rlod_roi_pool_forward": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P]),
+    "rlod_roi_pool_backward": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "rlod_proposal_workspace_bytes": (_Z, [_I, _I, _I, _I, _I, _I]),
+    "rlod_proposal_forward": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P,
+                                   _P, _Z, _P]),
+    "rlod_bbox_transform_inv": (_I, [_P, _P, _L, _I, _P, _P]),
+    "rlod_clip_boxes": (_I, [_P, _P, _I, _L, _I, _P]),
+    "rlod_bbox_overlaps": (_I, [_P, _P, _I, _I, _P, _P]),
+    "rlod_bbox_overlaps_batch": (_I, [_P, _L, _I, _P, _I, _I, _I, _I, _P, _P]),
+    "rlod_action_reward": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _F, _P, _P, _P,
+                                _P]),
+    "rlod_move_from_act": (_I, [_P, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
+}
+
+_LIB = None
+
+
+def build(verbose=False):
+    """Compile csrc/*.cu into csrc/librlod_sm100a.so with nvcc for sm_100a (in-tree)."""
+    r = subprocess.run(["make", "-C", CSRC, "-j8"], capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        print(r.stdout, r.stderr)
+    if r.returncode != 0:
+        raise RuntimeError("building librlod_sm100a.so failed")
+    return LIB_PATH
+
+
+def lib():
+    """The loaded library; raises (never falls back) when it has not been built."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C rlobjectdetection_b200/csrc`). There is no CPU / PyTorch fallback.")
+        l = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = l
+    return _LIB
+
+
+def profile_collect():
+    """{kernel name: (total_ms, launches)} of everything recorded since rlod_profile_enable(1)."""
+    out = {}
+    for i, name in enumerate(KERNELS):
+        ms, n = ctypes.c_double(0.0), ctypes.c_int(0)
+        check(lib().rlod_profile_collect(i, ctypes.byref(ms), ctypes.byref(n)), "rlod_profile_collect")
+        if n.value:
+            out[name] = (ms.value, n.value)
+    return out
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().rlod_error_string(int(rc)).decode()
+        raise RuntimeError(f"{what} failed: {msg} (code {rc})")
+
+
+def ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def stream_of(t):
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def require_cuda(name, *tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            # the reference raises NotImplementedError for CPU features as well
+            # (lib/model/roi_align/functions/roi_align.py:28-29)
+            raise NotImplementedError(f"{name}: CUDA tensors required, there is no CPU path")
+
+
+def f32c(t):
+    """fp32 + contiguous view of t (copy only when needed)."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def workspace(nbytes, device):
+    """Caller-owned scratch from torch's caching allocator (stream-ordered with the launch)."""
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+# ------------------------------------------------------------------------------------------
+# thin functional layer: one python function per C entry point
+# ------------------------------------------------------------------------------------------
+def nms_padded(dets, thresh, max_keep=0):
+    """rlod_nms.  Returns (keep (n,) int32 padded with -1, num (1,) int32), no host sync."""
+    require_cuda("nms", dets)
+    dets = f32c(dets)
+    n, stride = dets.shape
+    keep = torch.empty(max(n, 1), dtype=torch.int32, device=dets.device)
+    num = torch.empty(1, dtype=torch.int32, device=dets.device)
+    l = lib()
+    with torch.cuda.device(dets.device):
+        ws = workspace(l.rlod_nms_workspace_bytes(1, n), dets.device)
+        check(l.rlod_nms(ptr(dets), n, stride, float(thresh), int(max_keep), ptr(keep), ptr(num),
+                         ptr(ws), ws.numel(), stream_of(dets)), "rlod_nms")
+    return keep[:n], num
+
+
+def nms_batched(dets, seg_offsets, thresh, max_seg=None, max_keep=0):
+    """rlod_nms_batched.  seg_offsets (nseg+1,) int32 on the device; max_seg: upper bound of
+    the segment length (computed with one host read when not given).
+    Returns (keep (n,) int32 segment-local indices, -1 padded; num (nseg,) int32)."""
+    require_cuda("nms_batched", dets, seg_offsets)
+    dets = f32c(dets)
+    seg_offsets = seg_offsets.to(torch.int32).contiguous()
+    n, stride = dets.shape
+    nseg = seg_offsets.numel() - 1
+    if max_seg is None:
+        max_seg = int((seg_offsets[1:] - seg_offsets[:-1]).max().item()) if nseg > 0 else 0
+    keep = torch.empty(max(n, 1), dtype=torch.int32, device=dets.device)
+    num = torch.empty(max(nseg, 1), dtype=torch.int32, device=dets.device)
+    l = lib()
+    with torch.cuda.device(dets.device):
+        ws = workspace(l.rlod_nms_workspace_bytes(nseg, max_seg), dets.device)
+        check(l.rlod_nms_batched(ptr(dets), stride, ptr(seg_offsets), nseg, int(max_seg),
+                                 float(thresh), int(max_keep), ptr(keep), ptr(num), ptr(ws),
+                                 ws.numel(), stream_of(dets)), "rlod_nms_batched")
+    return keep[:n], num[:nseg]
+
+
+def _check_rois(features, rois):
+    if features.dim() != 4:
+        raise ValueError("features must be (B, C, H, W)")
+    if rois.dim() != 2 or rois.size(1) != 5:
+        # the reference's C glue returns 0 here and the caller ignores it
+        # (roi_align_cuda.c:20-24); we raise instead of producing garbage
+        raise ValueError("rois must be (R, 5) = [batch_idx, x1, y1, x2, y2]")
+    if rois.device != features.device:
+        raise ValueError("features and rois must be on the same device")
+
+
+def roi_align_forward(features, rois, ah, aw, scale, pool_mode):
+    require_cuda("roi_align", features, rois)
+    _check_rois(features, rois)
+    features, rois = f32c(features), f32c(rois)
+    B, C, H, W = features.shape
+    R = rois.size(0)
+    out = torch.empty(R, C, ah, aw, dtype=torch.float32, device=features.device)
+    l = lib()
+    with torch.cuda.device(features.device):
+        ws = workspace(l.rlod_roi_align_workspace_bytes(B, R, ah, aw, pool_mode), features.device)
+        check(l.rlod_roi_align_forward(ptr(features), ptr(rois), B, C, H, W, R, ah, aw,
+                                       float(scale), pool_mode, ptr(out), ptr(ws), ws.numel(),
+                                       stream_of(features)), "rlod_roi_align_forward")
+    return out
+
+
+def roi_align_backward(grad_out, rois, features, feature_size, ah, aw, scale, pool_mode,
+                       grad_in=None):
+    """grad wrt features.  grad_in given: accumulate into it; else a fresh tensor is written
+    (no memset: the kernel overwrites every element)."""
+    require_cuda("roi_align backward", grad_out, rois)
+    grad_out, rois = f32c(grad_out), f32c(rois)
+    B, C, H, W = feature_size
+    R = rois.size(0)
+    accumulate = grad_in is not None
+    if grad_in is None:
+        grad_in = torch.empty(B, C, H, W, dtype=torch.float32, device=grad_out.device)
+    feat = f32c(features) if (features is not None and pool_mode == POOL_MAX) else None
+    l = lib()
+    with torch.cuda.device(grad_out.device):
+        ws = workspace(l.rlod_roi_align_workspace_bytes(B, R, ah, aw, pool_mode), grad_out.device)
+        check(l.rlod_roi_align_backward(ptr(grad_out), ptr(rois), ptr(feat), B, C, H, W, R, ah, aw,
+                                        float(scale), pool_mode, int(accumulate), ptr(grad_in),
+                                        ptr(ws), ws.numel(), stream_of(grad_out)),
+              "rlod_roi_align_backward")
+    return grad_in
+
+
+def roi_pool_forward(features, rois, ph, pw, scale):
+    require_cuda("roi_pool", features, rois)
+    _check_rois(features, rois)
+    features, rois = f32c(features), f32c(rois)
+    B, C, H, W = features.shape
+    R = rois.size(0)
+    out = torch.empty(R, C, ph, pw, dtype=torch.float32, device=features.device)
+    argmax = torch.empty(R, C, ph, pw, dtype=torch.int32, device=features.device)
+    with torch.cuda.device(features.device):
+        check(lib().rlod_roi_pool_forward(ptr(features), ptr(rois), B, C, H, W, R, ph, pw,
+                                          float(scale), ptr(out), ptr(argmax),
+                                          stream_of(features)), "rlod_roi_pool_forward")
+    return out, argmax
+
+
+def roi_pool_backward(grad_out, argmax, feature_size, ph, pw, grad_in=None):
+    require_cuda("roi_pool backward", grad_out, argmax)
+    grad_out = f32c(grad_out)
+    B, C, H, W = feature_size
+    R = grad_out.size(0)
+    accumulate = grad_in is not None
+    if grad_in is None:
+        grad_in = torch.empty(B, C, H, W, dtype=torch.float32, device=grad_out.device)
+    with torch.cuda.device(grad_out.device):
+        check(lib().rlod_roi_pool_backward(ptr(grad_out), ptr(argmax), B, C, H, W, R, ph, pw,
+                                           int(accumulate), ptr(grad_in), stream_of(grad_out)),
+              "rlod_roi_pool_backward")
+    return grad_in
+
+
+def proposal_forward(scores, deltas, im_info, anchors, feat_stride, pre_nms_topN, post_nms_topN,
+                     nms_thresh, return_taps=False):
+    """rlod_proposal_forward.  scores (B,2A,H,W), deltas (B,4A,H,W), im_info (B,3),
+    anchors (A,4).  Returns rois (B, post, 5) [and order, props, nkeep taps]."""
+    require_cuda("_ProposalLayer", scores, deltas, im_info, anchors)
+    scores, deltas, im_info, anchors = f32c(scores), f32c(deltas), f32c(im_info), f32c(anchors)
+    B, A2, H, W = scores.shape
+    A = A2 // 2
+    if anchors.shape != (A, 4) or deltas.shape != (B, 4 * A, H, W) or im_info.shape != (B, 3):
+        raise ValueError("proposal layer: inconsistent input shapes")
+    KA = A * H * W
+    pre = pre_nms_topN if 0 < pre_nms_topN < KA else KA
+    dev = scores.device
+    rois = torch.empty(B, post_nms_topN, 5, dtype=torch.float32, device=dev)
+    order = props = nkeep = None
+    if return_taps:
+        order = torch.empty(B, pre, dtype=torch.int32, device=dev)
+        props = torch.empty(B, pre, 4, dtype=torch.float32, device=dev)
+        nkeep = torch.empty(B, dtype=torch.int32, device=dev)
+    l = lib()
+    with torch.cuda.device(dev):
+        ws = workspace(l.rlod_proposal_workspace_bytes(B, A, H, W, int(pre_nms_topN),
+                                                       int(post_nms_topN)), dev)
+        check(l.rlod_proposal_forward(ptr(scores), ptr(deltas), ptr(im_info), ptr(anchors), B, A,
+                                      H, W, int(feat_stride), int(pre_nms_topN),
+                                      int(post_nms_topN), float(nms_thresh), ptr(rois), ptr(order),
+                                      ptr(props), ptr(nkeep), ptr(ws), ws.numel(),
+                                      stream_of(scores)), "rlod_proposal_forward")
+    if return_taps:
+        return rois, order, props, nkeep
+    return rois
+
+
+def action_reward(boxes, gt, act, crowd=None, ngt=None, mode=IOU_COCO, iou_thres=0.0,
+                  pos_wratio=1.0, neg_wratio=1.0, want_labels=True):
+    """rlod_action_reward.  boxes (B,N,4), gt (B,G,4), act (A,4) -> reward[, label, weight]
+    each (B,N,A)."""
+    require_cuda("action_reward", boxes, gt, act, crowd, ngt)
+    boxes, gt, act = f32c(boxes), f32c(gt), f32c(act)
+    B, N, _ = boxes.shape
+    G = gt.size(1)
+    A = act.size(0)
+    dev = boxes.device
+    if crowd is not None:
+        crowd = crowd.to(torch.uint8).contiguous()
+    if ngt is not None:
+        ngt = ngt.to(torch.int32).contiguous()
+    reward = torch.empty(B, N, A, dtype=torch.float32, device=dev)
+    label = torch.empty_like(reward) if want_labels else None
+    weight = torch.empty_like(reward) if want_labels else None
+    with torch.cuda.device(dev):
+        check(lib().rlod_action_reward(ptr(boxes), ptr(gt), ptr(crowd), ptr(ngt), ptr(act), B, N, A,
+                                       G, int(mode), float(iou_thres), float(pos_wratio),
+                                       float(neg_wratio), ptr(reward), ptr(label), ptr(weight),
+                                       stream_of(boxes)), "rlod_action_reward")
+    if want_labels:
+        return reward, label, weight
+    return reward
+
+
+def move_from_act(boxes, preds, targets, act, maxk, corners=False):
+    """rlod_move_from_act.  boxes (B,N,4) [x,y,w,h] -- or, with corners=True, (B,N,4)
+    [x1,y1,x2,y2] / (B,N,5) rois [b,x1,y1,x2,y2] -- is updated IN PLACE; returns the device
+    int32 count of moved boxes (no host sync)."""
+    require_cuda("move_from_act", boxes, preds, targets, act)
+    if not (boxes.is_contiguous() and boxes.dtype == torch.float32):
+        raise ValueError("move_from_act: boxes must be a contiguous fp32 tensor (updated in place)")
+    preds, targets, act = f32c(preds), f32c(targets), f32c(act)
+    B, N, stride = boxes.shape
+    if stride not in (4, 5) or (stride == 5 and not corners):
+        raise ValueError("move_from_act: boxes must be (B,N,4), or (B,N,5) rois with corners=True")
+    A = act.size(0)
+    correct = torch.zeros(1, dtype=torch.int32, device=boxes.device)
+    base = ctypes.c_void_p(boxes.data_ptr() + 4 * (stride - 4))
+    with torch.cuda.device(boxes.device):
+        check(lib().rlod_move_from_act(base, stride, int(bool(corners)), ptr(preds), ptr(targets),
+                                       ptr(act), B, N, A, int(maxk), ptr(correct),
+                                       stream_of(boxes)), "rlod_move_from_act")
+    return correct

@@ -1,0 +1,34 @@
+"""RoIAlign / RoIAlignAvg / RoIAlignMax modules (reference:
+lib/model/roi_align/modules/roi_align.py:6-42), same constructors.  Avg / Max sample an
+(ah+1) x (aw+1) grid and pool it 2x2 stride 1 -- here inside the same kernel, so the
+(R, C, ah+1, aw+1) intermediate (268 MB at 1024 rois x 1024 channels) never exists."""
+from torch.nn.modules.module import Module
+
+from ... import _backend as be
+from ..functions.roi_align import RoIAlignFunction
+
+
+class _RoIAlignBase(Module):
+    pool_mode = be.POOL_NONE
+
+    def __init__(self, aligned_height, aligned_width, spatial_scale):
+        super().__init__()
+        self.aligned_width = int(aligned_width)
+        self.aligned_height = int(aligned_height)
+        self.spatial_scale = float(spatial_scale)
+
+    def forward(self, features, rois):
+        return RoIAlignFunction(self.aligned_height, self.aligned_width, self.spatial_scale,
+                                self.pool_mode)(features, rois)
+
+
+class RoIAlign(_RoIAlignBase):
+    pool_mode = be.POOL_NONE
+
+
+class RoIAlignAvg(_RoIAlignBase):
+    pool_mode = be.POOL_AVG
+
+
+class RoIAlignMax(_RoIAlignBase):
+    pool_mode = be.POOL_MAX

@@ -1,0 +1,51 @@
+"""The configuration keys the hot path reads, under the reference's names
+(lib/model/utils/config.py:141-147, 175, 191-199, 283-298).  Only these keys are provided:
+the reference's dataset / solver / yaml machinery is out of scope.  `cfg` is an attribute
+dict, so `cfg[cfg_key].RPN_PRE_NMS_TOP_N` (proposal_layer.py:72-75) and `cfg.POOLING_SIZE`
+(faster_rcnn.py:33-34) work unchanged; `cfg_from_list` accepts the same flat key/value list as
+the reference's --set option."""
+import ast
+
+
+class AttrDict(dict):
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+cfg = AttrDict(
+    TRAIN=AttrDict(RPN_NMS_THRESH=0.7, RPN_PRE_NMS_TOP_N=12000, RPN_POST_NMS_TOP_N=2000,
+                   RPN_MIN_SIZE=8),
+    TEST=AttrDict(NMS=0.3, RPN_NMS_THRESH=0.7, RPN_PRE_NMS_TOP_N=6000, RPN_POST_NMS_TOP_N=300,
+                  RPN_MIN_SIZE=16),
+    POOLING_MODE="align",  # the reference defaults to 'crop' (:283); roi_crop is out of scope
+    POOLING_SIZE=7,
+    MAX_NUM_GT_BOXES=20,
+    ANCHOR_SCALES=[8, 16, 32],
+    ANCHOR_RATIOS=[0.5, 1, 2],
+    FEAT_STRIDE=[16],
+    CUDA=True,
+)
+
+
+def cfg_from_list(cfg_list):
+    """['TEST.RPN_POST_NMS_TOP_N', '100', ...] -> cfg (reference: config.py:376-399)."""
+    if len(cfg_list) % 2:
+        raise ValueError("cfg_from_list expects key/value pairs")
+    for key, value in zip(cfg_list[0::2], cfg_list[1::2]):
+        node = cfg
+        *path, leaf = key.split(".")
+        for part in path:
+            node = node[part]
+        if leaf not in node:
+            raise KeyError(key)
+        try:
+            value = ast.literal_eval(value) if isinstance(value, str) else value
+        except (ValueError, SyntaxError):
+            pass
+        node[leaf] = value

@@ -1,0 +1,498 @@
+"""GPU parity: the sm_100a kernels (through the C ABI / the reference-shaped modules) against the
+CPU oracle on identical seeded inputs.  Integer / index results are bit-exact; pooled features,
+gradients and rewards are within 1e-5 relative (tolerance written at each assert)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from rlobjectdetection_b200 import synthetic as syn  # noqa: E402
+from rlobjectdetection_b200.model import _backend as be  # noqa: E402
+
+DEV = "cuda:0"
+RTOL = 1e-5
+
+
+def close(a, ref, rtol=RTOL, what=""):
+    """|a - ref| <= rtol*|ref| + rtol*max|ref|  (fp32 outputs of O(1) data)."""
+    a = np.asarray(a, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    assert a.shape == ref.shape, (what, a.shape, ref.shape)
+    scale = float(np.abs(ref).max()) if ref.size else 0.0
+    np.testing.assert_allclose(a, ref, rtol=rtol, atol=rtol * max(scale, 1e-30), err_msg=what)
+
+
+def cu(x, dtype=None):
+    t = torch.as_tensor(np.ascontiguousarray(x)) if not torch.is_tensor(x) else x
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.to(DEV)
+
+
+# ------------------------------------------------------------------------------------------
+# NMS
+# ------------------------------------------------------------------------------------------
+def _sorted_dets(seed, n, im=600.0, smin=8.0, smax=200.0):
+    g = torch.Generator().manual_seed(seed)
+    bx = syn.random_boxes(g, n, im, im, smin, smax)
+    sc = syn.distinct_scores(g, (n,)).sort(descending=True).values
+    return torch.cat([bx, sc[:, None]], 1).contiguous()
+
+
+@pytest.mark.parametrize("force_large", [0, 1])
+@pytest.mark.parametrize("n", [1, 2, 63, 64, 65, 300, 511, 513, 1000, 3000])
+@pytest.mark.parametrize("thresh", [0.3, 0.7])
+def test_nms_bit_exact(orc, n, thresh, force_large):
+    dets = _sorted_dets(100 + n, n)
+    ref = orc.nms(dets.numpy(), thresh)
+    prev = be.lib().rlod_debug_nms_force_large(force_large)
+    try:
+        keep, num = be.nms_padded(cu(dets), thresh)
+    finally:
+        be.lib().rlod_debug_nms_force_large(prev)
+    k = int(num.item())
+    assert k == len(ref)
+    assert np.array_equal(keep[:k].cpu().numpy(), ref)
+    assert (keep[k:].cpu().numpy() == -1).all()
+
+
+@pytest.mark.parametrize("max_keep", [1, 7, 64, 65, 300])
+def test_nms_max_keep(orc, max_keep):
+    dets = _sorted_dets(7, 2000)
+    ref = orc.nms(dets.numpy(), 0.5, max_keep=max_keep)
+    keep, num = be.nms_padded(cu(dets), 0.5, max_keep=max_keep)
+    k = int(num.item())
+    assert k == len(ref) == min(max_keep, len(orc.nms(dets.numpy(), 0.5)))
+    assert np.array_equal(keep[:k].cpu().numpy(), ref)
+
+
+def test_nms_near_threshold_and_degenerate(orc):
+    # integer boxes whose IoU sits exactly on / one ulp around the threshold, duplicates,
+    # inverted and zero-size boxes: decisions must equal the IEEE-division reference
+    rows = []
+    for s in range(1, 40):
+        rows += [[0, 0, 9, 9], [0, 0, 9, 4 + (s % 3)], [s, 0, 9 + s, 9], [0, s, 9, 9 + s],
+                 [3, 3, 3, 3], [10, 10, 5, 5], [0, 0, 2 * s, s], [s, s, 3 * s, 2 * s]]
+    base = np.array(rows, dtype=np.float32)
+    rng = np.random.default_rng(5)
+    jit = base + rng.integers(0, 2, base.shape).astype(np.float32)
+    boxes = np.concatenate([base, jit, base + 0.5], 0)
+    dets = np.concatenate([boxes, np.linspace(1, 0, len(boxes), dtype=np.float32)[:, None]], 1)
+    for thresh in (0.5, 0.25, 1.0 / 3.0, 0.7, 0.0, 0.9999999, -0.5, 1.5):
+        ref = orc.nms(dets, thresh)
+        for fl in (0, 1):
+            prev = be.lib().rlod_debug_nms_force_large(fl)
+            try:
+                keep, num = be.nms_padded(cu(dets), thresh)
+            finally:
+                be.lib().rlod_debug_nms_force_large(prev)
+            k = int(num.item())
+            assert k == len(ref), (thresh, fl)
+            assert np.array_equal(keep[:k].cpu().numpy(), ref), (thresh, fl)
+
+
+def test_nms_stride4_and_wrapper(orc):
+    from rlobjectdetection_b200.model.nms.nms_wrapper import nms
+    dets = _sorted_dets(11, 700)
+    ref = orc.nms(dets.numpy(), 0.7)
+    out = nms(cu(dets), 0.7)
+    assert out.dtype == torch.int32 and out.shape == (len(ref), 1)
+    assert np.array_equal(out.view(-1).cpu().numpy(), ref)
+    keep, num = be.nms_padded(cu(dets[:, :4].contiguous()), 0.7)  # float4 path
+    assert np.array_equal(keep[: int(num.item())].cpu().numpy(), ref)
+    assert nms(torch.zeros(0, 5, device=DEV), 0.7) == []  # reference: nms_wrapper.py:13-14
+
+
+def test_nms_c1_size(orc):
+    # config 1 size: 12000 boxes, thr 0.7 -- full keep list and the post-NMS 2000 cut
+    dets = _sorted_dets(1, 12000, im=1000.0, smin=16.0, smax=400.0)
+    ref = orc.nms(dets.numpy(), 0.7)
+    keep, num = be.nms_padded(cu(dets), 0.7)
+    k = int(num.item())
+    assert k == len(ref) and np.array_equal(keep[:k].cpu().numpy(), ref)
+    keep2, num2 = be.nms_padded(cu(dets), 0.7, max_keep=2000)
+    k2 = int(num2.item())
+    assert k2 == min(2000, len(ref)) and np.array_equal(keep2[:k2].cpu().numpy(), ref[:k2])
+
+
+@pytest.mark.parametrize("shape", [(3, 5, 300), (64, 81, 300)])
+def test_nms_batched_per_class(orc, shape):
+    # config 5: images x classes segments of 300 clustered boxes, thr 0.3, one launch
+    ni, nc, per = shape
+    dets, seg = syn.clustered_dets(4, ni, nc, per)
+    rk, rn = orc.nms_batched(dets.numpy(), seg.numpy(), 0.3)
+    keep, num = be.nms_batched(cu(dets), cu(seg), 0.3, max_seg=per)
+    assert np.array_equal(num.cpu().numpy(), rn)
+    assert np.array_equal(keep.cpu().numpy(), rk)
+
+
+def test_nms_batched_ragged(orc):
+    g = torch.Generator().manual_seed(9)
+    lens = [0, 1, 64, 0, 129, 700, 5, 513, 0]
+    parts = [_sorted_dets(50 + i, n) for i, n in enumerate(lens) if n > 0]
+    dets = torch.cat(parts, 0)
+    seg = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int32)
+    rk, rn = orc.nms_batched(dets.numpy(), seg.numpy(), 0.5)
+    for max_seg in (max(lens), None):
+        keep, num = be.nms_batched(cu(dets), cu(seg), 0.5, max_seg=max_seg)
+        assert np.array_equal(num.cpu().numpy(), rn)
+        assert np.array_equal(keep.cpu().numpy(), rk)
+    del g
+
+
+# ------------------------------------------------------------------------------------------
+# RoIAlign
+# ------------------------------------------------------------------------------------------
+def _align_case(seed, B, C, H, W, n_per, stride=16.0, shuffle=False):
+    g = torch.Generator().manual_seed(seed)
+    feat = torch.randn(B, C, H, W, generator=g)
+    rois = syn.rois_for_batch(seed + 1, B, n_per, H * stride, W * stride)
+    if shuffle:
+        rois = rois[torch.randperm(rois.size(0), generator=g)].contiguous()
+    return feat, rois
+
+
+@pytest.mark.parametrize("mode", [be.POOL_NONE, be.POOL_AVG, be.POOL_MAX])
+@pytest.mark.parametrize("case", [
+    dict(B=1, C=2, H=5, W=6, n_per=8, p=7),          # tiny map, generic path (R small? no: fast needs C%4)
+    dict(B=2, C=8, H=20, W=31, n_per=16, p=7),        # fast path, edge rois
+    dict(B=3, C=12, H=38, W=63, n_per=40, p=7),       # fast path
+    dict(B=2, C=6, H=19, W=23, n_per=12, p=7),        # C % 4 != 0 -> generic
+    dict(B=2, C=8, H=16, W=16, n_per=9, p=3),         # other pooled size -> generic
+    dict(B=2, C=4, H=12, W=40, n_per=10, p=7, shuffle=True),  # rois not grouped by image
+])
+def test_roi_align_forward(orc, case, mode):
+    p = case["p"]
+    feat, rois = _align_case(3, case["B"], case["C"], case["H"], case["W"], case["n_per"],
+                             shuffle=case.get("shuffle", False))
+    ah = p + 1 if mode == be.POOL_NONE else p  # NONE: sample an (p+1)x(p+1) grid directly
+    ref = orc.roi_align(feat.numpy(), rois.numpy(), ah, ah, 1 / 16.0, pool_mode=mode)
+    out = be.roi_align_forward(cu(feat), cu(rois), ah, ah, 1 / 16.0, mode)
+    close(out.cpu().numpy(), ref, what=f"roi_align fwd {case} mode {mode}")
+
+
+def test_roi_align_forward_bad_batch_index(orc):
+    feat, rois = _align_case(5, 2, 8, 20, 30, 8)
+    rois[3, 0] = 7.0   # image 7 of 2
+    rois[5, 0] = -1.0
+    out = be.roi_align_forward(cu(feat), cu(rois), 7, 7, 1 / 16.0, be.POOL_AVG).cpu().numpy()
+    assert (out[3] == 0).all() and (out[5] == 0).all()
+    good = [i for i in range(rois.size(0)) if i not in (3, 5)]
+    ref = orc.roi_align(feat.numpy(), rois[good].numpy(), 7, 7, 1 / 16.0, pool_mode=orc.POOL_AVG)
+    close(out[good], ref)
+
+
+def test_roi_align_c2_full_size(orc):
+    # config 2: Res-101 C4 at 600x1000 -> (4,1024,38,63), 4 x 256 rois, 7x7
+    feat, rois = _align_case(1, 4, 1024, 38, 63, 256)
+    ref = orc.roi_align(feat.numpy(), rois.numpy(), 7, 7, 1 / 16.0, pool_mode=orc.POOL_AVG)
+    out = be.roi_align_forward(cu(feat), cu(rois), 7, 7, 1 / 16.0, be.POOL_AVG)
+    close(out.cpu().numpy(), ref, what="C2 fwd")
+
+
+@pytest.mark.parametrize("mode", [be.POOL_NONE, be.POOL_AVG, be.POOL_MAX])
+@pytest.mark.parametrize("case", [
+    dict(B=2, C=8, H=20, W=31, n_per=16, p=7),
+    dict(B=3, C=12, H=38, W=63, n_per=40, p=7),
+    dict(B=2, C=6, H=19, W=23, n_per=12, p=7),
+    dict(B=2, C=8, H=16, W=16, n_per=9, p=3),
+    dict(B=2, C=4, H=50, W=75, n_per=30, p=7, shuffle=True),
+])
+def test_roi_align_backward(orc, case, mode):
+    p = case["p"]
+    feat, rois = _align_case(4, case["B"], case["C"], case["H"], case["W"], case["n_per"],
+                             shuffle=case.get("shuffle", False))
+    ah = p + 1 if mode == be.POOL_NONE else p
+    g = torch.Generator().manual_seed(44)
+    gout = torch.randn(rois.size(0), case["C"], ah, ah, generator=g)
+    ref = orc.roi_align_bwd(gout.numpy(), feat.numpy(), rois.numpy(), ah, ah, 1 / 16.0, pool_mode=mode)
+    gin = be.roi_align_backward(cu(gout), cu(rois), cu(feat), tuple(feat.shape), ah, ah, 1 / 16.0, mode)
+    close(gin.cpu().numpy(), ref, what=f"roi_align bwd {case} mode {mode}")
+    # accumulate form
+    base = torch.randn(feat.shape, generator=g)
+    acc = cu(base.clone())
+    be.roi_align_backward(cu(gout), cu(rois), cu(feat), tuple(feat.shape), ah, ah, 1 / 16.0, mode,
+                          grad_in=acc)
+    close(acc.cpu().numpy(), ref + base.numpy().astype(np.float64), what="bwd accumulate")
+
+
+def test_roi_align_backward_c2_full_size(orc):
+    feat, rois = _align_case(1, 4, 1024, 38, 63, 256)
+    g = torch.Generator().manual_seed(2)
+    gout = torch.randn(rois.size(0), 1024, 7, 7, generator=g)
+    ref = orc.roi_align_bwd(gout.numpy(), feat.numpy(), rois.numpy(), 7, 7, 1 / 16.0,
+                            pool_mode=orc.POOL_AVG)
+    gin = be.roi_align_backward(cu(gout), cu(rois), None, tuple(feat.shape), 7, 7, 1 / 16.0,
+                                be.POOL_AVG)
+    close(gin.cpu().numpy(), ref, what="C2 bwd")
+    # deterministic: the banded kernel has no atomics
+    gin2 = be.roi_align_backward(cu(gout), cu(rois), None, tuple(feat.shape), 7, 7, 1 / 16.0,
+                                 be.POOL_AVG)
+    assert torch.equal(gin, gin2)
+
+
+def test_roi_align_module_autograd(orc):
+    from rlobjectdetection_b200.model.roi_align.modules.roi_align import RoIAlign, RoIAlignAvg, RoIAlignMax
+    feat, rois = _align_case(6, 2, 8, 24, 30, 12)
+    g = torch.Generator().manual_seed(3)
+    for mod, mode, ah in ((RoIAlignAvg(7, 7, 1 / 16.0), orc.POOL_AVG, 7),
+                          (RoIAlignMax(7, 7, 1 / 16.0), orc.POOL_MAX, 7),
+                          (RoIAlign(8, 8, 1 / 16.0), orc.POOL_NONE, 8)):
+        x = cu(feat).requires_grad_(True)
+        y = mod(x, cu(rois))
+        gout = torch.randn(y.shape, generator=g)
+        y.backward(cu(gout))
+        close(y.detach().cpu().numpy(), orc.roi_align(feat.numpy(), rois.numpy(), ah, ah, 1 / 16.0, pool_mode=mode))
+        close(x.grad.cpu().numpy(), orc.roi_align_bwd(gout.numpy(), feat.numpy(), rois.numpy(), ah, ah,
+                                                      1 / 16.0, pool_mode=mode))
+    with pytest.raises(NotImplementedError):
+        RoIAlignAvg(7, 7, 1 / 16.0)(feat, rois)  # CPU tensors: no fallback
+
+
+def test_roi_align_properties_c3_size():
+    # config 3 size (8 images 800x1200 -> 50x75x1024, 300 rois each): size-independent checks.
+    # (1) constant map -> every fully-inside sample equals the constant; (2) linearity of the
+    # backward in grad_out; (3) <fwd(x), g> == <x, bwd(g)> (adjointness) within fp32 error.
+    B, C, H, W, n = 8, 1024, 50, 75, 300
+    rois = cu(syn.rois_for_batch(2, B, n, 800, 1200))
+    ones = torch.full((B, C, H, W), 2.5, device=DEV)
+    y = be.roi_align_forward(ones, rois, 7, 7, 1 / 16.0, be.POOL_AVG)
+    inside = (rois[:, 1] >= 0) & (rois[:, 2] >= 0) & (rois[:, 3] <= 1199 - 16) & (rois[:, 4] <= 799 - 16) \
+        & (rois[:, 3] >= rois[:, 1]) & (rois[:, 4] >= rois[:, 2])
+    yi = y[inside]
+    assert yi.numel() > 0 and (yi - 2.5).abs().max().item() <= 2.5 * 1e-6
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(B, C, H, W, generator=g).to(DEV)
+    g1 = torch.randn(B * n, C, 7, 7, generator=g).to(DEV)
+    fx = be.roi_align_forward(x, rois, 7, 7, 1 / 16.0, be.POOL_AVG)
+    b1 = be.roi_align_backward(g1, rois, None, (B, C, H, W), 7, 7, 1 / 16.0, be.POOL_AVG)
+    b2 = be.roi_align_backward(2.0 * g1, rois, None, (B, C, H, W), 7, 7, 1 / 16.0, be.POOL_AVG)
+    assert torch.equal(b2, 2.0 * b1)  # scaling by 2 is exact in fp32
+    lhs = (fx.double() * g1.double()).sum().item()
+    rhs = (x.double() * b1.double()).sum().item()
+    assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), abs(rhs), 1.0)
+
+
+# ------------------------------------------------------------------------------------------
+# RoIPool
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", [dict(B=2, C=8, H=20, W=31, n_per=16), dict(B=3, C=5, H=38, W=63, n_per=33)])
+def test_roi_pool(orc, case):
+    feat, rois = _align_case(12, case["B"], case["C"], case["H"], case["W"], case["n_per"])
+    ro, ra = orc.roi_pool(feat.numpy(), rois.numpy(), 7, 7, 1 / 16.0)
+    out, arg = be.roi_pool_forward(cu(feat), cu(rois), 7, 7, 1 / 16.0)
+    assert np.array_equal(out.cpu().numpy(), ro)     # max of fp32 values: bit-exact
+    assert np.array_equal(arg.cpu().numpy(), ra)     # flat NCHW argmax, -1 for empty bins
+    g = torch.Generator().manual_seed(13)
+    gout = torch.randn(out.shape, generator=g)
+    ref = orc.roi_pool_bwd(gout.numpy(), ra, tuple(feat.shape))
+    gin = be.roi_pool_backward(cu(gout), arg, tuple(feat.shape), 7, 7)
+    close(gin.cpu().numpy(), ref, what="roi_pool bwd")
+
+
+def test_roi_pool_module_autograd(orc):
+    from rlobjectdetection_b200.model.roi_pooling.modules.roi_pool import _RoIPooling
+    feat, rois = _align_case(14, 2, 8, 24, 30, 12)
+    x = cu(feat).requires_grad_(True)
+    y = _RoIPooling(7, 7, 1 / 16.0)(x, cu(rois))
+    ro, ra = orc.roi_pool(feat.numpy(), rois.numpy(), 7, 7, 1 / 16.0)
+    assert np.array_equal(y.detach().cpu().numpy(), ro)
+    gout = torch.randn(y.shape, generator=torch.Generator().manual_seed(1))
+    y.backward(cu(gout))
+    close(x.grad.cpu().numpy(), orc.roi_pool_bwd(gout.numpy(), ra, tuple(feat.shape)))
+
+
+# ------------------------------------------------------------------------------------------
+# box algebra + proposal layer
+# ------------------------------------------------------------------------------------------
+def test_box_algebra_vs_golden(orc, golden):
+    from rlobjectdetection_b200.model.rpn import bbox_transform as bt
+    dec = bt.bbox_transform_inv(cu(golden["dec_boxes"]), cu(golden["dec_deltas"]), 2).cpu().numpy()
+    ref = golden["dec_out"]
+    fin = np.isfinite(ref)
+    assert np.array_equal(np.isfinite(dec), fin)
+    # only exp() may differ (libdevice expf vs torch CPU): a few ulp on the exp-scaled terms
+    np.testing.assert_allclose(dec[fin], ref[fin], rtol=3e-6, atol=1e-4)
+    clp = bt.clip_boxes(cu(golden["dec_out"]).clone(), cu(golden["clip_im_info"]), 2).cpu().numpy()
+    assert np.array_equal(clp, golden["clip_out"])
+    o = bt.bbox_overlaps(cu(golden["ovl_anchors"]), cu(golden["ovl_gt"])).cpu().numpy()
+    assert np.array_equal(o, golden["ovl_out"])
+    o3 = bt.bbox_overlaps_batch(cu(golden["ovlb_anchors"]), cu(golden["ovlb_gt"])).cpu().numpy()
+    assert np.array_equal(o3, golden["ovlb_out3"])
+    o2 = bt.bbox_overlaps_batch(cu(golden["ovlb_anchors"][0]), cu(golden["ovlb_gt"])).cpu().numpy()
+    assert np.array_equal(o2, golden["ovlb_out2"])
+    # (B,N,5) anchors: columns 1:5 are the box
+    a5 = np.concatenate([np.zeros((2, golden["ovlb_anchors"].shape[1], 1), np.float32),
+                         golden["ovlb_anchors"]], 2)
+    o5 = bt.bbox_overlaps_batch(cu(a5), cu(golden["ovlb_gt"])).cpu().numpy()
+    assert np.array_equal(o5, golden["ovlb_out3"])
+
+
+def _proposal_parity(orc, scores, deltas, im_info, anchors, stride, pre, post, thresh):
+    rois, order, props, nkeep = be.proposal_forward(cu(scores), cu(deltas), cu(im_info), cu(anchors),
+                                                    stride, pre, post, thresh, return_taps=True)
+    rois, order, props, nkeep = (t.cpu().numpy() for t in (rois, order, props, nkeep))
+    # stage 1: sort order bit-exact, decoded boxes equal up to the expf ulp
+    o_rois, o_order, o_props, o_keep, o_nkeep = orc.proposal_layer(
+        scores.numpy(), deltas.numpy(), im_info.numpy(), anchors.numpy(), stride, pre, post, thresh,
+        return_taps=True)
+    assert np.array_equal(order, o_order)
+    np.testing.assert_allclose(props, o_props, rtol=3e-6, atol=2e-4)
+    # stage 2: NMS + padding bit-exact when the oracle runs on the GPU's decoded boxes
+    g_rois, _, _, g_keep, g_nkeep = orc.proposal_layer(
+        scores.numpy(), deltas.numpy(), im_info.numpy(), anchors.numpy(), stride, pre, post, thresh,
+        boxes_override=props, return_taps=True)
+    assert np.array_equal(nkeep, g_nkeep)
+    assert np.array_equal(rois, g_rois)
+    return rois
+
+
+@pytest.mark.parametrize("tag", ["test", "train", "all"])
+def test_proposal_layer_golden(orc, golden, tag):
+    stride, pre, post, A = [int(v) for v in golden[f"prop_{tag}_cfg"]]
+    t = lambda k: torch.from_numpy(golden[f"prop_{tag}_{k}"])  # noqa: E731
+    rois = _proposal_parity(orc, t("scores"), t("deltas"), t("im_info"), t("anchors"), stride, pre, post, 0.7)
+    ref = golden[f"prop_{tag}_rois"]  # produced by the reference's own _ProposalLayer
+    assert np.array_equal(rois[:, :, 0], ref[:, :, 0])
+    assert np.array_equal(rois[:, :, 1:].any(axis=2), ref[:, :, 1:].any(axis=2))
+    np.testing.assert_allclose(rois, ref, rtol=3e-6, atol=2e-4)
+
+
+@pytest.mark.parametrize("cfgname", ["c1_train", "c4_test", "c4_train", "ties"])
+def test_proposal_layer_full_size(orc, cfgname):
+    from rlobjectdetection_b200.model.rpn.generate_anchors import generate_anchors
+    if cfgname == "c1_train":   # VGG-16 600x1000: 37x62, A=9, 12000 -> 2000
+        B, H, W, scales, pre, post, imh, imw = 1, 37, 62, [8, 16, 32], 12000, 2000, 600, 1000
+    elif cfgname == "c4_test":  # COCO 800x1200: 50x75, A=12, 6000 -> 300
+        B, H, W, scales, pre, post, imh, imw = 3, 50, 75, [4, 8, 16, 32], 6000, 300, 800, 1200
+    elif cfgname == "c4_train":
+        B, H, W, scales, pre, post, imh, imw = 2, 50, 75, [4, 8, 16, 32], 12000, 2000, 800, 1200
+    else:                       # heavy score ties: order must be "lower anchor index first"
+        B, H, W, scales, pre, post, imh, imw = 2, 20, 30, [8, 16, 32], 1000, 100, 320, 480
+    anchors = torch.from_numpy(generate_anchors(scales=np.array(scales), ratios=np.array([0.5, 1, 2]))).float()
+    A = anchors.size(0)
+    scores, deltas, im_info = syn.rpn_outputs(3, B, A, H, W, imh, imw)
+    if cfgname == "ties":
+        scores[:, A:] = (scores[:, A:] * 16).floor() / 16  # 16 distinct values over 5400 anchors
+    _proposal_parity(orc, scores, deltas, im_info, anchors, 16, pre, post, 0.7)
+
+
+def test_proposal_module_and_cfg(orc):
+    from rlobjectdetection_b200.model.rpn.proposal_layer import _ProposalLayer
+    from rlobjectdetection_b200.model.utils.config import cfg
+    layer = _ProposalLayer(16, [8, 16, 32], [0.5, 1, 2])
+    scores, deltas, im_info = syn.rpn_outputs(5, 2, 9, 14, 21, 224, 336)
+    old = (cfg.TEST.RPN_PRE_NMS_TOP_N, cfg.TEST.RPN_POST_NMS_TOP_N)
+    cfg.TEST.RPN_PRE_NMS_TOP_N, cfg.TEST.RPN_POST_NMS_TOP_N = 600, 50
+    try:
+        rois = layer((cu(scores), cu(deltas), cu(im_info), "TEST"))
+    finally:
+        cfg.TEST.RPN_PRE_NMS_TOP_N, cfg.TEST.RPN_POST_NMS_TOP_N = old
+    assert rois.shape == (2, 50, 5)
+    assert (rois[1, :, 0] == 1).all()  # image index on every row, padding included
+    ref = orc.proposal_layer(scores.numpy(), deltas.numpy(), im_info.numpy(),
+                             layer._anchors.cpu().numpy(), 16, 600, 50, 0.7)
+    np.testing.assert_allclose(rois.cpu().numpy(), ref, rtol=3e-6, atol=2e-4)
+    with pytest.raises(NotImplementedError):
+        layer((scores, deltas, im_info, "TEST"))
+
+
+# ------------------------------------------------------------------------------------------
+# RL refinement
+# ------------------------------------------------------------------------------------------
+def test_reward_vs_golden(orc, golden):
+    r, l, w = be.action_reward(cu(golden["iou_dt"][None]), cu(golden["iou_gt"][None]), cu(golden["act16"]),
+                               crowd=cu(golden["iou_crowd"][None]), mode=be.IOU_COCO, iou_thres=0.0,
+                               pos_wratio=2.0, neg_wratio=0.5)
+    assert np.array_equal(r[0].cpu().numpy(), golden["reward_out"].astype(np.float32))  # bit-exact
+    assert np.array_equal(l[0].cpu().numpy(), golden["reward_label"].astype(np.float32))
+    np.testing.assert_allclose(w[0].cpu().numpy(), golden["reward_weight"], rtol=1e-6)
+
+
+@pytest.mark.parametrize("mode", [be.IOU_COCO, be.IOU_RCNN])
+@pytest.mark.parametrize("nact", [16, 56])
+def test_reward_c3_size(orc, mode, nact):
+    # config 3: 8 images x 300 boxes x 16 (and the reference default 56) actions x 20 gt
+    B, N, G = 8, 300, 20
+    g = torch.Generator().manual_seed(2)
+    boxes = torch.stack([syn.random_boxes(g, N, 800, 1200) for _ in range(B)], 0)
+    gt, crowd = syn.gt_boxes(21, B, G, 800, 1200)
+    ngt = torch.tensor([20, 0, 7, 20, 1, 20, 13, 20], dtype=torch.int32)
+    if mode == be.IOU_COCO:
+        boxes, gt = syn.to_xywh(boxes), syn.to_xywh(gt)
+    delta = [.5, .25] if nact == 16 else [.5, .25, .125, .0625, .03125, .015625, .008]
+    act = orc.action_table(delta)
+    cr = crowd if mode == be.IOU_COCO else None
+    rr, rl, rw = orc.action_reward(boxes.numpy(), gt.numpy(), act, crowd=None if cr is None else cr.numpy(),
+                                   ngt=ngt.numpy(), mode=mode, iou_thres=0.0, pos_wratio=1.5, neg_wratio=0.75)
+    r, l, w = be.action_reward(cu(boxes), cu(gt), cu(act), crowd=None if cr is None else cu(cr), ngt=cu(ngt),
+                               mode=mode, iou_thres=0.0, pos_wratio=1.5, neg_wratio=0.75)
+    assert np.array_equal(r.cpu().numpy(), rr)  # same IEEE ops in the same order: bit-exact
+    assert np.array_equal(l.cpu().numpy(), rl)
+    np.testing.assert_allclose(w.cpu().numpy(), rw, rtol=1e-6)
+
+
+def test_move_from_act_vs_golden(orc, golden):
+    from rlobjectdetection_b200.model.Reinforcement.action import Action
+    act = Action([0.5, 0.25])
+    for k in (1, 5, 40, 1000):
+        bb = golden["move_in_boxes"].copy()
+        moved, prec = act.move_from_act(bb, golden["move_preds"], golden["move_targets"], k, device=DEV)
+        rb, rp = orc.move_from_act(golden["move_in_boxes"], golden["move_preds"], golden["move_targets"],
+                                   golden["act16"], k)
+        assert np.array_equal(moved, rb) and prec == rp
+        if k in (1, 5):  # the reference's own outputs
+            assert np.array_equal(moved, golden[f"move_k{k}_boxes"]) and prec == float(golden[f"move_k{k}_prec"])
+
+
+def test_move_from_act_corners_matches_reward():
+    # refining an x1y1x2y2 roi tensor in place: the moved box's IoU gain equals the reward
+    B, N, G = 2, 64, 5
+    g = torch.Generator().manual_seed(31)
+    boxes = torch.stack([syn.random_boxes(g, N, 600, 1000) for _ in range(B)], 0)
+    gt, _ = syn.gt_boxes(32, B, G, 600, 1000)
+    rois = torch.cat([torch.arange(B).float()[:, None, None].expand(B, N, 1), boxes], 2).contiguous()
+    act = cu(np.asarray([[0.5, 0, 0, 0], [-0.5, 0, 0, 0], [0, 0.25, 0, 0], [0, 0, 0.25, 0], [0, 0, 0, -0.25]],
+                        dtype=np.float32))
+    r, l, _ = be.action_reward(cu(boxes), cu(gt), act, mode=be.IOU_RCNN)
+    refined = cu(rois).clone()
+    moved = be.move_from_act(refined, r, l, act, N, corners=True)
+    zero_act = torch.zeros(1, 4, device=DEV)
+    before = be.action_reward(cu(boxes), cu(gt), zero_act, mode=be.IOU_RCNN, want_labels=False)
+    # IoU of refined boxes vs gt, via a zero action on the refined boxes: reward 0, so use overlaps
+    from rlobjectdetection_b200.model.rpn.bbox_transform import bbox_overlaps_batch
+    iou_new = bbox_overlaps_batch(refined[:, :, 1:5].contiguous(), cu(gt)).max(dim=2).values
+    iou_old = bbox_overlaps_batch(cu(boxes), cu(gt)).max(dim=2).values
+    best = r.max(dim=2).values
+    gain = torch.where(best > 0, best, torch.zeros_like(best))
+    assert torch.equal(iou_new - iou_old, gain)
+    assert int(moved.item()) == int((best > 0).sum().item())
+    assert (before == 0).all()
+    assert torch.equal(refined[:, :, 0], cu(rois)[:, :, 0])
+
+
+# ------------------------------------------------------------------------------------------
+# whole step
+# ------------------------------------------------------------------------------------------
+def test_hotpath_step_matches_oracle_chain(orc):
+    from rlobjectdetection_b200.hotpath import DetectRefineStep
+    B, C, H, W, G = 2, 16, 25, 38, 6
+    step = DetectRefineStep(cfg_key="TEST", backward=True)
+    A = step.proposal._num_anchors
+    scores, deltas, im_info = syn.rpn_outputs(9, B, A, H, W, H * 16, W * 16)
+    g = torch.Generator().manual_seed(10)
+    feat = torch.randn(B, C, H, W, generator=g)
+    gt, _ = syn.gt_boxes(11, B, G, H * 16, W * 16)
+    gp = torch.randn(B * 300, C, 7, 7, generator=g)
+    out = step(cu(scores), cu(deltas), cu(im_info), cu(feat), cu(gt), cu(gp))
+    rois = out["rois"].cpu().numpy()
+    pooled_ref = orc.roi_align(feat.numpy(), rois.reshape(-1, 5), 7, 7, 1 / 16.0, pool_mode=orc.POOL_AVG)
+    close(out["pooled"].cpu().numpy(), pooled_ref)
+    rr, rl, _ = orc.action_reward(rois[:, :, 1:5], gt.numpy(), step.action.actDeltas, mode=orc.MODE_RCNN)
+    assert np.array_equal(out["reward"].cpu().numpy(), rr) and np.array_equal(out["label"].cpu().numpy(), rl)
+    refined = out["refined"].cpu().numpy()
+    close(out["pooled_refined"].cpu().numpy(),
+          orc.roi_align(feat.numpy(), refined.reshape(-1, 5), 7, 7, 1 / 16.0, pool_mode=orc.POOL_AVG))
+    close(out["grad_feat"].cpu().numpy(),
+          orc.roi_align_bwd(gp.numpy(), feat.numpy(), refined.reshape(-1, 5), 7, 7, 1 / 16.0, pool_mode=orc.POOL_AVG))
