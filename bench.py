@@ -136,48 +136,45 @@ def workload_config(images_per_gpu, world, arm):
 # clocks
 # ------------------------------------------------------------------------------------------
 class ClockSampler:
-    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled DURING the timed region: an NVML polling thread
+    (every 2 ms -- a timed region of tens of milliseconds is too short for `nvidia-smi -lms`)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+               0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index):
-        self.idx = gpu_index
-        self.proc = None
+        import threading
+        self.idx, self.samples, self.mask, self.max_mhz = gpu_index, [], 0, None
+        self._stop = threading.Event()
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self.err = None
+
+    def _run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[self.idx]) if visible and visible.split(",")[self.idx].isdigit() else self.idx
+            h = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            while not self._stop.is_set():
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                time.sleep(0.002)
+        except Exception as e:  # noqa: BLE001 -- clocks are reported, never fatal
+            self.err = repr(e)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
-                text=True)
-        except OSError:
-            self.proc = None
+        self._thread.start()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            out, _ = self.proc.communicate(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-            out, _ = self.proc.communicate()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in out.strip().splitlines():
-            p = [x.strip() for x in ln.split(",")]
-            if len(p) < 9:
-                continue
-            try:
-                sm.append(float(p[1]))
-                mx.append(float(p[2]))
-            except ValueError:
-                continue
-            for name, v in zip(names, p[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self._stop.set()
+        self._thread.join(timeout=5)
+        reasons = sorted(name for bit, name in self.REASONS.items() if self.mask & bit)
+        out = {"sm_mhz": statistics.median(self.samples) if self.samples else None,
+               "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(self.samples)}
+        if self.err:
+            out["error"] = self.err
+        return out
 
 
 # ------------------------------------------------------------------------------------------

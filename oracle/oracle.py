@@ -190,12 +190,16 @@ def roi_pool(feat, rois, ph, pw, scale):
     return out, arg
 
 
-def roi_pool_bwd(grad_out, argmax, feat_shape):
+def roi_pool_bwd(grad_out, argmax, feat_shape, rois, scale):
+    """roi_pooling_kernel.cu:128-203 (the gather's visiting rules included); fp64 (B,C,H,W)."""
     grad_out = _f32(grad_out)
     argmax = np.ascontiguousarray(argmax, dtype=np.int32)
+    rois = _f32(rois)
+    B, C, H, W = feat_shape
+    R, _, ph, pw = grad_out.shape
     gin = np.zeros(feat_shape, dtype=np.float64)
-    lib().orc_roi_pool_bwd(_p(grad_out, c_f), _p(argmax, c_i), ctypes.c_long(grad_out.size),
-                           ctypes.c_long(gin.size), _p(gin, c_d))
+    lib().orc_roi_pool_bwd(_p(grad_out, c_f), _p(argmax, c_i), _p(rois, c_f), B, C, H, W, R, ph, pw,
+                           ctypes.c_float(scale), _p(gin, c_d))
     return gin
 
 

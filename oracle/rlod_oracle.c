@@ -313,13 +313,46 @@ ORC_API void orc_roi_pool_fwd(const float *feat, const float *rois, int B, int C
   }
 }
 
-/* RoIPool backward, roi_pooling_kernel.cu:128-203: every bottom element sums top_diff of the
- * bins whose argmax points at it.  Equivalent scatter form, fp64 accumulate. */
-ORC_API void orc_roi_pool_bwd(const float *top_diff, const int *argmax, long n_top,
-                              long n_bottom, double *grad_in) {
-  for (long i = 0; i < n_top; ++i) {
-    int a = argmax[i];
-    if (a >= 0 && a < n_bottom) grad_in[a] += (double)top_diff[i];
+/* RoIPool backward, roi_pooling_kernel.cu:128-203, restated as the scatter that produces the
+ * same sums as the reference's gather: a pooled bin (n,c,ph,pw) whose argmax is the input
+ * element (h,w) contributes its top_diff iff the gather at (h,w) would have visited it, i.e.
+ * (h,w) lies inside the ROUNDED roi [start,end] (:161-165 -- false everywhere for an inverted
+ * roi, whose gradient the reference therefore drops) and (ph,pw) is in the feasible bin range
+ * the gather derives from (h,w) (:178-186).  fp64 accumulate (the reference adds in fp32,
+ * roi-major); grad_in (B,C,H,W) fp64, zeroed by the caller (the reference overwrites, :201). */
+ORC_API void orc_roi_pool_bwd(const float *top_diff, const int *argmax, const float *rois, int B,
+                              int C, int H, int W, int R, int ph_n, int pw_n, float scale,
+                              double *grad_in) {
+  long n_bottom = (long)B * C * H * W;
+  for (int n = 0; n < R; ++n) {
+    const float *roi = rois + (size_t)n * 5;
+    int roi_start_w = (int)roundf(roi[1] * scale);
+    int roi_start_h = (int)roundf(roi[2] * scale);
+    int roi_end_w = (int)roundf(roi[3] * scale);
+    int roi_end_h = (int)roundf(roi[4] * scale);
+    int roi_width = (int)fmaxf((float)(roi_end_w - roi_start_w + 1), 1.f);
+    int roi_height = (int)fmaxf((float)(roi_end_h - roi_start_h + 1), 1.f);
+    float bin_size_h = (float)roi_height / (float)ph_n;
+    float bin_size_w = (float)roi_width / (float)pw_n;
+    for (int c = 0; c < C; ++c)
+      for (int ph = 0; ph < ph_n; ++ph)
+        for (int pw = 0; pw < pw_n; ++pw) {
+          size_t ti = (((size_t)n * C + c) * ph_n + ph) * pw_n + pw;
+          int a = argmax[ti];
+          if (a < 0 || a >= n_bottom) continue;
+          int w = a % W, h = (a / W) % H;
+          if (!(w >= roi_start_w && w <= roi_end_w && h >= roi_start_h && h <= roi_end_h)) continue;
+          int phstart = (int)floorf((float)(h - roi_start_h) / bin_size_h);
+          int phend = (int)ceilf((float)(h - roi_start_h + 1) / bin_size_h);
+          int pwstart = (int)floorf((float)(w - roi_start_w) / bin_size_w);
+          int pwend = (int)ceilf((float)(w - roi_start_w + 1) / bin_size_w);
+          phstart = (int)fminf(fmaxf((float)phstart, 0.f), (float)ph_n);
+          phend = (int)fminf(fmaxf((float)phend, 0.f), (float)ph_n);
+          pwstart = (int)fminf(fmaxf((float)pwstart, 0.f), (float)pw_n);
+          pwend = (int)fminf(fmaxf((float)pwend, 0.f), (float)pw_n);
+          if (ph < phstart || ph >= phend || pw < pwstart || pw >= pwend) continue;
+          grad_in[a] += (double)top_diff[ti];
+        }
   }
 }
 

@@ -8,7 +8,8 @@
 //
 // The reference's backward is a gather that makes every one of B*C*H*W threads loop over
 // ALL R rois (O(B*C*H*W*R)); here the saved argmax turns it into a single pass over the
-// R*C*ph*pw gradients with one fp32 RED each -- the only work that exists.
+// R*C*ph*pw gradients with at most one fp32 RED each -- the only work that exists -- while
+// keeping the gather's visiting rules, so malformed rois lose their gradient exactly as there.
 #include "rlod_common.cuh"
 
 namespace rlod {
@@ -61,13 +62,42 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// A pooled bin sends its gradient to its argmax element iff the reference's gather at that
+// element would have visited the bin (roi_pooling_kernel.cu:161-186): the element lies inside
+// the ROUNDED roi (never true for an inverted roi: the reference drops that gradient) and the
+// bin is inside the feasible range derived back from the element.
 __global__ void __launch_bounds__(256)
-    k_roi_pool_bwd(const float *__restrict__ gout, const int *__restrict__ argmax, long long total,
-                   long long n_bottom, float *__restrict__ gin) {
+    k_roi_pool_bwd(const float *__restrict__ gout, const int *__restrict__ argmax,
+                   const float *__restrict__ rois, int C, int H, int W, int PH, int PW, float scale,
+                   long long total, long long n_bottom, float *__restrict__ gin) {
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     const int a = __ldg(argmax + idx);
-    if (a >= 0 && a < n_bottom) atomicAdd(gin + a, __ldg(gout + idx));
+    if (a < 0 || a >= n_bottom) continue;
+    const int pw = (int)(idx % PW);
+    const int ph = (int)((idx / PW) % PH);
+    const int n = (int)(idx / ((long long)PW * PH * C));
+    const float *roi = rois + (size_t)n * 5;
+    const int roi_start_w = (int)roundf(__fmul_rn(roi[1], scale));
+    const int roi_start_h = (int)roundf(__fmul_rn(roi[2], scale));
+    const int roi_end_w = (int)roundf(__fmul_rn(roi[3], scale));
+    const int roi_end_h = (int)roundf(__fmul_rn(roi[4], scale));
+    const int w = a % W, h = (a / W) % H;
+    if (!(w >= roi_start_w && w <= roi_end_w && h >= roi_start_h && h <= roi_end_h)) continue;
+    const int roi_width = max(roi_end_w - roi_start_w + 1, 1);
+    const int roi_height = max(roi_end_h - roi_start_h + 1, 1);
+    const float bin_h = __fdiv_rn((float)roi_height, (float)PH);
+    const float bin_w = __fdiv_rn((float)roi_width, (float)PW);
+    int phstart = (int)floorf(__fdiv_rn((float)(h - roi_start_h), bin_h));
+    int phend = (int)ceilf(__fdiv_rn((float)(h - roi_start_h + 1), bin_h));
+    int pwstart = (int)floorf(__fdiv_rn((float)(w - roi_start_w), bin_w));
+    int pwend = (int)ceilf(__fdiv_rn((float)(w - roi_start_w + 1), bin_w));
+    phstart = min(max(phstart, 0), PH);
+    phend = min(max(phend, 0), PH);
+    pwstart = min(max(pwstart, 0), PW);
+    pwend = min(max(pwend, 0), PW);
+    if (ph < phstart || ph >= phend || pw < pwstart || pw >= pwend) continue;
+    atomicAdd(gin + a, __ldg(gout + idx));
   }
 }
 
@@ -90,8 +120,9 @@ RLOD_API int rlod_roi_pool_forward(const float *feat, const float *rois, int B, 
   return launch_status();
 }
 
-RLOD_API int rlod_roi_pool_backward(const float *grad_out, const int *argmax, int B, int C, int H,
-                                    int W, int R, int ph, int pw, int accumulate, float *grad_in,
+RLOD_API int rlod_roi_pool_backward(const float *grad_out, const int *argmax, const float *rois,
+                                    int B, int C, int H, int W, int R, int ph, int pw,
+                                    float spatial_scale, int accumulate, float *grad_in,
                                     rlod_stream_t stream) {
   if (B < 0 || C < 0 || H < 1 || W < 1 || R < 0 || ph < 1 || pw < 1) return RLOD_EINVAL;
   if ((long long)B * C * H * W >= (1LL << 31)) return RLOD_EUNSUPPORTED;
@@ -101,10 +132,12 @@ RLOD_API int rlod_roi_pool_backward(const float *grad_out, const int *argmax, in
   const long long n_bottom = (long long)B * C * H * W;
   if (!accumulate) cudaMemsetAsync(grad_in, 0, (size_t)n_bottom * sizeof(float), st);
   if (R == 0) return launch_status();
-  if (!grad_out || !argmax) return RLOD_EINVAL;
+  if (!grad_out || !argmax || !rois) return RLOD_EINVAL;
   const long long total = (long long)R * C * ph * pw;
   const long long blocks = cdiv(total, 256);
   const unsigned grid = (unsigned)(blocks < (1LL << 30) ? blocks : (1LL << 30));
-  RLOD_LAUNCH(RLOD_KERNEL_POOL_BWD, st, k_roi_pool_bwd<<<grid, 256, 0, st>>>(grad_out, argmax, total, n_bottom, grad_in));
+  RLOD_LAUNCH(RLOD_KERNEL_POOL_BWD, st,
+              k_roi_pool_bwd<<<grid, 256, 0, st>>>(grad_out, argmax, rois, C, H, W, ph, pw,
+                                                   spatial_scale, total, n_bottom, grad_in));
   return launch_status();
 }

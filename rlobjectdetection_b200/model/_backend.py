@@ -41,7 +41,7 @@ SIGNATURES = {
     "rlod_roi_align_backward": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _I, _I, _P, _P,
                                      _Z, _P]),
     "rlod_roi_pool_forward": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P]),
-    "rlod_roi_pool_backward": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "rlod_roi_pool_backward": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P, _P]),
     "rlod_proposal_workspace_bytes": (_Z, [_I, _I, _I, _I, _I, _I]),
     "rlod_proposal_forward": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P,
                                    _P, _Z, _P]),
@@ -233,17 +233,18 @@ def roi_pool_forward(features, rois, ph, pw, scale):
     return out, argmax
 
 
-def roi_pool_backward(grad_out, argmax, feature_size, ph, pw, grad_in=None):
-    require_cuda("roi_pool backward", grad_out, argmax)
-    grad_out = f32c(grad_out)
+def roi_pool_backward(grad_out, argmax, rois, feature_size, ph, pw, scale, grad_in=None):
+    require_cuda("roi_pool backward", grad_out, argmax, rois)
+    grad_out, rois = f32c(grad_out), f32c(rois)
     B, C, H, W = feature_size
     R = grad_out.size(0)
     accumulate = grad_in is not None
     if grad_in is None:
         grad_in = torch.empty(B, C, H, W, dtype=torch.float32, device=grad_out.device)
     with torch.cuda.device(grad_out.device):
-        check(lib().rlod_roi_pool_backward(ptr(grad_out), ptr(argmax), B, C, H, W, R, ph, pw,
-                                           int(accumulate), ptr(grad_in), stream_of(grad_out)),
+        check(lib().rlod_roi_pool_backward(ptr(grad_out), ptr(argmax), ptr(rois), B, C, H, W, R, ph,
+                                           pw, float(scale), int(accumulate), ptr(grad_in),
+                                           stream_of(grad_out)),
               "rlod_roi_pool_backward")
     return grad_in
 

@@ -8,16 +8,16 @@ class _RoIPoolOp(Function):
     @staticmethod
     def forward(ctx, features, rois, ph, pw, scale):
         out, argmax = be.roi_pool_forward(features, rois, ph, pw, scale)
-        ctx.cfg = (int(ph), int(pw), tuple(features.shape))
-        ctx.save_for_backward(argmax)
+        ctx.cfg = (int(ph), int(pw), float(scale), tuple(features.shape))
+        ctx.save_for_backward(argmax, rois)
         ctx.mark_non_differentiable(argmax)
         return out, argmax
 
     @staticmethod
     def backward(ctx, grad_output, _grad_argmax):
-        ph, pw, fsize = ctx.cfg
-        (argmax,) = ctx.saved_tensors
-        return be.roi_pool_backward(grad_output, argmax, fsize, ph, pw), None, None, None, None
+        ph, pw, scale, fsize = ctx.cfg
+        argmax, rois = ctx.saved_tensors
+        return be.roi_pool_backward(grad_output, argmax, rois, fsize, ph, pw, scale), None, None, None, None
 
 
 class RoIPoolFunction:

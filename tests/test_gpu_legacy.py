@@ -148,7 +148,7 @@ def test_roi_pool_vs_legacy(orc, legacy, shape):
     torch.cuda.synchronize()
     bref = bottom.cpu().numpy()
     bscale = np.abs(bref).max()
-    np.testing.assert_allclose(orc.roi_pool_bwd(gout.cpu().numpy(), ra, (B, C, H, W)), bref, rtol=1e-5,
-                               atol=1e-5 * bscale)
-    gin = be.roi_pool_backward(gout, am, (B, C, H, W), 7, 7).cpu().numpy()
+    np.testing.assert_allclose(orc.roi_pool_bwd(gout.cpu().numpy(), ra, (B, C, H, W), rois.numpy(), 1 / 16.0),
+                               bref, rtol=1e-5, atol=1e-5 * bscale)
+    gin = be.roi_pool_backward(gout, am, r, (B, C, H, W), 7, 7, 1 / 16.0).cpu().numpy()
     np.testing.assert_allclose(gin, bref, rtol=1e-5, atol=1e-5 * bscale)

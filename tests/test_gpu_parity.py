@@ -286,8 +286,8 @@ def test_roi_pool(orc, case):
     assert np.array_equal(arg.cpu().numpy(), ra)     # flat NCHW argmax, -1 for empty bins
     g = torch.Generator().manual_seed(13)
     gout = torch.randn(out.shape, generator=g)
-    ref = orc.roi_pool_bwd(gout.numpy(), ra, tuple(feat.shape))
-    gin = be.roi_pool_backward(cu(gout), arg, tuple(feat.shape), 7, 7)
+    ref = orc.roi_pool_bwd(gout.numpy(), ra, tuple(feat.shape), rois.numpy(), 1 / 16.0)
+    gin = be.roi_pool_backward(cu(gout), arg, cu(rois), tuple(feat.shape), 7, 7, 1 / 16.0)
     close(gin.cpu().numpy(), ref, what="roi_pool bwd")
 
 
@@ -300,7 +300,7 @@ def test_roi_pool_module_autograd(orc):
     assert np.array_equal(y.detach().cpu().numpy(), ro)
     gout = torch.randn(y.shape, generator=torch.Generator().manual_seed(1))
     y.backward(cu(gout))
-    close(x.grad.cpu().numpy(), orc.roi_pool_bwd(gout.numpy(), ra, tuple(feat.shape)))
+    close(x.grad.cpu().numpy(), orc.roi_pool_bwd(gout.numpy(), ra, tuple(feat.shape), rois.numpy(), 1 / 16.0))
 
 
 # ------------------------------------------------------------------------------------------
