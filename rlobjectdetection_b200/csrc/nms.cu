@@ -241,13 +241,136 @@ __global__ void __launch_bounds__(kSmallThreads)
   o.finish(seg, off, n, s_total, t, kSmallThreads);
 }
 
+// ----------------------------------------------------------------------------------------
+// kept-list NMS for a bounded number of keeps (the proposal layer: post_nms_topN = 300).
+// One CTA (512 threads) per segment walks the score-sorted boxes 64 at a time and never
+// materialises the n x n mask: a chunk is tested against the boxes kept SO FAR (held in
+// shared memory), then its 64 x 64 diagonal tile is resolved, survivors are appended.  Work
+// is n_visited x n_kept pair tests instead of n^2 / 2, and the walk stops at max_keep keeps
+// -- typically after a few hundred of the 6000 boxes.  Same greedy result as the mask scan:
+// box j is suppressed iff some kept earlier box i has IoU(i, j) > thresh.
+// smem: float4 kbox[max_keep]; float kSa[max_keep].
+// ----------------------------------------------------------------------------------------
+constexpr int kLazyThreads = 512;
+constexpr int kLazyMaxKeep = 512;
+
+__global__ void __launch_bounds__(kLazyThreads)
+    k_nms_lazy(NmsSegs segs, float thresh, int max_keep, NmsOut o) {
+  extern __shared__ __align__(16) unsigned char lz_raw[];
+  float4 *kbox = reinterpret_cast<float4 *>(lz_raw);
+  float *kSa = reinterpret_cast<float *>(kbox + max_keep);
+  __shared__ float4 cbox[64];
+  __shared__ float2 cwh[64];
+  __shared__ unsigned supw[kLazyThreads / 32];
+  __shared__ unsigned diag32[64][2];
+  __shared__ unsigned long long s_kept;
+  __shared__ int s_base, s_total;
+  const int seg = blockIdx.x;
+  int off, n;
+  segs.get(seg, off, n);
+  const int nblk = (n + 63) >> 6;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int c = t & 63, slice = t >> 6;
+  constexpr int kSlices = kLazyThreads / 64;
+  const bool zf = thresh >= 0.f && thresh < 1e30f;
+  if (t == 0) s_total = 0;
+  float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (t < 64 && t < n) nxt = segs.load_box(off + t);
+  __syncthreads();
+  for (int k = 0; k < nblk; ++k) {
+    const int valid = min(64, n - k * 64);
+    if (t < 64) {
+      cbox[t] = nxt;
+      cwh[t] = make_float2(__fadd_rn(__fsub_rn(nxt.z, nxt.x), 1.f), __fadd_rn(__fsub_rn(nxt.w, nxt.y), 1.f));
+      const int j = (k + 1) * 64 + t;
+      nxt = (j < n) ? segs.load_box(off + j) : make_float4(0.f, 0.f, 0.f, 0.f);  // prefetch
+    }
+    __syncthreads();
+    const int K = s_total;
+    // (a) candidate c against the kept list, slice-strided; kept-box reads are broadcasts
+    {
+      const float4 cb = cbox[c];
+      const float2 cw = cwh[c];
+      bool sup = false;
+      if (c < valid)
+        for (int kk = slice; kk < K && !sup; kk += kSlices) sup = iou_gt(kbox[kk], kSa[kk], cb, cw, thresh, zf);
+      const unsigned bal = __ballot_sync(0xffffffffu, sup);
+      if (lane == 0) supw[warp] = bal;
+    }
+    // (b) diagonal tile: row i vs the later boxes j of the same chunk
+#pragma unroll
+    for (int q = 0; q < 4096 / kLazyThreads; ++q) {
+      const int p = t + q * kLazyThreads;
+      const int i = p >> 6, j = p & 63;
+      bool bit = false;
+      if (j > i && j < valid) {
+        const float2 wi = cwh[i];
+        bit = iou_gt(cbox[i], __fmul_rn(wi.x, wi.y), cbox[j], cwh[j], thresh, zf);
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, bit);
+      if (lane == 0) diag32[i][j >> 5] = bal;
+    }
+    __syncthreads();
+    if (t == 0) {
+      unsigned lo = 0u, hi = 0u;
+#pragma unroll
+      for (int w = 0; w < kLazyThreads / 32; w += 2) {
+        lo |= supw[w];
+        hi |= supw[w + 1];
+      }
+      unsigned long long r = ((unsigned long long)hi << 32) | lo;
+      if (valid < 64) r |= ~0ull << valid;
+      unsigned long long kb = 0ull;
+#pragma unroll 8
+      for (int i = 0; i < 64; ++i) {
+        if (!((r >> i) & 1ull)) {
+          kb |= 1ull << i;
+          r |= ((unsigned long long)diag32[i][1] << 32) | diag32[i][0];
+        }
+      }
+      const int total = K;
+      int cnt = __popcll(kb);
+      if (total + cnt > max_keep) {
+        int need = max_keep - total;
+        unsigned long long trimmed = 0ull, rest = kb;
+        while (need-- > 0) {
+          const unsigned long long low = rest & (~rest + 1ull);
+          trimmed |= low;
+          rest ^= low;
+        }
+        kb = trimmed;
+        cnt = __popcll(kb);
+      }
+      s_kept = kb;
+      s_base = total;
+      s_total = total + cnt;
+    }
+    __syncthreads();
+    const unsigned long long kb = s_kept;
+    const int total = s_total;
+    if (t < 64 && ((kb >> t) & 1ull)) {
+      const int rank = s_base + __popcll(kb & ((1ull << t) - 1ull));
+      const float4 b = cbox[t];
+      const float2 w = cwh[t];
+      kbox[rank] = b;
+      kSa[rank] = __fmul_rn(w.x, w.y);
+      o.emit(seg, off, rank, k * 64 + t, segs);
+    }
+    if (total >= max_keep) break;  // CTA-uniform
+    __syncthreads();
+  }
+  __syncthreads();
+  o.finish(seg, off, n, s_total, t, kLazyThreads);
+}
+
 static size_t small_smem(int max_pad) {
   const int nblk = max_pad / 64;
   return (size_t)max_pad * (sizeof(float4) + sizeof(float2)) +
          (size_t)nblk * (max_pad + 1) * sizeof(unsigned long long);
 }
 
-size_t nms_mask_bytes(int nseg, int max_seg) {
+size_t nms_mask_bytes(int nseg, int max_seg, int max_keep) {
+  if (max_keep > 0 && max_keep <= kLazyMaxKeep) return 0;  // kept-list path: no mask
   if (nseg <= 0 || max_seg <= 0) return 0;
   const size_t nblk = (size_t)(max_seg + 63) / 64;
   return (size_t)nseg * nblk * nblk * 64 * sizeof(unsigned long long);
@@ -260,6 +383,13 @@ int nms_launch(const NmsSegs &segs, int nseg, int max_seg, float thresh, int max
   if (max_seg <= 0) {
     // every segment is empty: counts = 0
     RLOD_LAUNCH(RLOD_KERNEL_NMS_SMALL, st, k_nms_small<<<nseg, kSmallThreads, small_smem(64), st>>>(segs, thresh, max_keep, 64, out));
+    return launch_status();
+  }
+  if (max_keep > 0 && max_keep <= kLazyMaxKeep && !force_large) {
+    // bounded keeps (proposal layer): kept-list walk, no n x n mask, no workspace
+    const size_t smem = (size_t)max_keep * (sizeof(float4) + sizeof(float));
+    RLOD_LAUNCH(RLOD_KERNEL_NMS_LAZY, st,
+                k_nms_lazy<<<nseg, kLazyThreads, smem, st>>>(segs, thresh, max_keep, out));
     return launch_status();
   }
   if (max_seg <= kSmallMaxN && !force_large) {

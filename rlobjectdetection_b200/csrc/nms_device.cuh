@@ -98,7 +98,7 @@ __device__ __forceinline__ bool iou_gt(const float4 &a, float Sa, const float4 &
   return __fdiv_rn(inter, u) > thresh;
 }
 
-size_t nms_mask_bytes(int nseg, int max_seg);
+size_t nms_mask_bytes(int nseg, int max_seg, int max_keep);
 int nms_launch(const NmsSegs &segs, int nseg, int max_seg, float thresh, int max_keep,
                const NmsOut &out, void *workspace, size_t workspace_bytes, cudaStream_t st,
                int force_large);

@@ -35,24 +35,45 @@ struct PropArgs {
   const float *scores, *deltas, *im_info, *anchors;
   int B, A, H, W, feat_stride, pre;  // pre = min(pre_nms_topN, H*W*A), > 0
   float4 *props;                     // (B, pre) decoded + clipped, sorted
+  unsigned long long *sel;           // (B, mp) scratch: the selected composite keys, unordered
+  int keys_in_smem;                  // all H*W*A score keys fit in shared memory
   int *order_out;                    // (B, pre) or NULL
   float *props_out;                  // (B, pre, 4) or NULL
 };
 
 __global__ void __launch_bounds__(kSortThreads) k_proposal_sort_decode(PropArgs a, int mp) {
+  // dynamic smem, two lives: first the 32-bit score keys of ALL anchors (select phase, when
+  // they fit), then the mp selected 64-bit composite keys (sort phase)
   extern __shared__ __align__(16) unsigned long long keys[];  // [mp], mp = pow2 >= pre
-  __shared__ unsigned int hist[256];
+  uint32_t *skeys = reinterpret_cast<uint32_t *>(keys);       // [KA], indexed by anchor index
+  __shared__ unsigned int hist_w[kSortThreads / 32][256];     // one histogram per warp: no atomics
   __shared__ unsigned int wsum[8];
   __shared__ unsigned long long s_prefix;
   __shared__ unsigned int s_remaining, s_done, s_count;
-  const int b = blockIdx.x, t = threadIdx.x, lane = t & 31;
+  const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int HW = a.H * a.W, KA = HW * a.A, M = a.pre;
   const float *fg = a.scores + ((size_t)b * 2 * a.A + a.A) * HW;
 
-  // memory index e = a*HW + pix  <->  anchor index idx = pix*A + a  (proposal_layer.py:92-103)
-  auto composite = [&](int e) -> unsigned long long {
-    const int an = e / HW, pix = e - an * HW;
-    return ((unsigned long long)desc_key(__ldg(fg + e)) << 32) | (unsigned)(pix * a.A + an);
+  // One coalesced pass over the NCHW fg score map; keys land at their ANCHOR index
+  // idx = pix*A + a (memory index e = a*HW + pix, proposal_layer.py:92-103), so every later
+  // pass is a plain linear walk of shared memory and the composite key is (key << 32) | idx.
+  const bool ks = a.keys_in_smem != 0;
+  if (ks) {
+    for (int e = t; e < KA; e += kSortThreads) {
+      const int an = e / HW, pix = e - an * HW;
+      skeys[pix * a.A + an] = desc_key(__ldg(fg + e));
+    }
+    __syncthreads();
+  }
+  auto composite = [&](int i) -> unsigned long long {
+    uint32_t key;
+    if (ks) {
+      key = skeys[i];
+    } else {
+      const int pix = i / a.A, an = i - pix * a.A;
+      key = desc_key(__ldg(fg + (size_t)an * HW + pix));
+    }
+    return ((unsigned long long)key << 32) | (unsigned)i;
   };
 
   unsigned long long T = ~0ull;  // threshold: select composite <= T
@@ -64,26 +85,31 @@ __global__ void __launch_bounds__(kSortThreads) k_proposal_sort_decode(PropArgs 
     }
     for (int pass = 0; pass < 8; ++pass) {
       const int shift = 56 - 8 * pass;
-      if (t < 256) hist[t] = 0u;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) hist_w[warp][lane + 32 * q] = 0u;
       __syncthreads();
       if (s_done) break;  // CTA-uniform (written before the previous barrier)
       const unsigned long long prefix = s_prefix;
       const unsigned rem = s_remaining;
       for (int e0 = 0; e0 < KA; e0 += kSortThreads) {
         const int e = e0 + t;
-        int digit = -1 - lane;  // unique sentinel: never matches another lane
+        int digit = -1;  // not a candidate
         if (e < KA) {
           const unsigned long long c = composite(e);
           if (pass == 0 || (c >> (shift + 8)) == (prefix >> (shift + 8))) digit = (int)((c >> shift) & 255ull);
         }
+        // one leader per distinct digit adds the whole group's count to the warp's own bins
         const unsigned peers = __match_any_sync(0xffffffffu, digit);
-        if (digit >= 0 && lane == __ffs(peers) - 1) atomicAdd(&hist[digit], (unsigned)__popc(peers));
+        if (digit >= 0 && lane == __ffs(peers) - 1) hist_w[warp][digit] += (unsigned)__popc(peers);
+        __syncwarp();
       }
       __syncthreads();
-      // 256 threads: inclusive scan of the histogram, find the digit holding the M-th key
+      // 256 threads: sum the warp histograms (rotated start: conflict-free), inclusive scan,
+      // find the digit holding the M-th key
       unsigned cnt = 0, inc = 0;
       if (t < 256) {
-        cnt = hist[t];
+#pragma unroll 8
+        for (int w = 0; w < kSortThreads / 32; ++w) cnt += hist_w[(w + t) & (kSortThreads / 32 - 1)][t];
         inc = cnt;
         for (int d = 1; d < 32; d <<= 1) {
           const unsigned v = __shfl_up_sync(0xffffffffu, inc, d);
@@ -116,9 +142,10 @@ __global__ void __launch_bounds__(kSortThreads) k_proposal_sort_decode(PropArgs 
     T = s_prefix;
   }
 
-  // compaction (unordered; the sort below orders the distinct composite keys)
+  // compaction (unordered; the sort below orders the distinct composite keys) through a
+  // global scratch row, because the sort buffer reuses the shared memory the keys live in
+  unsigned long long *sel = a.sel + (size_t)b * mp;
   if (t == 0) s_count = 0u;
-  for (int i = t; i < mp; i += kSortThreads) keys[i] = ~0ull;
   __syncthreads();
   for (int e0 = 0; e0 < KA; e0 += kSortThreads) {
     const int e = e0 + t;
@@ -134,16 +161,21 @@ __global__ void __launch_bounds__(kSortThreads) k_proposal_sort_decode(PropArgs 
     wbase = __shfl_sync(0xffffffffu, wbase, 0);
     if (take) {
       const unsigned pos = wbase + __popc(bal & ((1u << lane) - 1u));
-      if (pos < (unsigned)mp) keys[pos] = c;
+      if (pos < (unsigned)mp) sel[pos] = c;
     }
+  }
+  __syncthreads();  // also orders this CTA's global writes before its own reads below
+  {
+    const unsigned cnt = s_count;
+    for (int i = t; i < mp; i += kSortThreads) keys[i] = (unsigned)i < cnt ? sel[i] : ~0ull;
   }
   __syncthreads();
 
-  // bitonic sort, ascending, mp a power of two
+  // bitonic sort, ascending, mp a power of two (j is a power of two: shifts, no division)
   for (int k = 2; k <= mp; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
       for (int p = t; p < (mp >> 1); p += kSortThreads) {
-        const int i = ((p / j) * (j << 1)) + (p % j);
+        const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
         const int l = i + j;
         const unsigned long long x = keys[i], y = keys[l];
         const bool up = (i & k) == 0;
@@ -194,18 +226,27 @@ __global__ void __launch_bounds__(kSortThreads) k_proposal_sort_decode(PropArgs 
 
 struct PropWs {
   float4 *props;
+  unsigned long long *sel;
   void *mask;
   size_t mask_bytes, bytes;
 };
 
-static PropWs carve_prop_ws(void *base, int B, int pre) {
+static int pow2_at_least(int v) {
+  int mp = 64;
+  while (mp < v) mp <<= 1;
+  return mp;
+}
+
+static PropWs carve_prop_ws(void *base, int B, int pre, int post) {
   PropWs w;
   char *p = (char *)base;
   size_t off = 0;
   w.props = (float4 *)(p ? p + off : nullptr);
   off += align_up((size_t)B * pre * sizeof(float4), 256);
+  w.sel = (unsigned long long *)(p ? p + off : nullptr);
+  off += align_up((size_t)B * pow2_at_least(pre) * sizeof(unsigned long long), 256);
   w.mask = p ? p + off : nullptr;
-  w.mask_bytes = nms_mask_bytes(B, pre);
+  w.mask_bytes = nms_mask_bytes(B, pre, post);
   off += align_up(w.mask_bytes, 256);
   w.bytes = off;
   return w;
@@ -223,9 +264,8 @@ using namespace rlod;
 
 RLOD_API size_t rlod_proposal_workspace_bytes(int B, int A, int H, int W, int pre_nms_topN,
                                               int post_nms_topN) {
-  (void)post_nms_topN;
   if (B <= 0 || A <= 0 || H <= 0 || W <= 0) return 0;
-  return carve_prop_ws(nullptr, B, eff_pre(A, H, W, pre_nms_topN)).bytes;
+  return carve_prop_ws(nullptr, B, eff_pre(A, H, W, pre_nms_topN), post_nms_topN).bytes;
 }
 
 RLOD_API int rlod_proposal_forward(const float *scores, const float *deltas, const float *im_info,
@@ -242,17 +282,20 @@ RLOD_API int rlod_proposal_forward(const float *scores, const float *deltas, con
   if ((long long)A * H * W >= (1LL << 30)) return RLOD_EUNSUPPORTED;
   const int pre = eff_pre(A, H, W, pre_nms_topN);
   if (pre > kSortMax) return RLOD_EUNSUPPORTED;
-  PropWs ws = carve_prop_ws(workspace, B, pre);
+  PropWs ws = carve_prop_ws(workspace, B, pre, post_nms_topN);
   if (workspace_bytes < ws.bytes) return RLOD_ENOSPC;
   cudaStream_t st = (cudaStream_t)stream;
 
-  int mp = 64;
-  while (mp < pre) mp <<= 1;
+  const int mp = pow2_at_least(pre);
+  const size_t key_bytes = (size_t)A * H * W * sizeof(uint32_t);
   PropArgs pa;
   pa.scores = scores, pa.deltas = deltas, pa.im_info = im_info, pa.anchors = anchors;
   pa.B = B, pa.A = A, pa.H = H, pa.W = W, pa.feat_stride = feat_stride, pa.pre = pre;
   pa.props = ws.props, pa.order_out = order_out, pa.props_out = props_out;
-  const size_t smem = (size_t)mp * sizeof(unsigned long long);
+  pa.sel = ws.sel;
+  pa.keys_in_smem = key_bytes <= (size_t)(kMaxSmemPerCta - 36 * 1024) ? 1 : 0;  // 33 KB static
+  size_t smem = (size_t)mp * sizeof(unsigned long long);
+  if (pa.keys_in_smem && key_bytes > smem) smem = align_up(key_bytes, 16);
   cudaFuncSetAttribute(k_proposal_sort_decode, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)smem);
   RLOD_LAUNCH(RLOD_KERNEL_PROPOSAL_SORT, st, k_proposal_sort_decode<<<B, kSortThreads, smem, st>>>(pa, mp));
@@ -271,7 +314,6 @@ RLOD_API int rlod_proposal_forward(const float *scores, const float *deltas, con
   o.num_out = nkeep_out;
   o.rois = rois_out;
   o.post = post_nms_topN;
-  // proposals always take the tiled path (pre is thousands); tiny maps fall to the
-  // shared-memory kernel, which emits the same output
+  // post_nms_topN <= 512: kept-list walk (k_nms_lazy); larger: tiled mask + device scan
   return nms_launch(segs, B, pre, nms_thresh, post_nms_topN, o, ws.mask, ws.mask_bytes, st, 0);
 }

@@ -11,11 +11,11 @@
 //      computed once with the reference's exact fp32/fp64 expression order, plus per-image
 //      roi lists.  The hot kernels never touch roi coordinates again.
 //   2. forward (k_align8_fwd_planes): a CTA owns 4 consecutive channel planes of ONE image,
-//      pulls them HBM -> shared memory with a single 1-D bulk async copy (TMA engine,
-//      mbarrier completion) and then serves EVERY roi of that image from shared memory.
-//      The feature map is read from HBM exactly once, all bilinear taps are LDS, and each
-//      (roi, 4 channels) result is staged in shared memory and leaves as full 16-byte
-//      streaming stores of one contiguous 784-byte run.  No 8x8 intermediate tensor exists.
+//      pulls them HBM -> shared memory once (coalesced, interleaved per pixel so that lanes
+//      of different channels never share a bank) and then serves EVERY roi of that image
+//      from shared memory.  The feature map is read from HBM exactly once, all bilinear taps
+//      are LDS, and each (roi, 4 channels) result is staged in shared memory and leaves as
+//      ONE 784-byte bulk async store (TMA engine).  No 8x8 intermediate tensor exists.
 //   3. backward (k_align8_bwd_bands): a warp owns a band of rows of 4 gradient planes in
 //      shared memory exclusively, walks the image's rois, and accumulates with plain
 //      LDS/FADD/STS (segmented warp-shuffle reduction resolves intra-roi collisions), so
@@ -37,6 +37,7 @@ struct AlignWs {
   int *order;    // [R]   roi ids grouped by image (stable)
   int *roi_b;    // [R]   batch index (0 when out of range: the plan is all-invalid then)
   int *plan;     // [R * words]
+  int *ext;      // [R * 64] forward-kernel record (8x8 grids only)
   size_t bytes;
 };
 
@@ -55,6 +56,7 @@ static AlignWs carve_align_ws(void *base, int B, int R, int GH, int GW) {
   w.order = (int *)take((size_t)(R > 0 ? R : 1) * sizeof(int));
   w.roi_b = (int *)take((size_t)(R > 0 ? R : 1) * sizeof(int));
   w.plan = (int *)take((size_t)(R > 0 ? R : 1) * (size_t)(2 * GH + 2 * GW) * sizeof(int));
+  w.ext = (int *)take((GH == 8 && GW == 8) ? (size_t)(R > 0 ? R : 1) * 64 * sizeof(int) : 0);
   w.bytes = off;
   return w;
 }
@@ -263,89 +265,216 @@ __device__ __forceinline__ void load_plan8(const int *__restrict__ plan, int r, 
 
 constexpr int kFwdThreads = 256;
 
+// bulk async store shared -> global (TMA engine, SASS: UBLKCP), tracked by bulk groups
+__device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem),
+               "r"(smem_u32(src_smem)), "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// One sample row of the forward walk, fully predicated on three warp-uniform flag bits:
+//   reload: load both rows' taps;  adv: load the lower row's taps (shift or reload);
+//   shift: the previous lower row becomes the upper row.
+//   t0/t1 = the two horizontally interpolated rows, s = t0 + hr*(t1 - t0).
+// Written as one PTX block so that the three predicates are materialised once (LOP3 -> P) and
+// guard the LDS and the FFMAs directly: no branches, no wavefront for a skipped load.
+template <int PH>
+__device__ __forceinline__ void sample_row_step(float &t0, float &t1, float &s, uint32_t pa,
+                                                uint32_t pb, uint32_t pa2, uint32_t pb2, float wr,
+                                                float hr, int flags) {
+  asm volatile(
+      "{\n"
+      ".reg .pred pr, pd, ps;\n"
+      ".reg .b32 tt;\n"
+      ".reg .f32 x0, x1, y0, y1, d;\n"
+      "and.b32 tt, %9, %10;\n"
+      "setp.ne.b32 pr, tt, 0;\n"
+      "and.b32 tt, %9, %11;\n"
+      "setp.ne.b32 pd, tt, 0;\n"
+      "and.b32 tt, %9, %12;\n"
+      "setp.ne.b32 ps, tt, 0;\n"
+      "@pr ld.shared.f32 x0, [%3];\n"
+      "@pr ld.shared.f32 x1, [%4];\n"
+      "@pd ld.shared.f32 y0, [%5];\n"
+      "@pd ld.shared.f32 y1, [%6];\n"
+      "@ps mov.f32 %0, %1;\n"
+      "@pr sub.f32 d, x1, x0;\n"
+      "@pr fma.rn.f32 %0, %7, d, x0;\n"
+      "@pd sub.f32 d, y1, y0;\n"
+      "@pd fma.rn.f32 %1, %7, d, y0;\n"
+      "sub.f32 d, %1, %0;\n"
+      "fma.rn.f32 %2, %8, d, %0;\n"
+      "}\n"
+      : "+f"(t0), "+f"(t1), "=f"(s)
+      : "r"(pa), "r"(pb), "r"(pa2), "r"(pb2), "f"(wr), "f"(hr), "r"(flags), "n"(1 << PH),
+        "n"(1 << (8 + PH)), "n"(1 << (16 + PH)));
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// ----------------------------------------------------------------------------------------
+// Shared-memory layout of the forward kernel.  The CTA's 4 channel planes are interleaved per
+// pixel, planes4[pix] = (c0, c1, c2, c3); lane (ch, pw) reads word 4*pix + ch, so lanes of
+// different channels can never collide on a bank (bank = 4*(pix mod 8) + ch).  Inside a row the
+// column is XOR-swizzled, col' = col ^ ((col >> 3) & 7) (identity in the last partial group of
+// 8), so the 8 sample columns of a roi fall on distinct bank groups for strides 1, 2, 3, 4 ...
+// as well.  Two extra all-zero rows (H, H+1) stand in for out-of-range sample rows and one
+// zero pixel for out-of-range sample columns: validity never appears in the hot loop.
+//
+// k_roi_plan8_fwd turns the generic plan into the forward kernel's per-roi record (64 words):
+//   [0..7]   byte offset of sample row ph inside planes4 (the zero row when invalid)
+//   [8..15]  row ratio hr (0 when invalid)
+//   [16]     flags: bit ph = both rows must be (re)loaded, bit 8+ph = shift or reload,
+//            bit 16+ph = shift only (the lower row becomes the previous upper row)
+//   [32+4pw..] per sample column: c0 = byte offset of the swizzled left tap, dc = offset of
+//            the right tap relative to it, m = 1 (0: column invalid -> c0 is the zero pixel and
+//            the row offset is multiplied away), wr = column ratio
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ int swz_col(int col, int W8) {
+  return col < W8 ? (col ^ ((col >> 3) & 7)) : col;
+}
+
+__global__ void k_roi_plan8_fwd(const int *__restrict__ plan, int R, int H, int W,
+                                int *__restrict__ ext) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const int *pl = plan + (size_t)r * 32;
+  int *e = ext + (size_t)r * 64;
+  const int W8 = W & ~7;
+  const int row_bytes = 16 * W;
+  int prev = -5;  // row index of the previous sample row (zero rows count as row H)
+  int flags = 0;
+  for (int ph = 0; ph < 8; ++ph) {
+    const int hs = pl[ph];
+    const int row = hs >= 0 ? hs : H;
+    e[ph] = row * row_bytes;
+    e[8 + ph] = hs >= 0 ? pl[8 + ph] : 0;
+    if (row == prev) {
+      // keep both interpolated rows
+    } else if (row == prev + 1) {
+      flags |= (1 << (8 + ph)) | (1 << (16 + ph));
+    } else {
+      flags |= (1 << ph) | (1 << (8 + ph));
+    }
+    prev = row;
+  }
+  e[16] = flags;
+  for (int pw = 0; pw < 8; ++pw) {
+    const int ws = pl[16 + 2 * pw];
+    int c0, dc, m;
+    if (ws >= 0) {
+      c0 = 16 * swz_col(ws, W8);
+      dc = 16 * swz_col(ws + 1, W8) - c0;
+      m = 1;
+    } else {
+      c0 = H * row_bytes;  // pixel 0 of the first zero row; its lower neighbour is zero too
+      dc = 0;
+      m = 0;
+    }
+    e[32 + 4 * pw + 0] = c0;
+    e[32 + 4 * pw + 1] = dc;
+    e[32 + 4 * pw + 2] = m;
+    e[32 + 4 * pw + 3] = pl[16 + 2 * pw + 1];
+  }
+}
+
+struct Plan8F {
+  int roff[8];
+  float hr[8];
+  int flags;
+  int c0, dc, m;
+  float wr;
+};
+
+__device__ __forceinline__ void load_plan8f(const int *__restrict__ ext, int r, int pw, Plan8F &p) {
+  const int4 *q = reinterpret_cast<const int4 *>(ext + (size_t)r * 64);
+  const int4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3);
+  p.roff[0] = a.x, p.roff[1] = a.y, p.roff[2] = a.z, p.roff[3] = a.w;
+  p.roff[4] = b.x, p.roff[5] = b.y, p.roff[6] = b.z, p.roff[7] = b.w;
+  p.hr[0] = __int_as_float(c.x), p.hr[1] = __int_as_float(c.y);
+  p.hr[2] = __int_as_float(c.z), p.hr[3] = __int_as_float(c.w);
+  p.hr[4] = __int_as_float(d.x), p.hr[5] = __int_as_float(d.y);
+  p.hr[6] = __int_as_float(d.z), p.hr[7] = __int_as_float(d.w);
+  p.flags = __ldg(ext + (size_t)r * 64 + 16);
+  const int4 w = __ldg(q + 8 + pw);
+  p.c0 = w.x, p.dc = w.y, p.m = w.z;
+  p.wr = __int_as_float(w.w);
+}
+
 template <int POOL>
-__global__ void __launch_bounds__(kFwdThreads)
-    k_align8_fwd_planes(const float *__restrict__ feat, const int *__restrict__ plan,
+__global__ void __launch_bounds__(kFwdThreads, 3)
+    k_align8_fwd_planes(const float *__restrict__ feat, const int *__restrict__ ext,
                         const int *__restrict__ order, const int *__restrict__ img_off, int C,
-                        int H, int W, int n_chunks, int use_bulk, float *__restrict__ out) {
+                        int H, int W, int n_chunks, float *__restrict__ out) {
   constexpr int OW = POOL == RLOD_POOL_NONE ? 8 : 7;
   constexpr int OHW = OW * OW;   // 64 | 49
   constexpr int STG = 4 * OHW;   // floats per (roi, 4 channels): 256 | 196
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw);
-  float *planes = reinterpret_cast<float *>(smem_raw + 16);
-  const int HW = H * W;
-  float *stage = planes + 4 * HW;
+  float4 *planes4 = reinterpret_cast<float4 *>(smem_raw);
+  const int HW = H * W, W8 = W & ~7;
+  float *stage = reinterpret_cast<float *>(planes4 + HW + 2 * W);
 
   const int b = blockIdx.x / n_chunks, chunk = blockIdx.x - b * n_chunks;
   const int r0 = img_off[b], r1 = img_off[b + 1];
   if (r0 >= r1) return;
   const float *src = feat + ((size_t)b * C + (size_t)chunk * 4) * HW;
-  if (use_bulk) {
-    if (threadIdx.x == 0) mbar_init(mbar, 1);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      mbar_expect_tx(mbar, (uint32_t)(4 * HW * sizeof(float)));
-      bulk_g2s(planes, src, (uint32_t)(4 * HW * sizeof(float)), mbar);
-    }
-  } else {
-    for (int i = threadIdx.x; i < 4 * HW; i += blockDim.x) planes[i] = __ldg(src + i);
+#pragma unroll 4
+  for (int p = threadIdx.x; p < HW; p += kFwdThreads) {
+    const int y = p / W, x = p - y * W;
+    planes4[y * W + swz_col(x, W8)] = make_float4(__ldg(src + p), __ldg(src + HW + p),
+                                                  __ldg(src + 2 * HW + p), __ldg(src + 3 * HW + p));
   }
+  for (int p = threadIdx.x; p < 2 * W; p += kFwdThreads) planes4[HW + p] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = kFwdThreads >> 5;
   const int pw = lane & 7, ch = lane >> 3;
-  const float *P = planes + ch * HW;
+  const uint32_t pbase = smem_u32(planes4) + 4u * (uint32_t)ch;  // word 4*pix + ch
+  const uint32_t w16 = 16u * (uint32_t)W;                           // bytes per plane row
   float *stg = stage + warp * (2 * STG);
 
   int k = r0 + warp;
-  Plan8 cur;
+  Plan8F cur;
   int r = 0;
   if (k < r1) {
     r = order[k];
-    load_plan8(plan, r, pw, cur);
+    load_plan8f(ext, r, pw, cur);
   }
-  if (use_bulk)
-    mbar_wait(mbar, 0);
-  else
-    __syncthreads();
+  __syncthreads();
 
   for (int it = 0; k < r1; k += nw, ++it) {
     // prefetch the next roi's plan while this one is computed
-    Plan8 nxt;
+    Plan8F nxt;
     int rn = 0;
-    const bool has_next = k + nw < r1;
-    if (has_next) {
+    if (k + nw < r1) {
       rn = order[k + nw];
-      load_plan8(plan, rn, pw, nxt);
+      load_plan8f(ext, rn, pw, nxt);
     }
-    const bool wv = cur.ws >= 0;
-    const int wsafe = wv ? cur.ws : 0;
     const float wr = cur.wr;
+    const uint32_t cbase = pbase + (uint32_t)cur.c0;
+    const int fl = cur.flags;  // warp-uniform: the sample rows come from the roi alone
     float s[8];
-    int row = -2;
     float t0 = 0.f, t1 = 0.f;
-#pragma unroll
-    for (int ph = 0; ph < 8; ++ph) {
-      const int h0 = cur.hs[ph];  // warp-uniform
-      if (h0 < 0) {
-        s[ph] = 0.f;
-        continue;
-      }
-      const float *p = P + h0 * W + wsafe;
-      if (h0 == row) {
-        // both rows already interpolated
-      } else if (h0 == row + 1) {
-        t0 = t1;
-        t1 = lerp_row(p + W, wr);
-      } else {
-        t0 = lerp_row(p, wr);
-        t1 = lerp_row(p + W, wr);
-      }
-      row = h0;
-      const float hr = cur.hr[ph];
-      s[ph] = wv ? fmaf(hr, t1, (1.f - hr) * t0) : 0.f;
+#define RLOD_ROW_STEP(PH)                                                                      \
+  {                                                                                            \
+    const uint32_t pa = cbase + (uint32_t)(cur.roff[PH] * cur.m);                              \
+    const uint32_t pb = pa + (uint32_t)cur.dc;                                                 \
+    sample_row_step<PH>(t0, t1, s[PH], pa, pb, pa + w16, pb + w16, wr, cur.hr[PH], fl);        \
+  }
+    RLOD_ROW_STEP(0) RLOD_ROW_STEP(1) RLOD_ROW_STEP(2) RLOD_ROW_STEP(3)
+    RLOD_ROW_STEP(4) RLOD_ROW_STEP(5) RLOD_ROW_STEP(6) RLOD_ROW_STEP(7)
+#undef RLOD_ROW_STEP
+    // the buffer about to be written was handed to the bulk-copy engine two iterations ago
+    if (it >= 2) {
+      if (lane == 0) bulk_wait_read<1>();
+      __syncwarp();
     }
-    float *sb = stg + (it & 1) * STG + ch * OHW;
+    float *sbuf = stg + (it & 1) * STG;
+    float *sb = sbuf + ch * OHW;
     if (POOL == RLOD_POOL_NONE) {
 #pragma unroll
       for (int ph = 0; ph < 8; ++ph) sb[ph * 8 + pw] = s[ph];
@@ -358,18 +487,16 @@ __global__ void __launch_bounds__(kFwdThreads)
         for (int i = 0; i < 7; ++i) sb[i * 7 + pw] = pool4<POOL>(s[i], sr[i], s[i + 1], sr[i + 1]);
       }
     }
+    // 4 channels x OHW floats are one contiguous, 16-byte aligned run of the (R,C,OH,OW)
+    // output: hand the staged block to the TMA engine as a single bulk store
+    fence_async_smem();
     __syncwarp();
-    // 4 channels x OHW floats are one contiguous run of the (R,C,OH,OW) output
-    const float *sbuf = stg + (it & 1) * STG;
-    float *dst = out + ((size_t)r * C + (size_t)chunk * 4) * OHW;
-#pragma unroll
-    for (int q = lane; q < STG / 4; q += 32) {
-      const float4 v = *reinterpret_cast<const float4 *>(sbuf + 4 * q);
-      st_stream4(dst + 4 * q, v);
-    }
+    if (lane == 0)
+      bulk_s2g(out + ((size_t)r * C + (size_t)chunk * 4) * OHW, sbuf, (uint32_t)(STG * sizeof(float)));
     cur = nxt;
     r = rn;
   }
+  if (lane == 0) bulk_wait_read<0>();  // shared memory must outlive the engine's reads
 }
 
 // ----------------------------------------------------------------------------------------
@@ -620,9 +747,9 @@ static int build_plan(const float *rois, int B, int H, int W, int R, int GH, int
   return launch_status();
 }
 
-static size_t fwd_planes_smem(int HW, int pool_mode) {
+static size_t fwd_planes_smem(int H, int W, int pool_mode) {
   const int stg = 4 * (pool_mode == RLOD_POOL_NONE ? 64 : 49);
-  return 16 + (size_t)4 * HW * 4 + (size_t)(kFwdThreads / 32) * 2 * stg * 4;
+  return (size_t)16 * ((size_t)H * W + 2 * W) + (size_t)(kFwdThreads / 32) * 2 * stg * 4;
 }
 
 }  // namespace rlod
@@ -652,22 +779,22 @@ RLOD_API int rlod_roi_align_forward(const float *feat, const float *rois, int B,
   rc = build_plan(rois, B, H, W, R, GH, GW, spatial_scale, ws, st);
   if (rc) return rc;
 
-  const int HW = H * W;
-  const size_t smem = fwd_planes_smem(HW, pool_mode);
+  const size_t smem = fwd_planes_smem(H, W, pool_mode);
   const bool fast = GH == 8 && GW == 8 && (C % 4) == 0 && smem <= (size_t)kMaxSmemPerCta &&
                     ((uintptr_t)out % 16) == 0 && R >= 2 * B;
   if (fast) {
     const int n_chunks = C / 4;
-    const int use_bulk = ((uintptr_t)feat % 16) == 0 ? 1 : 0;
     const unsigned grid = (unsigned)(B * n_chunks);
+    RLOD_LAUNCH(RLOD_KERNEL_ROI_PLAN, st,
+                k_roi_plan8_fwd<<<(unsigned)cdiv(R, 128), 128, 0, st>>>(ws.plan, R, H, W, ws.ext));
 #define RLOD_LAUNCH_FWD(POOL)                                                                  \
   do {                                                                                         \
     cudaFuncSetAttribute(k_align8_fwd_planes<POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                          (int)smem);                                                           \
     ProfScope _ps(RLOD_KERNEL_ALIGN_FWD, st);                                                  \
-    k_align8_fwd_planes<POOL><<<grid, kFwdThreads, smem, st>>>(feat, ws.plan, ws.order,        \
+    k_align8_fwd_planes<POOL><<<grid, kFwdThreads, smem, st>>>(feat, ws.ext, ws.order,         \
                                                                ws.img_off, C, H, W, n_chunks,  \
-                                                               use_bulk, out);                 \
+                                                               out);                           \
   } while (0)
     if (pool_mode == RLOD_POOL_NONE)
       RLOD_LAUNCH_FWD(RLOD_POOL_NONE);

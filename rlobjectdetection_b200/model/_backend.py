@@ -17,7 +17,8 @@ LIB_PATH = os.path.join(CSRC, "librlod_sm100a.so")
 
 POOL_NONE, POOL_AVG, POOL_MAX = 0, 1, 2
 KERNELS = ["align_fwd", "align_bwd", "align_fwd_generic", "align_bwd_generic", "roi_plan", "nms_mask",
-           "nms_scan", "nms_small", "proposal_sort", "pool_fwd", "pool_bwd", "boxes", "reward", "move"]
+           "nms_scan", "nms_small", "proposal_sort", "pool_fwd", "pool_bwd", "boxes", "reward", "move",
+           "nms_lazy"]
 IOU_COCO, IOU_RCNN = 0, 1
 SORT_MAX = 16384  # rlod_proposal_forward: min(pre_nms_topN, H*W*A) limit
 
