@@ -272,42 +272,10 @@ __device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, u
                : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
-// One sample row of the forward walk, fully predicated on three warp-uniform flag bits:
-//   reload: load both rows' taps;  adv: load the lower row's taps (shift or reload);
-//   shift: the previous lower row becomes the upper row.
-//   t0/t1 = the two horizontally interpolated rows, s = t0 + hr*(t1 - t0).
-// Written as one PTX block so that the three predicates are materialised once (LOP3 -> P) and
-// guard the LDS and the FFMAs directly: no branches, no wavefront for a skipped load.
-template <int PH>
-__device__ __forceinline__ void sample_row_step(float &t0, float &t1, float &s, uint32_t pa,
-                                                uint32_t pb, uint32_t pa2, uint32_t pb2, float wr,
-                                                float hr, int flags) {
-  asm volatile(
-      "{\n"
-      ".reg .pred pr, pd, ps;\n"
-      ".reg .b32 tt;\n"
-      ".reg .f32 x0, x1, y0, y1, d;\n"
-      "and.b32 tt, %9, %10;\n"
-      "setp.ne.b32 pr, tt, 0;\n"
-      "and.b32 tt, %9, %11;\n"
-      "setp.ne.b32 pd, tt, 0;\n"
-      "and.b32 tt, %9, %12;\n"
-      "setp.ne.b32 ps, tt, 0;\n"
-      "@pr ld.shared.f32 x0, [%3];\n"
-      "@pr ld.shared.f32 x1, [%4];\n"
-      "@pd ld.shared.f32 y0, [%5];\n"
-      "@pd ld.shared.f32 y1, [%6];\n"
-      "@ps mov.f32 %0, %1;\n"
-      "@pr sub.f32 d, x1, x0;\n"
-      "@pr fma.rn.f32 %0, %7, d, x0;\n"
-      "@pd sub.f32 d, y1, y0;\n"
-      "@pd fma.rn.f32 %1, %7, d, y0;\n"
-      "sub.f32 d, %1, %0;\n"
-      "fma.rn.f32 %2, %8, d, %0;\n"
-      "}\n"
-      : "+f"(t0), "+f"(t1), "=f"(s)
-      : "r"(pa), "r"(pb), "r"(pa2), "r"(pb2), "f"(wr), "f"(hr), "r"(flags), "n"(1 << PH),
-        "n"(1 << (8 + PH)), "n"(1 << (16 + PH)));
+__device__ __forceinline__ float lds_f32(uint32_t smem_addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(smem_addr));
+  return v;
 }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() {
@@ -459,15 +427,23 @@ __global__ void __launch_bounds__(kFwdThreads, 3)
     const int fl = cur.flags;  // warp-uniform: the sample rows come from the roi alone
     float s[8];
     float t0 = 0.f, t1 = 0.f;
-#define RLOD_ROW_STEP(PH)                                                                      \
-  {                                                                                            \
-    const uint32_t pa = cbase + (uint32_t)(cur.roff[PH] * cur.m);                              \
-    const uint32_t pb = pa + (uint32_t)cur.dc;                                                 \
-    sample_row_step<PH>(t0, t1, s[PH], pa, pb, pa + w16, pb + w16, wr, cur.hr[PH], fl);        \
-  }
-    RLOD_ROW_STEP(0) RLOD_ROW_STEP(1) RLOD_ROW_STEP(2) RLOD_ROW_STEP(3)
-    RLOD_ROW_STEP(4) RLOD_ROW_STEP(5) RLOD_ROW_STEP(6) RLOD_ROW_STEP(7)
-#undef RLOD_ROW_STEP
+#pragma unroll
+    for (int ph = 0; ph < 8; ++ph) {
+      // warp-uniform flag bits: which of the two interpolated rows must be refreshed
+      const bool reload = (fl >> ph) & 1, adv = (fl >> (8 + ph)) & 1, shift = (fl >> (16 + ph)) & 1;
+      const uint32_t pa = cbase + (uint32_t)(cur.roff[ph] * cur.m);
+      const uint32_t pb = pa + (uint32_t)cur.dc;
+      if (shift) t0 = t1;
+      if (reload) {
+        const float x0 = lds_f32(pa), x1 = lds_f32(pb);
+        t0 = fmaf(wr, x1 - x0, x0);
+      }
+      if (adv) {
+        const float y0 = lds_f32(pa + w16), y1 = lds_f32(pb + w16);
+        t1 = fmaf(wr, y1 - y0, y0);
+      }
+      s[ph] = fmaf(cur.hr[ph], t1 - t0, t0);
+    }
     // the buffer about to be written was handed to the bulk-copy engine two iterations ago
     if (it >= 2) {
       if (lane == 0) bulk_wait_read<1>();
