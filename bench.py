@@ -13,7 +13,7 @@ with ONE NCCL all-gather of the packed detections || rewards.
 
 One JSON line on rank 0 (see the task contract): value = device-resident throughput, e2e =
 through the public API from pinned HOST buffers (H2D of all inputs + D2H of detections and
-rewards inside the timed region), roofline = the dominant kernel (k_align8_fwd_planes) timed
+rewards inside the timed region), roofline = the dominant kernel (k_align8_fwd_walk) timed
 live with CUDA events on its own stream, cpu_baseline = the CPU port (oracle/) on a bounded
 sample.  --impl reference times that CPU port as the reference arm.
 """
@@ -278,7 +278,7 @@ def run_ours(args, rank, local_rank, world):
     except (OSError, ValueError):
         pass
     roofline = {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None,
-                "traffic": traffic, "kernel": "k_align8_fwd_planes<AVG>", "peak_source": peak_src,
+                "traffic": traffic, "kernel": "k_align8_fwd_walk<AVG>", "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes}
     if "align_fwd" in prof:
         kms, kn = prof["align_fwd"]

@@ -88,5 +88,28 @@ def kernel(src, dst):
     print("\n".join(out))
 
 
+def stalls(src, dst, top=25):
+    """Per-SASS-instruction warp-stall samples of the FIRST kernel in the report (the source page)."""
+    txt = subprocess.run(["ncu", "-i", src, "--page", "source", "--csv", "--print-source", "sass"],
+                         capture_output=True, text=True, check=True).stdout
+    rows = list(csv.reader(io.StringIO(txt)))
+    name, hdr, data = rows[0][1], rows[1], rows[2:]
+    ix = {h: i for i, h in enumerate(hdr)}
+    keys = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
+    tot = {k: sum(int(r[ix[k]] or 0) for r in data) for k in keys}
+    T = sum(tot.values()) or 1
+    out = [f"# warp-stall sampling by SASS instruction: {src}\n", f"kernel `{name}`, {T} samples, {len(data)} SASS instructions\n",
+           "stall reasons (% of samples): " + ", ".join(f"{k[6:]} {100 * v / T:.1f}" for k, v in sorted(tot.items(), key=lambda kv: -kv[1]) if v * 200 > T),
+           "", "| # | SASS | samples | % | dominant reason | executed |", "|---|---|---|---|---|---|"]
+    order = sorted(range(len(data)), key=lambda i: -int(data[i][ix["# Samples"]] or 0))[:top]
+    for i in sorted(order):
+        r = data[i]
+        n = int(r[ix["# Samples"]] or 0)
+        dom = max(keys, key=lambda k: int(r[ix[k]] or 0))
+        out.append(f"| {i} | `{r[ix['Source']].strip()[:64]}` | {n} | {100 * n / T:.1f} | {dom[6:]} | {r[ix['Instructions Executed']]} |")
+    open(dst, "w").write("\n".join(out) + "\n")
+    print("\n".join(out))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "kernel": kernel}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "kernel": kernel, "stalls": stalls}[sys.argv[1]](sys.argv[2], sys.argv[3])

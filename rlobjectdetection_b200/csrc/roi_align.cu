@@ -37,7 +37,8 @@ struct AlignWs {
   int *order;    // [R]   roi ids grouped by image (stable)
   int *roi_b;    // [R]   batch index (0 when out of range: the plan is all-invalid then)
   int *plan;     // [R * words]
-  int *ext;      // [R * 64] forward-kernel record (8x8 grids only)
+  int *ext;      // [R * 32] forward-kernel record (8x8 grids only)
+  int *order2;   // [R]   `order` with every image's list partitioned by walk mode (stable)
   size_t bytes;
 };
 
@@ -56,7 +57,8 @@ static AlignWs carve_align_ws(void *base, int B, int R, int GH, int GW) {
   w.order = (int *)take((size_t)(R > 0 ? R : 1) * sizeof(int));
   w.roi_b = (int *)take((size_t)(R > 0 ? R : 1) * sizeof(int));
   w.plan = (int *)take((size_t)(R > 0 ? R : 1) * (size_t)(2 * GH + 2 * GW) * sizeof(int));
-  w.ext = (int *)take((GH == 8 && GW == 8) ? (size_t)(R > 0 ? R : 1) * 64 * sizeof(int) : 0);
+  w.ext = (int *)take((GH == 8 && GW == 8) ? (size_t)(R > 0 ? R : 1) * 32 * sizeof(int) : 0);
+  w.order2 = (int *)take((GH == 8 && GW == 8) ? (size_t)(R > 0 ? R : 1) * sizeof(int) : 0);
   w.bytes = off;
   return w;
 }
@@ -263,19 +265,277 @@ __device__ __forceinline__ void load_plan8(const int *__restrict__ plan, int r, 
   p.wr = __int_as_float(w.y);
 }
 
-constexpr int kFwdThreads = 256;
+// ----------------------------------------------------------------------------------------
+// fast forward ("walk" kernel): 8x8 sample grid, CTA = (image, 4 channel planes resident in
+// shared memory), a warp serves FOUR rois per iteration (8 lanes each) and every lane carries
+// 4 channels per LDS.128.
+//
+// Shared-memory plane layout: planes4[row * P + col] = float4(c0, c1, c2, c3).
+//   * P (pixels per row) is the smallest odd number >= W + 1, so 8 consecutive rows of one
+//     column fall into 8 distinct 16-byte bank groups, exactly like 8 consecutive columns of
+//     one row;
+//   * column W of every row and rows H, H+1 are zero: an out-of-range sample column / row is
+//     redirected there with ratio 0, so validity never appears in the hot loop.
+//
+// A roi's 8x8 sample grid is separable.  The 8 lanes of a roi own the 8 positions of one axis
+// (the "lane axis") and walk the 8 positions of the other ("walk axis"), keeping the two
+// interpolated lines of the current walk position in registers (a line is re-used when
+// consecutive walk positions share it or shift by one).  Every line costs two LDS.128
+// requests per roi: each lane fetches its two neighbouring taps, one per request.  WHICH tap
+// goes into the first request is free per lane (lerp(L, R, w) == lerp(R, L, 1 - w)), and the 16
+// taps of a line cover each bank group at most twice as long as they span <= 16 pixels -- so
+// an assignment exists that makes both requests conflict-free.  k_roi_plan8_walk searches,
+// per roi, all 2^8 tap orders for both orientations
+//   mode 0: lanes = sample columns, walk = sample rows
+//   mode 1: lanes = sample rows,    walk = sample columns
+// and keeps the cheapest (fewest shared-memory wavefronts = bank multiplicity x line loads);
+// it emits one 32-word (128-byte) record per roi so that the kernel is the same
+// straight-line code for every case:
+//   [0..7]   walk position t: bit 0 "load line slot a", bit 1 "load line slot b"; bits 4-16 =
+//            byte offset of slot a's line (a multiple of 16, < 128 KB); bits 17-29 = pixel offset
+//            (bytes / 16) of slot b's line; bit 30 of word 0 = mode
+//   [8..15]  r'[t] ratio from slot a to slot b (= 1 - r when the slots hold the pair swapped)
+//   [16+2k]  lane k: low half = pixel offset of the tap it fetches first, high half (signed) =
+//            pixel offset of the other tap relative to it;  [17+2k] ratio from first to second
+// k_roi_order_by_mode then partitions every image's roi list by mode so that the four rois a
+// warp serves together stage their results with the same strides (bank-disjoint stores).
+// ----------------------------------------------------------------------------------------
+constexpr int kWalkWarps = 8;
+constexpr int kWalkThreads = kWalkWarps * 32;
+
+__host__ __device__ __forceinline__ int walk_pitch(int W) { return (W + 1) | 1; }
+
+// Walk plan over the line pairs (L[t], L[t] + 1), t = 0..7.  Two register slots a, b hold
+// interpolated lines; a position loads only the lines neither slot holds, and when the pair
+// sits in the slots in swapped order (b = first line) the kernel's s = a + r' * (b - a) is made
+// right by r' = 1 - r instead of moving registers.  Per position: bit t = load slot a, bit 8+t =
+// load slot b, bit 16+t = swapped; la/lb = the line each slot holds after the position.
+__device__ __forceinline__ int walk_slots(const int *L, int *la_out, int *lb_out, int &nloads) {
+  int la = -5, lb = -5, flags = 0;
+  nloads = 0;
+  for (int t = 0; t < 8; ++t) {
+    const int f = L[t], g = L[t] + 1;
+    if (la == f && lb == g) {
+    } else if (lb == f && la == g) {
+      flags |= 1 << (16 + t);
+    } else if (lb == f) {
+      la = g;
+      flags |= (1 << t) | (1 << (16 + t));
+      nloads += 1;
+    } else if (la == f) {
+      lb = g;
+      flags |= 1 << (8 + t);
+      nloads += 1;
+    } else {
+      la = f, lb = g;
+      flags |= (1 << t) | (1 << (8 + t));
+      nloads += 2;
+    }
+    la_out[t] = la, lb_out[t] = lb;
+  }
+  return flags;
+}
+
+// LDS.128 wavefronts of one quarter-warp request = the largest number of DISTINCT 16-byte
+// words in one of the 8 bank groups.  `occ` is the occupancy bitmap of the request's pixel
+// indices along the lane axis (relative to the smallest one); along either axis the bank
+// group of an index is a bijection of (index mod 8) because the row pitch is odd.
+struct Occ {
+  unsigned long long lo, hi;
+};
+template <bool WIDE>
+__device__ __forceinline__ int bank_multiplicity(Occ o) {
+  int worst = 1;
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    const unsigned long long m = 0x0101010101010101ull << g;
+    int c = __popcll(o.lo & m);
+    if (WIDE) c += __popcll(o.hi & m);
+    worst = max(worst, c);
+  }
+  return worst;
+}
+template <bool WIDE>
+__device__ __forceinline__ void occ_set(Occ &o, int i) {
+  if (!WIDE || i < 64) o.lo |= 1ull << i;
+  else o.hi |= 1ull << (i - 64);
+}
+
+// Best tap order for the lane-axis tap pairs (L[k], R[k]) (bit k set: lane k fetches R first).
+// The 32 lanes of the warp split the 256 orders: lane bits 0-4 fix the order of taps 0-4,
+// the loop runs over the orders of taps 5-7.  Returns cost << 8 | bits of this lane's best.
+template <bool WIDE>
+__device__ __forceinline__ unsigned tap_order_search(const int *L, const int *R, int base, int lane) {
+  Occ f = {0ull, 0ull}, s = {0ull, 0ull};
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    const bool sw = (lane >> k) & 1;
+    occ_set<WIDE>(f, (sw ? R[k] : L[k]) - base);
+    occ_set<WIDE>(s, (sw ? L[k] : R[k]) - base);
+  }
+  unsigned best = 0xffffffffu;
+#pragma unroll 1
+  for (int j = 0; j < 8; ++j) {
+    Occ ff = f, ss = s;
+#pragma unroll
+    for (int k = 5; k < 8; ++k) {
+      const bool sw = (j >> (k - 5)) & 1;
+      occ_set<WIDE>(ff, (sw ? R[k] : L[k]) - base);
+      occ_set<WIDE>(ss, (sw ? L[k] : R[k]) - base);
+    }
+    const unsigned c = (unsigned)(bank_multiplicity<WIDE>(ff) + bank_multiplicity<WIDE>(ss));
+    best = min(best, (c << 8) | (unsigned)(lane | (j << 5)));
+  }
+  return best;
+}
+
+template <bool WIDE>
+__device__ __forceinline__ int tap_order_natural(const int *L, const int *R, int base) {
+  Occ f = {0ull, 0ull}, s = {0ull, 0ull};
+#pragma unroll
+  for (int k = 0; k < 8; ++k) occ_set<WIDE>(f, L[k] - base), occ_set<WIDE>(s, R[k] - base);
+  return bank_multiplicity<WIDE>(f) + bank_multiplicity<WIDE>(s);
+}
+
+// one warp per roi
+__global__ void __launch_bounds__(128)
+    k_roi_plan8_walk(const int *__restrict__ plan, int R, int H, int W, int P,
+                     int *__restrict__ ext) {
+  const int r = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (r >= R) return;
+  const int *pl = plan + (size_t)r * 32;
+  int *e = ext + (size_t)r * 32;
+  int row[8], col[8];
+  bool colv[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int hs = __ldg(pl + i), ws = __ldg(pl + 16 + 2 * i);
+    row[i] = hs >= 0 ? hs : H;  // zero rows H, H+1
+    colv[i] = ws >= 0;
+    col[i] = ws >= 0 ? ws : W;  // zero column
+  }
+  int nl[2], ra[8], rb[8], ca[8], cb[8];
+  const int fl_rows = walk_slots(row, ra, rb, nl[0]), fl_cols = walk_slots(col, ca, cb, nl[1]);
+  // lane-axis tap pairs in index space: mode 0 = columns, mode 1 = rows
+  int L0[8], R0[8], L1[8], R1[8], base0 = 1 << 30, base1 = 1 << 30, top0 = 0, top1 = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    L0[k] = col[k], R0[k] = colv[k] ? col[k] + 1 : col[k];
+    L1[k] = row[k], R1[k] = row[k] + 1;
+    base0 = min(base0, L0[k]), top0 = max(top0, R0[k]);
+    base1 = min(base1, L1[k]), top1 = max(top1, R1[k]);
+  }
+  const int span0 = top0 - base0, span1 = top1 - base1;
+  const bool ok0 = span0 < 128, ok1 = span1 < 128;
+  // natural order first: it is already optimal when it meets the other mode's lower bound
+  // (2 wavefronts per line load); only otherwise search the 256 tap orders of a mode
+  const int lb0 = 2 * nl[0], lb1 = 2 * nl[1];
+  int c0 = 16 * nl[0], c1 = 16 * nl[1];
+  if (ok0) c0 = (span0 < 64 ? tap_order_natural<false>(L0, R0, base0) : tap_order_natural<true>(L0, R0, base0)) * nl[0];
+  if (ok1) c1 = (span1 < 64 ? tap_order_natural<false>(L1, R1, base1) : tap_order_natural<true>(L1, R1, base1)) * nl[1];
+  unsigned best = c1 < c0 ? (((unsigned)c1 << 9) | 256u) : ((unsigned)c0 << 9);  // cost << 9 | mode << 8 | bits
+  const int nat = min(c0, c1);
+  if (ok0 && lb0 < nat && c0 > lb0) {  // warp-uniform
+    const unsigned q = span0 < 64 ? tap_order_search<false>(L0, R0, base0, lane) : tap_order_search<true>(L0, R0, base0, lane);
+    best = min(best, (((q >> 8) * (unsigned)nl[0]) << 9) | (q & 255u));
+  }
+  if (ok1 && lb1 < nat && c1 > lb1) {
+    const unsigned q = span1 < 64 ? tap_order_search<false>(L1, R1, base1, lane) : tap_order_search<true>(L1, R1, base1, lane);
+    best = min(best, (((q >> 8) * (unsigned)nl[1]) << 9) | 256u | (q & 255u));
+  }
+  best = __reduce_min_sync(0xffffffffu, best);
+  const int mode = (best >> 8) & 1, bits = best & 255;
+  if (lane >= 8) return;
+  // lane t writes walk position t and lane-axis entry t; pixel offsets (bytes / 16) stay
+  // below 8192 (host-checked)
+  const int t = lane;
+  const int hs = __ldg(pl + t), ws = __ldg(pl + 16 + 2 * t);
+  const int rowt = hs >= 0 ? hs : H, colt = ws >= 0 ? ws : W;
+  const int hrt = hs >= 0 ? __ldg(pl + 8 + t) : 0, wrt = ws >= 0 ? __ldg(pl + 16 + 2 * t + 1) : 0;
+  const int colt1 = ws >= 0 ? colt + 1 : colt;
+  int sa = 0, sb = 0;  // the lines slots a / b hold at walk position t
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (i == t) sa = mode ? ca[i] : ra[i], sb = mode ? cb[i] : rb[i];
+  const int fl = mode ? fl_cols : fl_rows;
+  // line -> pixel offset: rows scale by the pitch; the line after the zero column is itself
+  const int A = mode ? min(sa, W) : sa * P;
+  const int Bq = mode ? min(sb, W) : sb * P;
+  const int f2 = ((fl >> t) & 1) | (((fl >> (8 + t)) & 1) << 1);
+  e[t] = f2 | (A << 4) | (Bq << 17) | ((t == 0 && mode) ? (1 << 30) : 0);
+  {
+    const float rr = __int_as_float(mode ? wrt : hrt);
+    e[8 + t] = __float_as_int(((fl >> (16 + t)) & 1) ? 1.f - rr : rr);
+  }
+  const int Lk = mode ? rowt * P : colt;
+  const int Rk = mode ? (rowt + 1) * P : colt1;
+  const float w = __int_as_float(mode ? hrt : wrt);
+  const bool sw = (bits >> t) & 1;
+  const int first = sw ? Rk : Lk, second = sw ? Lk : Rk;
+  e[16 + 2 * t] = (first & 0xffff) | ((second - first) << 16);
+  e[17 + 2 * t] = __float_as_int(sw ? 1.f - w : w);
+}
+
+// one warp per image: stable partition of its roi list by walk mode (mode 0 first)
+__global__ void k_roi_order_by_mode(const int *__restrict__ ext, const int *__restrict__ order,
+                                    const int *__restrict__ img_off, int *__restrict__ order2) {
+  const int b = blockIdx.x, lane = threadIdx.x;
+  const int r0 = img_off[b], r1 = img_off[b + 1];
+  int n0 = 0;
+  for (int base = r0; base < r1; base += 32) {
+    const int i = base + lane;
+    const bool m0 = i < r1 && !((ext[(size_t)order[i] * 32] >> 30) & 1);
+    n0 += __popc(__ballot_sync(0xffffffffu, m0));
+  }
+  int c0 = r0, c1 = r0 + n0;
+  for (int base = r0; base < r1; base += 32) {
+    const int i = base + lane;
+    const bool in = i < r1;
+    const int r = in ? order[i] : 0;
+    const bool m1 = in && ((ext[(size_t)r * 32] >> 30) & 1);
+    const unsigned b0 = __ballot_sync(0xffffffffu, in && !m1), b1 = __ballot_sync(0xffffffffu, m1);
+    const unsigned below = (1u << lane) - 1u;
+    if (in) order2[m1 ? c1 + __popc(b1 & below) : c0 + __popc(b0 & below)] = r;
+    c0 += __popc(b0);
+    c1 += __popc(b1);
+  }
+}
+
+struct WalkRec {
+  int w[8];     // packed walk positions
+  float rt[8];  // walk ratios
+  int la;       // packed lane taps
+  float wa;     // lane ratio
+};
+
+__device__ __forceinline__ void walk_rec_clear(WalkRec &p) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) p.w[i] = 0, p.rt[i] = 0.f;
+  p.la = 0, p.wa = 0.f;
+}
+
+__device__ __forceinline__ void walk_rec_load(const int *__restrict__ ext, int r, int k, WalkRec &p) {
+  const int4 *q = reinterpret_cast<const int4 *>(ext + (size_t)r * 32);
+  const int4 a0 = __ldg(q), a1 = __ldg(q + 1), c0 = __ldg(q + 2), c1 = __ldg(q + 3);
+  p.w[0] = a0.x, p.w[1] = a0.y, p.w[2] = a0.z, p.w[3] = a0.w;
+  p.w[4] = a1.x, p.w[5] = a1.y, p.w[6] = a1.z, p.w[7] = a1.w;
+  p.rt[0] = __int_as_float(c0.x), p.rt[1] = __int_as_float(c0.y);
+  p.rt[2] = __int_as_float(c0.z), p.rt[3] = __int_as_float(c0.w);
+  p.rt[4] = __int_as_float(c1.x), p.rt[5] = __int_as_float(c1.y);
+  p.rt[6] = __int_as_float(c1.z), p.rt[7] = __int_as_float(c1.w);
+  const int2 l = __ldg(reinterpret_cast<const int2 *>(ext + (size_t)r * 32 + 16) + k);
+  p.la = l.x;
+  p.wa = __int_as_float(l.y);
+}
 
 // bulk async store shared -> global (TMA engine, SASS: UBLKCP), tracked by bulk groups
-__device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, uint32_t bytes) {
+__device__ __forceinline__ void bulk_s2g_nocommit(void *dst_gmem, const void *src_smem, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem),
                "r"(smem_u32(src_smem)), "r"(bytes)
                : "memory");
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
-__device__ __forceinline__ float lds_f32(uint32_t smem_addr) {
-  float v;
-  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(smem_addr));
-  return v;
+__device__ __forceinline__ void bulk_commit() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() {
@@ -285,194 +545,228 @@ __device__ __forceinline__ void fence_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-// ----------------------------------------------------------------------------------------
-// Shared-memory layout of the forward kernel.  The CTA's 4 channel planes are interleaved per
-// pixel, planes4[pix] = (c0, c1, c2, c3); lane (ch, pw) reads word 4*pix + ch, so lanes of
-// different channels can never collide on a bank (bank = 4*(pix mod 8) + ch).  Inside a row the
-// column is XOR-swizzled, col' = col ^ ((col >> 3) & 7) (identity in the last partial group of
-// 8), so the 8 sample columns of a roi fall on distinct bank groups for strides 1, 2, 3, 4 ...
-// as well.  Two extra all-zero rows (H, H+1) stand in for out-of-range sample rows and one
-// zero pixel for out-of-range sample columns: validity never appears in the hot loop.
-//
-// k_roi_plan8_fwd turns the generic plan into the forward kernel's per-roi record (64 words):
-//   [0..7]   byte offset of sample row ph inside planes4 (the zero row when invalid)
-//   [8..15]  row ratio hr (0 when invalid)
-//   [16]     flags: bit ph = both rows must be (re)loaded, bit 8+ph = shift or reload,
-//            bit 16+ph = shift only (the lower row becomes the previous upper row)
-//   [32+4pw..] per sample column: c0 = byte offset of the swizzled left tap, dc = offset of
-//            the right tap relative to it, m = 1 (0: column invalid -> c0 is the zero pixel and
-//            the row offset is multiplied away), wr = column ratio
-// ----------------------------------------------------------------------------------------
-__device__ __forceinline__ int swz_col(int col, int W8) {
-  return col < W8 ? (col ^ ((col >> 3) & 7)) : col;
-}
-
-__global__ void k_roi_plan8_fwd(const int *__restrict__ plan, int R, int H, int W,
-                                int *__restrict__ ext) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= R) return;
-  const int *pl = plan + (size_t)r * 32;
-  int *e = ext + (size_t)r * 64;
-  const int W8 = W & ~7;
-  const int row_bytes = 16 * W;
-  int prev = -5;  // row index of the previous sample row (zero rows count as row H)
-  int flags = 0;
-  for (int ph = 0; ph < 8; ++ph) {
-    const int hs = pl[ph];
-    const int row = hs >= 0 ? hs : H;
-    e[ph] = row * row_bytes;
-    e[8 + ph] = hs >= 0 ? pl[8 + ph] : 0;
-    if (row == prev) {
-      // keep both interpolated rows
-    } else if (row == prev + 1) {
-      flags |= (1 << (8 + ph)) | (1 << (16 + ph));
-    } else {
-      flags |= (1 << ph) | (1 << (8 + ph));
-    }
-    prev = row;
-  }
-  e[16] = flags;
-  for (int pw = 0; pw < 8; ++pw) {
-    const int ws = pl[16 + 2 * pw];
-    int c0, dc, m;
-    if (ws >= 0) {
-      c0 = 16 * swz_col(ws, W8);
-      dc = 16 * swz_col(ws + 1, W8) - c0;
-      m = 1;
-    } else {
-      c0 = H * row_bytes;  // pixel 0 of the first zero row; its lower neighbour is zero too
-      dc = 0;
-      m = 0;
-    }
-    e[32 + 4 * pw + 0] = c0;
-    e[32 + 4 * pw + 1] = dc;
-    e[32 + 4 * pw + 2] = m;
-    e[32 + 4 * pw + 3] = pl[16 + 2 * pw + 1];
-  }
-}
-
-struct Plan8F {
-  int roff[8];
-  float hr[8];
-  int flags;
-  int c0, dc, m;
-  float wr;
+// One walk position for 4 channels, fully predicated on two flag bits of this lane's roi:
+//   bit 0: fetch the line of slot a (t0);  bit 1: fetch the line of slot b (t1).
+//   line value = x0 + wa * (x1 - x0) over the lane's two taps; s = t0 + r' * (t1 - t0).
+// One PTX block so that the predicates guard the LDS.128 and the FFMAs directly: the four
+// rois of a warp follow different flag patterns without a single divergent branch.
+// The tap registers (x, y: first line, z, w: second line) are C++ variables handed in as
+// read-write operands: a predicated load does not kill its destination, so block-local PTX
+// temporaries would be live across the whole loop and cost 16 registers PER walk position.
+struct WalkTaps {
+  float4 x, y, z, w;
 };
 
-__device__ __forceinline__ void load_plan8f(const int *__restrict__ ext, int r, int pw, Plan8F &p) {
-  const int4 *q = reinterpret_cast<const int4 *>(ext + (size_t)r * 64);
-  const int4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3);
-  p.roff[0] = a.x, p.roff[1] = a.y, p.roff[2] = a.z, p.roff[3] = a.w;
-  p.roff[4] = b.x, p.roff[5] = b.y, p.roff[6] = b.z, p.roff[7] = b.w;
-  p.hr[0] = __int_as_float(c.x), p.hr[1] = __int_as_float(c.y);
-  p.hr[2] = __int_as_float(c.z), p.hr[3] = __int_as_float(c.w);
-  p.hr[4] = __int_as_float(d.x), p.hr[5] = __int_as_float(d.y);
-  p.hr[6] = __int_as_float(d.z), p.hr[7] = __int_as_float(d.w);
-  p.flags = __ldg(ext + (size_t)r * 64 + 16);
-  const int4 w = __ldg(q + 8 + pw);
-  p.c0 = w.x, p.dc = w.y, p.m = w.z;
-  p.wr = __int_as_float(w.w);
+__device__ __forceinline__ void walk_step(float4 &t0, float4 &t1, float4 &s, WalkTaps &q,
+                                          uint32_t pa, uint32_t pb, uint32_t pa2, uint32_t pb2,
+                                          float wa, float r, int flags) {
+  asm volatile(
+      "{\n"
+      ".reg .pred pr, pd;\n"
+      ".reg .b32 tt;\n"
+      ".reg .f32 d;\n"
+      "and.b32 tt, %34, 1;\n"
+      "setp.ne.b32 pr, tt, 0;\n"
+      "and.b32 tt, %34, 2;\n"
+      "setp.ne.b32 pd, tt, 0;\n"
+      "@pr ld.shared.v4.f32 {%12, %13, %14, %15}, [%28];\n"
+      "@pr ld.shared.v4.f32 {%16, %17, %18, %19}, [%29];\n"
+      "@pd ld.shared.v4.f32 {%20, %21, %22, %23}, [%30];\n"
+      "@pd ld.shared.v4.f32 {%24, %25, %26, %27}, [%31];\n"
+      "@pr sub.f32 d, %16, %12;\n"
+      "@pr fma.rn.f32 %0, %32, d, %12;\n"
+      "@pr sub.f32 d, %17, %13;\n"
+      "@pr fma.rn.f32 %1, %32, d, %13;\n"
+      "@pr sub.f32 d, %18, %14;\n"
+      "@pr fma.rn.f32 %2, %32, d, %14;\n"
+      "@pr sub.f32 d, %19, %15;\n"
+      "@pr fma.rn.f32 %3, %32, d, %15;\n"
+      "@pd sub.f32 d, %24, %20;\n"
+      "@pd fma.rn.f32 %4, %32, d, %20;\n"
+      "@pd sub.f32 d, %25, %21;\n"
+      "@pd fma.rn.f32 %5, %32, d, %21;\n"
+      "@pd sub.f32 d, %26, %22;\n"
+      "@pd fma.rn.f32 %6, %32, d, %22;\n"
+      "@pd sub.f32 d, %27, %23;\n"
+      "@pd fma.rn.f32 %7, %32, d, %23;\n"
+      "sub.f32 d, %4, %0;\n"
+      "fma.rn.f32 %8, %33, d, %0;\n"
+      "sub.f32 d, %5, %1;\n"
+      "fma.rn.f32 %9, %33, d, %1;\n"
+      "sub.f32 d, %6, %2;\n"
+      "fma.rn.f32 %10, %33, d, %2;\n"
+      "sub.f32 d, %7, %3;\n"
+      "fma.rn.f32 %11, %33, d, %3;\n"
+      "}\n"
+      : "+f"(t0.x), "+f"(t0.y), "+f"(t0.z), "+f"(t0.w), "+f"(t1.x), "+f"(t1.y), "+f"(t1.z),
+        "+f"(t1.w), "=f"(s.x), "=f"(s.y), "=f"(s.z), "=f"(s.w), "+f"(q.x.x), "+f"(q.x.y),
+        "+f"(q.x.z), "+f"(q.x.w), "+f"(q.y.x), "+f"(q.y.y), "+f"(q.y.z), "+f"(q.y.w),
+        "+f"(q.z.x), "+f"(q.z.y), "+f"(q.z.z), "+f"(q.z.w), "+f"(q.w.x), "+f"(q.w.y),
+        "+f"(q.w.z), "+f"(q.w.w)
+      : "r"(pa), "r"(pb), "r"(pa2), "r"(pb2), "f"(wa), "f"(r), "r"(flags));
+}
+
+// four staged values of one lane (channels 0..3, OHW floats apart), stored only when p
+__device__ __forceinline__ void sts4_if(float *q, int ohw_bytes, float4 v, bool p) {
+  const uint32_t a = smem_u32(q);
+  asm volatile(
+      "{\n"
+      ".reg .pred pp;\n"
+      "setp.ne.b32 pp, %5, 0;\n"
+      "@pp st.shared.f32 [%0], %1;\n"
+      "@pp st.shared.f32 [%6], %2;\n"
+      "@pp st.shared.f32 [%7], %3;\n"
+      "@pp st.shared.f32 [%8], %4;\n"
+      "}\n" ::"r"(a),
+      "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"((int)p), "r"(a + ohw_bytes), "r"(a + 2 * ohw_bytes),
+      "r"(a + 3 * ohw_bytes)
+      : "memory");
 }
 
 template <int POOL>
-__global__ void __launch_bounds__(kFwdThreads, 3)
-    k_align8_fwd_planes(const float *__restrict__ feat, const int *__restrict__ ext,
-                        const int *__restrict__ order, const int *__restrict__ img_off, int C,
-                        int H, int W, int n_chunks, float *__restrict__ out) {
+__device__ __forceinline__ float pool2(float a, float b) {
+  return POOL == RLOD_POOL_AVG ? a + b : fmaxf(a, b);
+}
+template <int POOL>
+__device__ __forceinline__ float4 pool2(float4 a, float4 b) {
+  return make_float4(pool2<POOL>(a.x, b.x), pool2<POOL>(a.y, b.y), pool2<POOL>(a.z, b.z),
+                     pool2<POOL>(a.w, b.w));
+}
+
+template <int POOL>
+__global__ void __launch_bounds__(kWalkThreads, 2)
+    k_align8_fwd_walk(const float *__restrict__ feat, const int *__restrict__ ext,
+                      const int *__restrict__ order, const int *__restrict__ img_off, int C,
+                      int H, int W, int P, int n_chunks, float *__restrict__ out) {
   constexpr int OW = POOL == RLOD_POOL_NONE ? 8 : 7;
-  constexpr int OHW = OW * OW;   // 64 | 49
-  constexpr int STG = 4 * OHW;   // floats per (roi, 4 channels): 256 | 196
+  constexpr int OHW = OW * OW;                            // 64 | 49
+  constexpr int STG = 4 * OHW;                            // floats per (roi, 4 channels)
+  constexpr int SLOT = POOL == RLOD_POOL_NONE ? 264 : 200;  // = 8 (mod 32): slots bank-disjoint
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float4 *planes4 = reinterpret_cast<float4 *>(smem_raw);
-  const int HW = H * W, W8 = W & ~7;
-  float *stage = reinterpret_cast<float *>(planes4 + HW + 2 * W);
+  const int HW = H * W;
+  float *stage = reinterpret_cast<float *>(planes4 + (H + 2) * P);
 
   const int b = blockIdx.x / n_chunks, chunk = blockIdx.x - b * n_chunks;
   const int r0 = img_off[b], r1 = img_off[b + 1];
   if (r0 >= r1) return;
   const float *src = feat + ((size_t)b * C + (size_t)chunk * 4) * HW;
-#pragma unroll 4
-  for (int p = threadIdx.x; p < HW; p += kFwdThreads) {
-    const int y = p / W, x = p - y * W;
-    planes4[y * W + swz_col(x, W8)] = make_float4(__ldg(src + p), __ldg(src + HW + p),
-                                                  __ldg(src + 2 * HW + p), __ldg(src + 3 * HW + p));
+  // HBM -> shared memory with 4-byte async copies (LDGSTS): the channel interleave happens in
+  // flight, nothing is staged in registers and the CTA's whole 4-plane read is outstanding at
+  // once instead of a few loads per thread.  Consecutive lanes take the 4 channels of one
+  // pixel, then the next pixel: a warp writes one contiguous 128-byte line of shared memory
+  // and reads four full 32-byte sectors.
+  {
+    const int c = threadIdx.x & 3;
+    constexpr int kStep = kWalkThreads / 4;  // pixels per sweep of the CTA
+    int p = threadIdx.x >> 2;
+    int y = p / W, x = p - y * W;
+    const int dy = kStep / W, dx = kStep - dy * W;
+    const float *sc = src + (size_t)c * HW;
+    const uint32_t pb0 = smem_u32(planes4) + 4u * c;
+    for (; p < HW; p += kStep) {
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(pb0 + 16u * (uint32_t)(y * P + x)), "l"(sc + p)
+                   : "memory");
+      x += dx, y += dy;
+      if (x >= W) x -= W, ++y;
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   }
-  for (int p = threadIdx.x; p < 2 * W; p += kFwdThreads) planes4[HW + p] = make_float4(0.f, 0.f, 0.f, 0.f);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = kFwdThreads >> 5;
-  const int pw = lane & 7, ch = lane >> 3;
-  const uint32_t pbase = smem_u32(planes4) + 4u * (uint32_t)ch;  // word 4*pix + ch
-  const uint32_t w16 = 16u * (uint32_t)W;                           // bytes per plane row
-  float *stg = stage + warp * (2 * STG);
-
-  int k = r0 + warp;
-  Plan8F cur;
-  int r = 0;
-  if (k < r1) {
-    r = order[k];
-    load_plan8f(ext, r, pw, cur);
+  {
+    const int padw = P - W;  // zero columns W .. P-1 of the data rows, then the two zero rows
+    for (int p = threadIdx.x; p < H * padw; p += kWalkThreads) {
+      const int y = p / padw, x = W + (p - y * padw);
+      planes4[y * P + x] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int p = threadIdx.x; p < 2 * P; p += kWalkThreads) planes4[H * P + p] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k = lane & 7, slot = lane >> 3;
+  const uint32_t pbase = smem_u32(planes4);
+  float *stg = stage + (warp * 2) * (4 * SLOT) + slot * SLOT;  // + (it & 1) * 4 * SLOT
+  const int n_groups = (r1 - r0 + 3) >> 2;
+
+  // the record of the NEXT group travels in registers while this one is computed (18 words),
+  // and the roi id of the group after that one too (order -> record is a dependent pair of
+  // loads: issued back to back it would stall the warp for an L2 round trip every iteration)
+  auto roi_of = [&](int gg) {
+    const int kk = r0 + 4 * gg + slot;
+    return (gg < n_groups && kk < r1) ? __ldg(order + kk) : -1;
+  };
+  WalkRec cur;
+  walk_rec_clear(cur);
+  int r = roi_of(warp);
+  if (r >= 0) walk_rec_load(ext, r, k, cur);
+  int rn = roi_of(warp + kWalkWarps);
+  WalkTaps taps[2];  // two sets: position T+1 loads while T computes
+  taps[0].x = taps[0].y = taps[0].z = taps[0].w = make_float4(0.f, 0.f, 0.f, 0.f);
+  taps[1] = taps[0];
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
 
-  for (int it = 0; k < r1; k += nw, ++it) {
-    // prefetch the next roi's plan while this one is computed
-    Plan8F nxt;
-    int rn = 0;
-    if (k + nw < r1) {
-      rn = order[k + nw];
-      load_plan8f(ext, rn, pw, nxt);
-    }
-    const float wr = cur.wr;
-    const uint32_t cbase = pbase + (uint32_t)cur.c0;
-    const int fl = cur.flags;  // warp-uniform: the sample rows come from the roi alone
-    float s[8];
-    float t0 = 0.f, t1 = 0.f;
-#pragma unroll
-    for (int ph = 0; ph < 8; ++ph) {
-      // warp-uniform flag bits: which of the two interpolated rows must be refreshed
-      const bool reload = (fl >> ph) & 1, adv = (fl >> (8 + ph)) & 1, shift = (fl >> (16 + ph)) & 1;
-      const uint32_t pa = cbase + (uint32_t)(cur.roff[ph] * cur.m);
-      const uint32_t pb = pa + (uint32_t)cur.dc;
-      if (shift) t0 = t1;
-      if (reload) {
-        const float x0 = lds_f32(pa), x1 = lds_f32(pb);
-        t0 = fmaf(wr, x1 - x0, x0);
-      }
-      if (adv) {
-        const float y0 = lds_f32(pa + w16), y1 = lds_f32(pb + w16);
-        t1 = fmaf(wr, y1 - y0, y0);
-      }
-      s[ph] = fmaf(cur.hr[ph], t1 - t0, t0);
-    }
+  for (int g = warp, it = 0; g < n_groups; g += kWalkWarps, ++it) {
+    WalkRec nxt;
+    walk_rec_clear(nxt);
+    if (rn >= 0) walk_rec_load(ext, rn, k, nxt);
+    const int rnn = roi_of(g + 2 * kWalkWarps);
+    float *sbuf = stg + (it & 1) * (4 * SLOT);
+    const bool mode1 = (cur.w[0] >> 30) & 1;
+    const int st_t = mode1 ? 1 : OW, st_k = mode1 ? OW : 1;
+    float *sp = sbuf + k * st_k;
+    const uint32_t cbase = pbase + (((uint32_t)cur.la & 0xffffu) << 4);
+    const uint32_t da = (uint32_t)((cur.la >> 16) << 4);
+    float4 s[8];
+    float4 t0 = make_float4(0.f, 0.f, 0.f, 0.f), t1 = t0;
+#define RLOD_WALK(T)                                                                        \
+  {                                                                                         \
+    const uint32_t pa = cbase + ((uint32_t)cur.w[T] & 0x1fff0u);                            \
+    const uint32_t pa2 = cbase + (((uint32_t)cur.w[T] >> 13) & 0x1fff0u);                   \
+    walk_step(t0, t1, s[T], taps[(T) & 1], pa, pa + da, pa2, pa2 + da, cur.wa, cur.rt[T], cur.w[T]); \
+  }
+    // output of walk position T: NONE stores the sample itself; AVG / MAX pool 2x2 stride 1,
+    // along the walk axis in registers and along the lane axis with one shuffle per value
+#define RLOD_EMIT(T)                                                                        \
+  if (POOL == RLOD_POOL_NONE) {                                                             \
+    float *q = sp + (T) * st_t;                                                             \
+    q[0] = s[T].x, q[OHW] = s[T].y, q[2 * OHW] = s[T].z, q[3 * OHW] = s[T].w;               \
+  } else if ((T) < 7) {                                                                     \
+    const float4 v = pool2<POOL>(s[T], s[(T) < 7 ? (T) + 1 : 7]);                           \
+    float4 n;                                                                               \
+    n.x = __shfl_down_sync(0xffffffffu, v.x, 1, 8);                                         \
+    n.y = __shfl_down_sync(0xffffffffu, v.y, 1, 8);                                         \
+    n.z = __shfl_down_sync(0xffffffffu, v.z, 1, 8);                                         \
+    n.w = __shfl_down_sync(0xffffffffu, v.w, 1, 8);                                         \
+    float4 o = pool2<POOL>(v, n);                                                           \
+    if (POOL == RLOD_POOL_AVG) o = make_float4(o.x * 0.25f, o.y * 0.25f, o.z * 0.25f, o.w * 0.25f); \
+    sts4_if(sp + (T) * st_t, OHW * 4, o, k < 7);                                            \
+  }
+    // software pipeline: the stores of position T-2 sit in the shadow of the loads of T
+    RLOD_WALK(0) RLOD_WALK(1) RLOD_WALK(2)
     // the buffer about to be written was handed to the bulk-copy engine two iterations ago
     if (it >= 2) {
-      if (lane == 0) bulk_wait_read<1>();
+      if (k == 0) bulk_wait_read<1>();
       __syncwarp();
     }
-    float *sbuf = stg + (it & 1) * STG;
-    float *sb = sbuf + ch * OHW;
-    if (POOL == RLOD_POOL_NONE) {
-#pragma unroll
-      for (int ph = 0; ph < 8; ++ph) sb[ph * 8 + pw] = s[ph];
-    } else {
-      float sr[8];
-#pragma unroll
-      for (int ph = 0; ph < 8; ++ph) sr[ph] = __shfl_down_sync(0xffffffffu, s[ph], 1);
-      if (pw < 7) {
-#pragma unroll
-        for (int i = 0; i < 7; ++i) sb[i * 7 + pw] = pool4<POOL>(s[i], sr[i], s[i + 1], sr[i + 1]);
-      }
-    }
+    RLOD_EMIT(0) RLOD_WALK(3) RLOD_EMIT(1)
+    RLOD_WALK(4) RLOD_EMIT(2) RLOD_WALK(5) RLOD_EMIT(3) RLOD_WALK(6) RLOD_EMIT(4)
+    RLOD_WALK(7) RLOD_EMIT(5) RLOD_EMIT(6) RLOD_EMIT(7)
+#undef RLOD_WALK
+#undef RLOD_EMIT
     // 4 channels x OHW floats are one contiguous, 16-byte aligned run of the (R,C,OH,OW)
-    // output: hand the staged block to the TMA engine as a single bulk store
+    // output: each roi's staged block leaves as a single bulk store
     fence_async_smem();
     __syncwarp();
-    if (lane == 0)
-      bulk_s2g(out + ((size_t)r * C + (size_t)chunk * 4) * OHW, sbuf, (uint32_t)(STG * sizeof(float)));
+    if (k == 0) {
+      if (r >= 0)
+        bulk_s2g_nocommit(out + ((size_t)r * C + (size_t)chunk * 4) * OHW, sbuf, (uint32_t)(STG * sizeof(float)));
+      bulk_commit();
+    }
     cur = nxt;
     r = rn;
+    rn = rnn;
   }
-  if (lane == 0) bulk_wait_read<0>();  // shared memory must outlive the engine's reads
+  if (k == 0) bulk_wait_read<0>();  // shared memory must outlive the engine's reads
 }
 
 // ----------------------------------------------------------------------------------------
@@ -723,9 +1017,9 @@ static int build_plan(const float *rois, int B, int H, int W, int R, int GH, int
   return launch_status();
 }
 
-static size_t fwd_planes_smem(int H, int W, int pool_mode) {
-  const int stg = 4 * (pool_mode == RLOD_POOL_NONE ? 64 : 49);
-  return (size_t)16 * ((size_t)H * W + 2 * W) + (size_t)(kFwdThreads / 32) * 2 * stg * 4;
+static size_t fwd_walk_smem(int H, int W, int pool_mode) {
+  const int slot = pool_mode == RLOD_POOL_NONE ? 264 : 200;
+  return (size_t)16 * (size_t)(H + 2) * walk_pitch(W) + (size_t)kWalkWarps * 2 * 4 * slot * 4;
 }
 
 }  // namespace rlod
@@ -755,22 +1049,25 @@ RLOD_API int rlod_roi_align_forward(const float *feat, const float *rois, int B,
   rc = build_plan(rois, B, H, W, R, GH, GW, spatial_scale, ws, st);
   if (rc) return rc;
 
-  const size_t smem = fwd_planes_smem(H, W, pool_mode);
+  const size_t smem = fwd_walk_smem(H, W, pool_mode);
   const bool fast = GH == 8 && GW == 8 && (C % 4) == 0 && smem <= (size_t)kMaxSmemPerCta &&
-                    ((uintptr_t)out % 16) == 0 && R >= 2 * B;
+                    (H + 2) * walk_pitch(W) <= 8192 && ((uintptr_t)out % 16) == 0 && R >= 2 * B;
   if (fast) {
     const int n_chunks = C / 4;
     const unsigned grid = (unsigned)(B * n_chunks);
+    const int P = walk_pitch(W);
     RLOD_LAUNCH(RLOD_KERNEL_ROI_PLAN, st,
-                k_roi_plan8_fwd<<<(unsigned)cdiv(R, 128), 128, 0, st>>>(ws.plan, R, H, W, ws.ext));
+                k_roi_plan8_walk<<<(unsigned)cdiv(R, 4), 128, 0, st>>>(ws.plan, R, H, W, P, ws.ext));
+    RLOD_LAUNCH(RLOD_KERNEL_ROI_PLAN, st,
+                k_roi_order_by_mode<<<B, 32, 0, st>>>(ws.ext, ws.order, ws.img_off, ws.order2));
 #define RLOD_LAUNCH_FWD(POOL)                                                                  \
   do {                                                                                         \
-    cudaFuncSetAttribute(k_align8_fwd_planes<POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+    cudaFuncSetAttribute(k_align8_fwd_walk<POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                          (int)smem);                                                           \
     ProfScope _ps(RLOD_KERNEL_ALIGN_FWD, st);                                                  \
-    k_align8_fwd_planes<POOL><<<grid, kFwdThreads, smem, st>>>(feat, ws.ext, ws.order,         \
-                                                               ws.img_off, C, H, W, n_chunks,  \
-                                                               out);                           \
+    k_align8_fwd_walk<POOL><<<grid, kWalkThreads, smem, st>>>(feat, ws.ext, ws.order2,         \
+                                                              ws.img_off, C, H, W, P,          \
+                                                              n_chunks, out);                  \
   } while (0)
     if (pool_mode == RLOD_POOL_NONE)
       RLOD_LAUNCH_FWD(RLOD_POOL_NONE);

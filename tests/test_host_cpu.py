@@ -34,8 +34,8 @@ def test_workspace_queries_are_pure_host_arithmetic():
     assert lib.rlod_nms_workspace_bytes(1, 12000) == 188 * 188 * 64 * 8   # [col_block][row] mask
     assert lib.rlod_nms_workspace_bytes(24, 6000) == 24 * 94 * 94 * 64 * 8
     small = lib.rlod_roi_align_workspace_bytes(4, 1024, 7, 7, be.POOL_AVG)
-    # one 128-byte plan + one 256-byte forward-kernel record per roi (8x8 sample grid)
-    assert 1024 * 384 <= small < 1024 * 384 + 64 * 1024
+    # 128-byte plan + 128-byte forward-kernel record + 4-byte order entry per roi (8x8 sample grid)
+    assert 1024 * 260 <= small < 1024 * 260 + 64 * 1024
     assert lib.rlod_proposal_workspace_bytes(1, 9, 37, 62, 12000, 2000) >= 12000 * 16 + 188 * 188 * 512
 
 
