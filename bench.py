@@ -82,6 +82,13 @@ def cpu_step(orc, inputs, anchors, act):
 def cpu_measure(sample_images, repeats, warmup=1):
     from oracle import oracle as orc
     orc.lib()
+    # torchrun exports OMP_NUM_THREADS=1: the CPU arm uses every core this process may run on
+    try:
+        ncores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncores = os.cpu_count() or 1
+    orc.set_threads(ncores)
+    torch.set_num_threads(ncores)
     inputs = make_inputs(7, sample_images)
     anchors = orc.generate_anchors(16, RATIOS, SCALES).astype(np.float32)
     act = orc.action_table(list(ACT_DELTA))
@@ -145,6 +152,8 @@ class ClockSampler:
         import threading
         self.idx, self.samples, self.mask, self.max_mhz = gpu_index, [], 0, None
         self._stop = threading.Event()
+        self._armed = threading.Event()   # samples count only while the timed region runs
+        self._ready = threading.Event()   # NVML is initialised (nvmlInit can take > 50 ms)
         self._thread = threading.Thread(target=self._run, daemon=True)
         self.err = None
 
@@ -156,15 +165,22 @@ class ClockSampler:
             phys = int(visible.split(",")[self.idx]) if visible and visible.split(",")[self.idx].isdigit() else self.idx
             h = nv.nvmlDeviceGetHandleByIndex(phys)
             self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self._ready.set()
             while not self._stop.is_set():
-                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
-                self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
-                time.sleep(0.002)
+                if self._armed.is_set():
+                    self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                    self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                time.sleep(0.001)
         except Exception as e:  # noqa: BLE001 -- clocks are reported, never fatal
             self.err = repr(e)
+            self._ready.set()
 
     def start(self):
         self._thread.start()
+        self._ready.wait(timeout=10)
+
+    def arm(self, on=True):
+        (self._armed.set if on else self._armed.clear)()
 
     def stop(self):
         self._stop.set()
@@ -231,14 +247,16 @@ def run_ours(args, rank, local_rank, world):
     # ---- device-resident throughput (inputs already in HBM) -----------------------------
     dev_in = [t.to(dev) for t in host]
     sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         device_step(dev_in)
     barrier()
     launches0 = lib.rlod_launch_count()
     lib.rlod_profile_enable(1)
-    if rank == 0:
-        sampler.start()
+    sampler.arm(True)
     ms = timed(lambda: device_step(dev_in), args.steps, 0)
+    sampler.arm(False)
     clocks = sampler.stop() if rank == 0 else None
     lib.rlod_profile_enable(0)
     launches = lib.rlod_launch_count() - launches0
@@ -310,19 +328,202 @@ def run_ours(args, rank, local_rank, world):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------
+# --ops: every op of the path next to the reference's own legacy CUDA kernel (oracle/_ref/
+# libref_legacy.so = the reference's .cu files compiled unchanged for sm_100a) on the same GPU.
+# This is the baseline leg north_star asks for ("for ops that are CUDA-only in the reference,
+# the reference's legacy CUDA kernel on the same GPU is reported alongside"); like
+# cpu_baseline it is the only place outside tests/ that executes anything under oracle/.
+# ------------------------------------------------------------------------------------------
+def run_ops(args):
+    import ctypes
+    from oracle import oracle as orc
+    from rlobjectdetection_b200 import synthetic as syn
+    from rlobjectdetection_b200.model import _backend as be
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    P = ctypes.c_void_p
+    leg = orc.ref_legacy()
+    if leg is not None:
+        leg.nms_cuda_compute.restype = None
+        leg.nms_cuda_compute.argtypes = [P, P, P, ctypes.c_int, ctypes.c_int, ctypes.c_float]
+        leg.ROIAlignForwardLaucher.argtypes = [P, ctypes.c_float] + [ctypes.c_int] * 6 + [P, P, P]
+        leg.ROIAlignBackwardLaucher.argtypes = [P, ctypes.c_float] + [ctypes.c_int] * 7 + [P, P, P]
+        leg.ROIPoolForwardLaucher.argtypes = [P, ctypes.c_float] + [ctypes.c_int] * 6 + [P, P, P, P]
+        leg.ROIPoolBackwardLaucher.argtypes = [P, ctypes.c_float] + [ctypes.c_int] * 7 + [P, P, P, P]
+    dp = lambda t: P(t.data_ptr())  # noqa: E731
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def time_us(fn, iters=20, warm=3):
+        for _ in range(warm):
+            fn()
+        ts = []
+        for _ in range(iters):
+            flush.zero_()  # cold L2 for every sample
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e3)
+        return statistics.median(ts)
+
+    peak = 6553.6
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except (OSError, ValueError, KeyError):
+        pass
+    rows = []
+
+    def add(name, alg_bytes, ours, legacy, note=""):
+        r = {"op": name, "ours_us": round(ours, 1), "legacy_cuda_us": None if legacy is None else round(legacy, 1),
+             "speedup": None if legacy is None else round(legacy / ours, 1), "alg_bytes": alg_bytes,
+             "gbs": round(alg_bytes / ours / 1e3, 1), "hbm_frac": round(alg_bytes / ours / 1e3 / peak, 3), "note": note}
+        rows.append(r)
+        print(json.dumps(r), file=sys.stderr, flush=True)
+
+    def align_case(tag, B, C, H, W, n_per, seed):
+        g = torch.Generator().manual_seed(seed)
+        feat = torch.randn(B, C, H, W, generator=g).to(dev)
+        rois = syn.rois_for_batch(seed + 1, B, n_per, H * 16.0, W * 16.0).to(dev)
+        R = rois.size(0)
+        gout = torch.randn(R, C, 7, 7, generator=g).to(dev)
+        fb = 4 * (B * C * H * W + 5 * R + R * C * 49)
+        # forward
+        ours = time_us(lambda: be.roi_align_forward(feat, rois, 7, 7, 1 / 16.0, be.POOL_AVG))
+        lg = None
+        if leg is not None:
+            top = torch.empty(R, C, 8, 8, device=dev)
+
+            def legacy_fwd():
+                top.zero_()  # functions/roi_align.py:22
+                leg.ROIAlignForwardLaucher(dp(feat), 1 / 16.0, R, H, W, C, 8, 8, dp(rois), dp(top),
+                                           P(torch.cuda.current_stream().cuda_stream))
+                return torch.nn.functional.avg_pool2d(top, kernel_size=2, stride=1)  # modules/roi_align.py:29
+            lg = time_us(legacy_fwd, iters=8, warm=2)
+        add(f"RoIAlignAvg fwd {tag}", fb, ours, lg, f"B={B} C={C} {H}x{W} R={R}")
+        # backward
+        ours = time_us(lambda: be.roi_align_backward(gout, rois, None, (B, C, H, W), 7, 7, 1 / 16.0, be.POOL_AVG))
+        lg = None
+        if leg is not None:
+            bottom = torch.empty(B, C, H, W, device=dev)
+
+            def legacy_bwd():
+                # autograd of avg_pool2d(2,1), then the legacy atomics into a zeroed buffer
+                ggrid = torch.ops.aten.avg_pool2d_backward(gout, top, [2, 2], [1, 1], [0, 0], False, True, None)
+                bottom.zero_()  # functions/roi_align.py:38-39
+                leg.ROIAlignBackwardLaucher(dp(ggrid), 1 / 16.0, B, R, H, W, C, 8, 8, dp(rois), dp(bottom),
+                                            P(torch.cuda.current_stream().cuda_stream))
+            lg = time_us(legacy_bwd, iters=8, warm=2)
+        add(f"RoIAlignAvg bwd {tag}", fb, ours, lg, f"B={B} C={C} {H}x{W} R={R}")
+        return feat, rois, gout
+
+    feat, rois, gout = align_case("C2", 4, 1024, 38, 63, 256, 1)
+    # RoIPool at C2
+    B, C, H, W = feat.shape
+    R = rois.size(0)
+    pb = 4 * (B * C * H * W + 5 * R + 2 * R * C * 49)
+    ours = time_us(lambda: be.roi_pool_forward(feat, rois, 7, 7, 1 / 16.0))
+    out, am = be.roi_pool_forward(feat, rois, 7, 7, 1 / 16.0)
+    lg = lgb = None
+    if leg is not None:
+        top = torch.empty(R, C, 7, 7, device=dev)
+        arg = torch.empty(R, C, 7, 7, dtype=torch.int32, device=dev)
+        st = lambda: P(torch.cuda.current_stream().cuda_stream)  # noqa: E731
+
+        def legacy_pool():
+            top.zero_(), arg.zero_()  # functions/roi_pool.py:17-18
+            leg.ROIPoolForwardLaucher(dp(feat), 1 / 16.0, R, H, W, C, 7, 7, dp(rois), dp(top), dp(arg), st())
+        lg = time_us(legacy_pool, iters=8, warm=2)
+        bottom = torch.empty(B, C, H, W, device=dev)
+
+        def legacy_pool_bwd():
+            bottom.zero_()
+            leg.ROIPoolBackwardLaucher(dp(gout), 1 / 16.0, B, R, H, W, C, 7, 7, dp(rois), dp(bottom), dp(arg), st())
+        lgb = time_us(legacy_pool_bwd, iters=3, warm=1)
+    add("RoIPool fwd C2", pb, ours, lg)
+    ours = time_us(lambda: be.roi_pool_backward(gout, am, rois, (B, C, H, W), 7, 7, 1 / 16.0))
+    add("RoIPool bwd C2", pb, ours, lgb, "legacy = O(B*C*H*W*R) gather")
+    del feat, rois, gout, out, am
+    align_case("C4", 24, 1024, 50, 75, 300, 3)
+
+    # NMS, C1 size: 12000 sorted boxes, thr 0.7
+    g = torch.Generator().manual_seed(0)
+    n = 12000
+    bx = syn.random_boxes(g, n, 600, 1000, 8.0, 300.0)
+    sc = syn.distinct_scores(g, (n,)).sort(descending=True).values
+    dets = torch.cat([bx, sc[:, None]], 1).contiguous()
+    d = dets.to(dev)
+    ours = time_us(lambda: be.nms_padded(d, 0.7))
+    lg = None
+    if leg is not None:
+        host = np.ascontiguousarray(dets.numpy())
+        keep = torch.zeros(n, dtype=torch.int32, device=dev)
+        num = torch.zeros(1, dtype=torch.int32, device=dev)
+
+        def legacy_nms():  # as the reference runs it: per-call malloc, mask D2H, host scan (nms_cuda_kernel.cu:87-161)
+            leg.nms_cuda_compute(dp(keep), dp(num), P(host.ctypes.data), n, 5, 0.7)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            legacy_nms()
+        torch.cuda.synchronize()
+        lg = (time.perf_counter() - t0) / 5 * 1e6
+    add("nms n=12000 thr 0.7 (C1)", 20 * n + 4 * n, ours, lg, "legacy timed on the host clock: it synchronises internally")
+    # C5: 64 images x 80 classes x 300 boxes, thr 0.3, one launch
+    dets5, offs = syn.clustered_dets(4, 64, 80, 300, 600, 1000)
+    d5, o5 = dets5.to(dev), offs.to(dev)
+    ours = time_us(lambda: be.nms_batched(d5, o5, 0.3, max_seg=300))
+    lg = None
+    if leg is not None:
+        sample = 256
+        host = np.ascontiguousarray(dets5.numpy())
+        keep = torch.zeros(300, dtype=torch.int32, device=dev)
+        num = torch.zeros(1, dtype=torch.int32, device=dev)
+        offs_h = offs.numpy()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for sgi in range(sample):
+            seg = host[offs_h[sgi]:offs_h[sgi + 1]]
+            leg.nms_cuda_compute(dp(keep), dp(num), P(seg.ctypes.data), seg.shape[0], 5, 0.3)
+        torch.cuda.synchronize()
+        lg = (time.perf_counter() - t0) / sample * (offs_h.size - 1) * 1e6
+    add("per-class nms 64x80x300 thr 0.3 (C5)", 20 * d5.size(0), ours, lg,
+        "legacy = 5120 calls, extrapolated from 256")
+    # proposal layer, C1 (TRAIN cfg) and C4 (TEST cfg, 24 images)
+    for tag, Bp, A, Hh, Ww, imh, imw, pre, post, scales in (("C1 12000->2000", 1, 9, 37, 62, 600, 1000, 12000, 2000, (8, 16, 32)),
+                                                              ("C4 6000->300 x24", 24, 12, 50, 75, 800, 1200, 6000, 300, SCALES)):
+        scores, deltas, im_info = syn.rpn_outputs(5, Bp, A, Hh, Ww, imh, imw, imh / 600.0)
+        anchors = torch.from_numpy(orc.generate_anchors(16, RATIOS, scales).astype(np.float32)).to(dev)
+        sd, dd, ii = scores.to(dev), deltas.to(dev), im_info.to(dev)
+        ours = time_us(lambda: be.proposal_forward(sd, dd, ii, anchors, 16, pre, post, 0.7))
+        add(f"_ProposalLayer {tag}", Bp * (4 * 5 * A * Hh * Ww + 12 + 20 * post), ours, None,
+            "reference = torch ops + per-image nms_gpu; no standalone legacy kernel")
+    out = {"gpu": torch.cuda.get_device_name(0), "hbm_peak_gbs": peak, "timing": "CUDA events, median, L2 flushed before every sample",
+           "ops": rows}
+    with open(os.path.join(ROOT, "profiles", "ops_latest.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print(json.dumps(out), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ops", action="store_true", help="per-op table vs the reference's legacy CUDA kernels")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.ops:
+        if rank == 0:
+            run_ops(args)
         return
     if world > 1:
         import torch.distributed as dist

@@ -16,7 +16,8 @@
 //      from shared memory.  The feature map is read from HBM exactly once, all bilinear taps
 //      are LDS, and each (roi, 4 channels) result is staged in shared memory and leaves as
 //      ONE 784-byte bulk async store (TMA engine).  No 8x8 intermediate tensor exists.
-//   3. backward (k_align8_bwd_bands): a warp owns a band of rows of 4 gradient planes in
+//   3. backward (k_align8_bwd_walk): see the kernel; the old description below is kept short:
+//      a CTA owns 4 gradient planes in
 //      shared memory exclusively, walks the image's rois, and accumulates with plain
 //      LDS/FADD/STS (segmented warp-shuffle reduction resolves intra-roi collisions), so
 //      there is not a single atomic and the result is deterministic.  grad_in is written
@@ -297,7 +298,7 @@ __device__ __forceinline__ void load_plan8(const int *__restrict__ plan, int r, 
 //   [8..15]  r'[t] ratio from slot a to slot b (= 1 - r when the slots hold the pair swapped)
 //   [16+2k]  lane k: low half = pixel offset of the tap it fetches first, high half (signed) =
 //            pixel offset of the other tap relative to it;  [17+2k] ratio from first to second
-// k_roi_order_by_mode then partitions every image's roi list by mode so that the four rois a
+// k_roi_order_by_key then partitions every image's roi list by mode so that the four rois a
 // warp serves together stage their results with the same strides (bank-disjoint stores).
 // ----------------------------------------------------------------------------------------
 constexpr int kWalkWarps = 8;
@@ -399,7 +400,7 @@ __device__ __forceinline__ int tap_order_natural(const int *L, const int *R, int
 
 // one warp per roi
 __global__ void __launch_bounds__(128)
-    k_roi_plan8_walk(const int *__restrict__ plan, int R, int H, int W, int P,
+    k_roi_plan8_walk(const int *__restrict__ plan, int R, int H, int W, int P, int bwd,
                      int *__restrict__ ext) {
   const int r = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (r >= R) return;
@@ -434,6 +435,9 @@ __global__ void __launch_bounds__(128)
   if (ok0) c0 = (span0 < 64 ? tap_order_natural<false>(L0, R0, base0) : tap_order_natural<true>(L0, R0, base0)) * nl[0];
   if (ok1) c1 = (span1 < 64 ? tap_order_natural<false>(L1, R1, base1) : tap_order_natural<true>(L1, R1, base1)) * nl[1];
   unsigned best = c1 < c0 ? (((unsigned)c1 << 9) | 256u) : ((unsigned)c0 << 9);  // cost << 9 | mode << 8 | bits
+  // the backward kernel scatters: it needs mode 0 (one row lock per line) and the natural tap
+  // order (two lanes may not hit one pixel in the same request)
+  if (bwd) best = 0u, c0 = c1 = 0;
   const int nat = min(c0, c1);
   if (ok0 && lb0 < nat && c0 > lb0) {  // warp-uniform
     const unsigned q = span0 < 64 ? tap_order_search<false>(L0, R0, base0, lane) : tap_order_search<true>(L0, R0, base0, lane);
@@ -472,32 +476,50 @@ __global__ void __launch_bounds__(128)
   const float w = __int_as_float(mode ? hrt : wrt);
   const bool sw = (bits >> t) & 1;
   const int first = sw ? Rk : Lk, second = sw ? Lk : Rk;
-  e[16 + 2 * t] = (first & 0xffff) | ((second - first) << 16);
+  if (!bwd) {
+    e[16 + 2 * t] = (first & 0xffff) | ((second - first) << 16);
+  } else {
+    // scatter: lanes of one roi that share a column take turns; rank = position inside the
+    // run of equal columns, maxrank = the longest run - 1 (invalid columns land in the zero
+    // column, whose content is never read: rank 0)
+    int rank = 0, maxrank = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int run = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < i && colv[j] && colv[i] && col[j] == col[i]) ++run;
+      if (i == t) rank = run;
+      maxrank = max(maxrank, run);
+    }
+    e[16 + 2 * t] = (first & 0xffff) | ((second - first) << 16) | (rank << 17) | (maxrank << 20);
+  }
   e[17 + 2 * t] = __float_as_int(sw ? 1.f - w : w);
 }
 
-// one warp per image: stable partition of its roi list by walk mode (mode 0 first)
-__global__ void k_roi_order_by_mode(const int *__restrict__ ext, const int *__restrict__ order,
-                                    const int *__restrict__ img_off, int *__restrict__ order2) {
+// one warp per image: stable counting sort of its roi list by a small key taken from the
+// record -- forward: the walk mode (word 0 bit 30), so that the four rois a warp serves
+// together stage with the same strides; backward: the longest run of lanes that share a
+// column (word 16 bits 20-22), so that a narrow roi does not impose its extra scatter rounds
+// on three wide ones.
+__global__ void k_roi_order_by_key(const int *__restrict__ ext, const int *__restrict__ order,
+                                   const int *__restrict__ img_off, int word, int shift, int nkeys,
+                                   int *__restrict__ order2) {
   const int b = blockIdx.x, lane = threadIdx.x;
   const int r0 = img_off[b], r1 = img_off[b + 1];
-  int n0 = 0;
-  for (int base = r0; base < r1; base += 32) {
-    const int i = base + lane;
-    const bool m0 = i < r1 && !((ext[(size_t)order[i] * 32] >> 30) & 1);
-    n0 += __popc(__ballot_sync(0xffffffffu, m0));
-  }
-  int c0 = r0, c1 = r0 + n0;
-  for (int base = r0; base < r1; base += 32) {
-    const int i = base + lane;
-    const bool in = i < r1;
-    const int r = in ? order[i] : 0;
-    const bool m1 = in && ((ext[(size_t)r * 32] >> 30) & 1);
-    const unsigned b0 = __ballot_sync(0xffffffffu, in && !m1), b1 = __ballot_sync(0xffffffffu, m1);
-    const unsigned below = (1u << lane) - 1u;
-    if (in) order2[m1 ? c1 + __popc(b1 & below) : c0 + __popc(b0 & below)] = r;
-    c0 += __popc(b0);
-    c1 += __popc(b1);
+  const unsigned full = 0xffffffffu, below = (1u << lane) - 1u;
+  int start = r0;
+  for (int key = 0; key < nkeys; ++key) {
+    int c = start;
+    for (int base = r0; base < r1; base += 32) {
+      const int i = base + lane;
+      const int r = i < r1 ? order[i] : 0;
+      const bool hit = i < r1 && ((ext[(size_t)r * 32 + word] >> shift) & (nkeys - 1)) == key;
+      const unsigned m = __ballot_sync(full, hit);
+      if (hit) order2[c + __popc(m & below)] = r;
+      c += __popc(m);
+    }
+    start = c;
   }
 }
 
@@ -844,153 +866,217 @@ __global__ void __launch_bounds__(256)
 }
 
 // ----------------------------------------------------------------------------------------
-// fast backward: 8x8 sample grid.  CTA = one warp = (image, 4 channels, band of rows); the
-// band lives in shared memory and belongs to this warp alone.  lane = (channel, pw).
+// fast backward ("scatter walk"): the transpose of k_align8_fwd_walk.  CTA = (image, 4
+// channels); the 4 gradient planes are accumulated in shared memory (same odd-pitch
+// interleaved layout) and written to HBM once, coalesced -- no global atomics, no memset.
+// A warp serves 4 rois per iteration (8 lanes each, 4 channels per lane):
+//   1. the rois' grad_out tiles (4 channels x OHW floats = one contiguous 784-byte run each)
+//      arrive by bulk async copy (TMA engine), double-buffered per warp behind mbarriers;
+//   2. the gradient of every sample point is rebuilt in registers (AVG: each pooled gradient
+//      / 4 goes to its 2x2 sample window);
+//   3. the sample rows are walked with the forward's two line slots: a slot ACCUMULATES the
+//      line's gradient while consecutive sample rows share it and is flushed when the forward
+//      would have loaded a new line into it.  A flush spreads the 8 sample columns over their
+//      two taps (LDS.128 / 4 FFMA / STS.128 per tap and lane) under a per-row spin lock in
+//      shared memory, because other warps (and the other three rois of this warp) may hold a
+//      line of the same row; lanes of one roi that share a column take turns (rank rounds).
+// Rounding order across rois is therefore not fixed (the reference's atomics are not either).
 // ----------------------------------------------------------------------------------------
-struct BandFlush {
-  float *plane;  // this lane's channel band, row-major [rows][W]
-  int lo, hi, W;
-  int ws;
-  float wr;
-  bool wv, f1, f2, f4, tail;
-};
+// plane[p] += w * v for 4 channels, shared-space LDS.128 / FFMA / STS.128, only where `on`
+__device__ __forceinline__ void smem_axpy4_if(uint32_t p, float w, float4 v, bool on) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      ".reg .f32 a, b, c, d;\n"
+      "setp.ne.b32 q, %6, 0;\n"
+      "@q ld.shared.v4.f32 {a, b, c, d}, [%0];\n"
+      "@q fma.rn.f32 a, %1, %2, a;\n"
+      "@q fma.rn.f32 b, %1, %3, b;\n"
+      "@q fma.rn.f32 c, %1, %4, c;\n"
+      "@q fma.rn.f32 d, %1, %5, d;\n"
+      "@q st.shared.v4.f32 [%0], {a, b, c, d};\n"
+      "}\n" ::"r"(p),
+      "f"(w), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"((int)on)
+      : "memory");
+}
 
-__device__ __forceinline__ void band_flush(const BandFlush &f, int row, float v) {
-  if (row < f.lo || row >= f.hi) return;  // warp-uniform
-  float x = f.wv ? v * (1.f - f.wr) : 0.f;
-  float y = f.wv ? v * f.wr : 0.f;
-  // inclusive segmented scan over runs of equal ws inside each 8-lane channel group
-  float tx = __shfl_up_sync(0xffffffffu, x, 1, 8), ty = __shfl_up_sync(0xffffffffu, y, 1, 8);
-  if (f.f1) x += tx, y += ty;
-  tx = __shfl_up_sync(0xffffffffu, x, 2, 8), ty = __shfl_up_sync(0xffffffffu, y, 2, 8);
-  if (f.f2) x += tx, y += ty;
-  tx = __shfl_up_sync(0xffffffffu, x, 4, 8), ty = __shfl_up_sync(0xffffffffu, y, 4, 8);
-  if (f.f4) x += tx, y += ty;
-  float *p = f.plane + (row - f.lo) * f.W + f.ws;
-  if (f.tail) p[0] += x;  // run tails hold distinct ws: no two lanes share an address
-  __syncwarp();
-  if (f.tail) p[1] += y;
-  __syncwarp();
+// One line of one roi per 8-lane group: v (4 channels) of every lane goes to its two taps
+// p0 / p1 with weights (1 - w1) / w1, under the spin lock of the line's row.  Deliberately
+// NOT inlined: the walk has 18 flush points and the instruction cache matters more than the
+// call.  Memory order inside a warp is program order, so a lane's second tap may be another
+// lane's first tap; lanes that share a column within one request take turns by rank.
+__device__ __noinline__ void row_flush(float4 v, int need, uint32_t p0, uint32_t p1, float w1, int rank,
+                                       int maxrank_warp, uint32_t lock_addr, int k) {
+  const unsigned full = 0xffffffffu;
+  const float w0 = 1.f - w1;
+  while (__any_sync(full, need)) {
+    int got = 0;
+    if (need && k == 0) {
+      asm volatile("atom.shared.cas.b32 %0, [%1], 0, 1;" : "=r"(got) : "r"(lock_addr) : "memory");
+      got = got == 0;
+    }
+    got = __shfl_sync(full, got, 0, 8);
+    const bool go = need && got;
+    if (maxrank_warp == 0) {
+      smem_axpy4_if(p0, w0, v, go);
+      smem_axpy4_if(p1, w1, v, go);
+    } else {
+      for (int rnd = 0; rnd <= maxrank_warp; ++rnd) {
+        smem_axpy4_if(p0, w0, v, go && rank == rnd);
+        smem_axpy4_if(p1, w1, v, go && rank == rnd);
+      }
+    }
+    __syncwarp();
+    // shared-memory accesses of one warp are performed in program order: a plain store after
+    // the updates releases the lock
+    if (go && k == 0) asm volatile("st.volatile.shared.b32 [%0], %1;" ::"r"(lock_addr), "r"(0) : "memory");
+    need = need && !got;
+  }
 }
 
 template <int POOL>
-__global__ void __launch_bounds__(32)
-    k_align8_bwd_bands(const float *__restrict__ gout, const int *__restrict__ plan,
-                       const int *__restrict__ order, const int *__restrict__ img_off, int C,
-                       int H, int W, int n_chunks, int n_bands, int band_rows, int accumulate,
-                       float *__restrict__ gin) {
+__global__ void __launch_bounds__(kWalkThreads, 2)
+    k_align8_bwd_walk(const float *__restrict__ gout, const int *__restrict__ ext,
+                      const int *__restrict__ order, const int *__restrict__ img_off, int C,
+                      int H, int W, int P, int n_chunks, int accumulate, int lock_mul,
+                      float *__restrict__ gin) {
   constexpr int OW = POOL == RLOD_POOL_NONE ? 8 : 7;
   constexpr int OHW = OW * OW;
   constexpr int STG = 4 * OHW;
-  extern __shared__ __align__(16) float bsm[];
-  float *stage = bsm;          // STG floats (16-byte aligned for the float4 staging writes)
-  float *band = bsm + STG;     // [4][band_rows * W]
-  const int lane = threadIdx.x, pw = lane & 7, ch = lane >> 3;
-  int t = blockIdx.x;
-  const int bandi = t % n_bands;
-  t /= n_bands;
-  const int chunk = t % n_chunks;
-  const int b = t / n_chunks;
-  const int lo = bandi * band_rows, hi = min(H, lo + band_rows);
-  const int rows = hi - lo, bstride = band_rows * W;
-  const size_t gbase = ((size_t)b * C + (size_t)chunk * 4) * ((size_t)H * W);
-  for (int i = lane; i < 4 * rows * W; i += 32) {
-    const int c = i / (rows * W), o = i - c * (rows * W);
-    band[c * bstride + o] = accumulate ? gin[gbase + (size_t)c * H * W + (size_t)lo * W + o] : 0.f;
-  }
-  __syncwarp();
+  constexpr int SLOT = POOL == RLOD_POOL_NONE ? 264 : 200;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float4 *planes4 = reinterpret_cast<float4 *>(smem_raw);
+  const int HW = H * W;
+  float *stage = reinterpret_cast<float *>(planes4 + (H + 2) * P);
+  int *locks = reinterpret_cast<int *>(stage + kWalkWarps * 2 * 4 * SLOT);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(locks + ((H + 2 + 3) & ~3));  // [kWalkWarps][2]
+
+  const int b = blockIdx.x / n_chunks, chunk = blockIdx.x - b * n_chunks;
   const int r0 = img_off[b], r1 = img_off[b + 1];
-  BandFlush f;
-  f.plane = band + ch * bstride;
-  f.lo = lo, f.hi = hi, f.W = W;
-  for (int k = r0; k < r1; ++k) {
-    const int r = order[k];
-    Plan8 p;
-    load_plan8(plan, r, pw, p);
-    int hmin = 1 << 30, hmax = -1;
-#pragma unroll
-    for (int ph = 0; ph < 8; ++ph)
-      if (p.hs[ph] >= 0) {
-        hmin = min(hmin, p.hs[ph]);
-        hmax = max(hmax, p.hs[ph] + 1);
-      }
-    if (hmax < lo || hmin >= hi) continue;  // warp-uniform: roi does not touch this band
-    // grad_out chunk: 4 channels x OHW floats, one contiguous run
-    const float *src = gout + ((size_t)r * C + (size_t)chunk * 4) * OHW;
-#pragma unroll
-    for (int q = lane; q < STG / 4; q += 32)
-      *reinterpret_cast<float4 *>(stage + 4 * q) = ld_stream4(src + 4 * q);
-    // per-roi run structure of the sample columns (ws is non-decreasing in pw)
-    f.wv = p.ws >= 0;
-    f.ws = f.wv ? p.ws : 0;
-    f.wr = p.wr;
-    const int key = f.wv ? p.ws : -100 - pw;
-    const int k1 = __shfl_up_sync(0xffffffffu, key, 1, 8);
-    const int k2 = __shfl_up_sync(0xffffffffu, key, 2, 8);
-    const int k4 = __shfl_up_sync(0xffffffffu, key, 4, 8);
-    const int kn = __shfl_down_sync(0xffffffffu, key, 1, 8);
-    f.f1 = pw >= 1 && k1 == key;
-    f.f2 = pw >= 2 && k2 == key;
-    f.f4 = pw >= 4 && k4 == key;
-    f.tail = f.wv && (pw == 7 || kn != key);
-    __syncwarp();
-    // gradient of each sample point of this lane's column: AVG spreads every pooled-bin
-    // gradient /4 over its 2x2 sample window (autograd of avg_pool2d(2, stride 1))
-    const float *g = stage + ch * OHW;
-    float gs[8];
-    if (POOL == RLOD_POOL_NONE) {
-#pragma unroll
-      for (int ph = 0; ph < 8; ++ph) gs[ph] = g[ph * 8 + pw];
-    } else {
-      float cs[7];
-#pragma unroll
-      for (int i = 0; i < 7; ++i) {
-        const float a = pw >= 1 ? g[i * 7 + pw - 1] : 0.f;
-        const float bb = pw <= 6 ? g[i * 7 + pw] : 0.f;
-        cs[i] = a + bb;
-      }
-      gs[0] = cs[0] * 0.25f;
-#pragma unroll
-      for (int ph = 1; ph < 7; ++ph) gs[ph] = (cs[ph - 1] + cs[ph]) * 0.25f;
-      gs[7] = cs[6] * 0.25f;
-    }
-    // walk the sample rows; hs is warp-uniform and non-decreasing, so the two live rows
-    // stay in registers and every touched row is flushed exactly once
-    int row = -2;
-    float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-    for (int ph = 0; ph < 8; ++ph) {
-      const int h0 = p.hs[ph];
-      if (h0 < 0) continue;
-      const float c0 = (1.f - p.hr[ph]) * gs[ph], c1 = p.hr[ph] * gs[ph];
-      if (h0 == row) {
-        a0 += c0;
-        a1 += c1;
-      } else if (h0 == row + 1) {
-        band_flush(f, row, a0);
-        a0 = a1 + c0;
-        a1 = c1;
-        row = h0;
-      } else {
-        if (row >= 0) {
-          band_flush(f, row, a0);
-          band_flush(f, row + 1, a1);
-        }
-        a0 = c0;
-        a1 = c1;
-        row = h0;
-      }
-    }
-    if (row >= 0) {
-      band_flush(f, row, a0);
-      band_flush(f, row + 1, a1);
-    }
-    __syncwarp();
+  float *dst = gin + ((size_t)b * C + (size_t)chunk * 4) * HW;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k = lane & 7, slot = lane >> 3;
+
+  // planes: zero, or the caller's gradient when accumulating
+  for (int p = threadIdx.x; p < (H + 2) * P; p += kWalkThreads) planes4[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int p = threadIdx.x; p < H + 2; p += kWalkThreads) locks[p] = 0;
+  if (lane == 0) {
+    mbar_init(bars + 2 * warp, 1);
+    mbar_init(bars + 2 * warp + 1, 1);
   }
-  __syncwarp();
-  for (int i = lane; i < 4 * rows * W; i += 32) {
-    const int c = i / (rows * W), o = i - c * (rows * W);
-    gin[gbase + (size_t)c * H * W + (size_t)lo * W + o] = band[c * bstride + o];
+  __syncthreads();
+  if (accumulate) {
+    for (int e = threadIdx.x; e < 4 * HW; e += kWalkThreads) {
+      const int p = e >> 2, c = e & 3;
+      const int y = p / W, x = p - y * W;
+      reinterpret_cast<float *>(planes4 + y * P + x)[c] = __ldg(dst + (size_t)c * HW + p);
+    }
+    __syncthreads();
+  }
+
+  const uint32_t pbase = smem_u32(planes4);
+  float *stg = stage + (warp * 2) * (4 * SLOT) + slot * SLOT;
+  const int n_groups = (r1 - r0 + 3) >> 2;
+  auto roi_of = [&](int gg) {
+    const int kk = r0 + 4 * gg + slot;
+    return (gg < n_groups && kk < r1) ? __ldg(order + kk) : -1;
+  };
+  // tile loads: lane 0 announces the byte count, every slot leader copies its roi's tile
+  auto issue_tiles = [&](int rr, int buf) {
+    const unsigned act = __ballot_sync(0xffffffffu, k == 0 && rr >= 0);
+    if (lane == 0) mbar_expect_tx(bars + 2 * warp + buf, (uint32_t)(__popc(act) * STG * sizeof(float)));
+    __syncwarp();
+    if (k == 0 && rr >= 0)
+      bulk_g2s(stg + buf * (4 * SLOT), gout + ((size_t)rr * C + (size_t)chunk * 4) * OHW,
+               (uint32_t)(STG * sizeof(float)), bars + 2 * warp + buf);
+  };
+
+  // records are pulled into L1 one group ahead (the iteration is long and the flush calls want
+  // the registers a register-held prefetch would take)
+  auto prefetch_rec = [&](int rr) {
+    if (rr >= 0 && k == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(ext + (size_t)rr * 32));
+  };
+  int r = roi_of(warp);
+  int rn = roi_of(warp + kWalkWarps);
+  prefetch_rec(r);
+  if (warp < n_groups) issue_tiles(r, 0);
+
+  for (int g = warp, it = 0; g < n_groups; g += kWalkWarps, ++it) {
+    WalkRec cur;
+    walk_rec_clear(cur);
+    if (r >= 0) walk_rec_load(ext, r, k, cur);
+    prefetch_rec(rn);
+    const int rnn = roi_of(g + 2 * kWalkWarps);
+    const int buf = it & 1;
+    // next group's tiles go into the other buffer: its last reads (previous iteration) are
+    // ordered before this point by the warp barriers of the flushes
+    if (g + kWalkWarps < n_groups) issue_tiles(rn, buf ^ 1);
+    mbar_wait(bars + 2 * warp + buf, (uint32_t)((it >> 1) & 1));
+
+    // ---- sample gradients of this lane's column, 4 channels, one sample row at a time --------
+    // (AVG: pooled gradient / 4 to its 2x2 sample window = 0.25 * (c[t-1] + c[t]), c[i] = column
+    // pair sum g[i][k-1] + g[i][k] of pooled row i)
+    const float *tile = stg + buf * (4 * SLOT);
+    float4 cprev = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto sample_grad = [&](int t) -> float4 {
+      float4 G;
+      if (POOL == RLOD_POOL_NONE) {
+        const float *q = tile + t * 8 + k;
+        G = make_float4(q[0], q[OHW], q[2 * OHW], q[3 * OHW]);
+      } else {
+        float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t < 7) {
+          const float *q = tile + t * 7 + k;
+          if (k <= 6) c = make_float4(q[0], q[OHW], q[2 * OHW], q[3 * OHW]);
+          if (k >= 1) c.x += q[-1], c.y += q[OHW - 1], c.z += q[2 * OHW - 1], c.w += q[3 * OHW - 1];
+        }
+        G = make_float4((cprev.x + c.x) * 0.25f, (cprev.y + c.y) * 0.25f, (cprev.z + c.z) * 0.25f,
+                        (cprev.w + c.w) * 0.25f);
+        cprev = c;
+      }
+      if (r < 0) G = make_float4(0.f, 0.f, 0.f, 0.f);
+      return G;
+    };
+
+    // ---- scatter walk ---------------------------------------------------------------------
+    const uint32_t lane_first = ((uint32_t)cur.la & 0xffffu) << 4;
+    const uint32_t lane_da = (((uint32_t)cur.la >> 16) & 1u) << 4;
+    const int rank = (cur.la >> 17) & 7;
+    const int maxrank_warp = __reduce_max_sync(0xffffffffu, (cur.la >> 20) & 7);
+    float4 da = make_float4(0.f, 0.f, 0.f, 0.f), db = da;
+    const uint32_t lock_base = smem_u32(locks);
+    const float wa = cur.wa;
+    auto flush = [&](float4 v, bool need, uint32_t line_bytes) {
+      const uint32_t row = ((line_bytes >> 4) * (uint32_t)lock_mul) >> 16;
+      const uint32_t p0 = pbase + line_bytes + lane_first;
+      row_flush(v, (int)need, p0, p0 + lane_da, wa, rank, maxrank_warp, lock_base + 4u * row, k);
+    };
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int w = cur.w[t];
+      if (t > 0) {
+        const int wp = cur.w[t - 1];
+        flush(da, (w & 1) && r >= 0, (uint32_t)wp & 0x1fff0u);
+        flush(db, (w & 2) && r >= 0, ((uint32_t)wp >> 13) & 0x1fff0u);
+      }
+      if (w & 1) da = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (w & 2) db = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float rb = cur.rt[t], ra = 1.f - rb;
+      const float4 G = sample_grad(t);
+      da.x = fmaf(ra, G.x, da.x), da.y = fmaf(ra, G.y, da.y), da.z = fmaf(ra, G.z, da.z), da.w = fmaf(ra, G.w, da.w);
+      db.x = fmaf(rb, G.x, db.x), db.y = fmaf(rb, G.y, db.y), db.z = fmaf(rb, G.z, db.z), db.w = fmaf(rb, G.w, db.w);
+    }
+    flush(da, r >= 0, (uint32_t)cur.w[7] & 0x1fff0u);
+    flush(db, r >= 0, ((uint32_t)cur.w[7] >> 13) & 0x1fff0u);
+    r = rn;
+    rn = rnn;
+  }
+  __syncthreads();
+  // planes -> HBM, coalesced per channel plane
+  for (int e = threadIdx.x; e < 4 * HW; e += kWalkThreads) {
+    const int c = e / HW, p = e - c * HW;
+    const int y = p / W, x = p - y * W;
+    dst[(size_t)c * HW + p] = reinterpret_cast<const float *>(planes4 + y * P + x)[c];
   }
 }
 
@@ -1057,9 +1143,9 @@ RLOD_API int rlod_roi_align_forward(const float *feat, const float *rois, int B,
     const unsigned grid = (unsigned)(B * n_chunks);
     const int P = walk_pitch(W);
     RLOD_LAUNCH(RLOD_KERNEL_ROI_PLAN, st,
-                k_roi_plan8_walk<<<(unsigned)cdiv(R, 4), 128, 0, st>>>(ws.plan, R, H, W, P, ws.ext));
+                k_roi_plan8_walk<<<(unsigned)cdiv(R, 4), 128, 0, st>>>(ws.plan, R, H, W, P, 0, ws.ext));
     RLOD_LAUNCH(RLOD_KERNEL_ROI_PLAN, st,
-                k_roi_order_by_mode<<<B, 32, 0, st>>>(ws.ext, ws.order, ws.img_off, ws.order2));
+                k_roi_order_by_key<<<B, 32, 0, st>>>(ws.ext, ws.order, ws.img_off, 0, 30, 2, ws.order2));
 #define RLOD_LAUNCH_FWD(POOL)                                                                  \
   do {                                                                                         \
     cudaFuncSetAttribute(k_align8_fwd_walk<POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
@@ -1116,33 +1202,34 @@ RLOD_API int rlod_roi_align_backward(const float *grad_out, const float *rois, c
   rc = build_plan(rois, B, H, W, R, GH, GW, spatial_scale, ws, st);
   if (rc) return rc;
 
+  const int P = walk_pitch(W);
+  const size_t smem = fwd_walk_smem(H, W, pool_mode) + (size_t)((H + 2 + 3) & ~3) * sizeof(int) +
+                      (size_t)kWalkWarps * 2 * sizeof(uint64_t);
   const bool fast = GH == 8 && GW == 8 && (C % 4) == 0 && pool_mode != RLOD_POOL_MAX &&
-                    ((uintptr_t)grad_out % 16) == 0 && W <= 2048;
+                    ((uintptr_t)grad_out % 16) == 0 && smem <= (size_t)kMaxSmemPerCta &&
+                    (H + 2) * P <= 8192 && H + 2 <= 64 * 4 && R >= 2 * B;
   if (fast) {
-    // band height: ~17 KB of shared memory per one-warp CTA -> ~12 resident warps per SM,
-    // each owning its band exclusively
-    int band_rows = (17 * 1024 / 16) / W;
-    if (band_rows < 1) band_rows = 1;
-    if (band_rows > H) band_rows = H;
-    const int n_bands = (int)cdiv(H, band_rows);
-    band_rows = (int)cdiv(H, n_bands);  // even out the bands
+    RLOD_LAUNCH(RLOD_KERNEL_ROI_PLAN, st,
+                k_roi_plan8_walk<<<(unsigned)cdiv(R, 4), 128, 0, st>>>(ws.plan, R, H, W, P, 1, ws.ext));
+    RLOD_LAUNCH(RLOD_KERNEL_ROI_PLAN, st,
+                k_roi_order_by_key<<<B, 32, 0, st>>>(ws.ext, ws.order, ws.img_off, 16, 20, 8, ws.order2));
     const int n_chunks = C / 4;
-    const int stg = 4 * (pool_mode == RLOD_POOL_NONE ? 64 : 49);
-    const size_t smem = ((size_t)stg + (size_t)4 * band_rows * W) * sizeof(float);
-    const unsigned grid = (unsigned)((long long)B * n_chunks * n_bands);
-    if (pool_mode == RLOD_POOL_NONE) {
-      cudaFuncSetAttribute(k_align8_bwd_bands<RLOD_POOL_NONE>,
-                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      RLOD_LAUNCH(RLOD_KERNEL_ALIGN_BWD, st, k_align8_bwd_bands<RLOD_POOL_NONE><<<grid, 32, smem, st>>>(
-          grad_out, ws.plan, ws.order, ws.img_off, C, H, W, n_chunks, n_bands, band_rows,
-          accumulate, grad_in));
-    } else {
-      cudaFuncSetAttribute(k_align8_bwd_bands<RLOD_POOL_AVG>,
-                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      RLOD_LAUNCH(RLOD_KERNEL_ALIGN_BWD, st, k_align8_bwd_bands<RLOD_POOL_AVG><<<grid, 32, smem, st>>>(
-          grad_out, ws.plan, ws.order, ws.img_off, C, H, W, n_chunks, n_bands, band_rows,
-          accumulate, grad_in));
-    }
+    const unsigned grid = (unsigned)(B * n_chunks);
+    const int lock_mul = (65536 + P - 1) / P;  // row = (pixel offset * lock_mul) >> 16, exact for rows < 2^16 / P
+#define RLOD_LAUNCH_BWD(POOL)                                                                  \
+  do {                                                                                         \
+    cudaFuncSetAttribute(k_align8_bwd_walk<POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                         (int)smem);                                                           \
+    ProfScope _ps(RLOD_KERNEL_ALIGN_BWD, st);                                                  \
+    k_align8_bwd_walk<POOL><<<grid, kWalkThreads, smem, st>>>(grad_out, ws.ext, ws.order2,     \
+                                                              ws.img_off, C, H, W, P, n_chunks, \
+                                                              accumulate, lock_mul, grad_in);  \
+  } while (0)
+    if (pool_mode == RLOD_POOL_NONE)
+      RLOD_LAUNCH_BWD(RLOD_POOL_NONE);
+    else
+      RLOD_LAUNCH_BWD(RLOD_POOL_AVG);
+#undef RLOD_LAUNCH_BWD
     return launch_status();
   }
   if (!accumulate) cudaMemsetAsync(grad_in, 0, gin_bytes, st);

@@ -226,10 +226,11 @@ def test_roi_align_backward_c2_full_size(orc):
     gin = be.roi_align_backward(cu(gout), cu(rois), None, tuple(feat.shape), 7, 7, 1 / 16.0,
                                 be.POOL_AVG)
     close(gin.cpu().numpy(), ref, what="C2 bwd")
-    # deterministic: the banded kernel has no atomics
+    # run-to-run: rois of different warps add into a pixel in lock order (like the reference's
+    # atomics), so repeats agree to rounding, not bit for bit
     gin2 = be.roi_align_backward(cu(gout), cu(rois), None, tuple(feat.shape), 7, 7, 1 / 16.0,
                                  be.POOL_AVG)
-    assert torch.equal(gin, gin2)
+    close(gin2.cpu().numpy(), gin.cpu().numpy(), what="C2 bwd repeat")
 
 
 def test_roi_align_module_autograd(orc):
@@ -268,7 +269,8 @@ def test_roi_align_properties_c3_size():
     fx = be.roi_align_forward(x, rois, 7, 7, 1 / 16.0, be.POOL_AVG)
     b1 = be.roi_align_backward(g1, rois, None, (B, C, H, W), 7, 7, 1 / 16.0, be.POOL_AVG)
     b2 = be.roi_align_backward(2.0 * g1, rois, None, (B, C, H, W), 7, 7, 1 / 16.0, be.POOL_AVG)
-    assert torch.equal(b2, 2.0 * b1)  # scaling by 2 is exact in fp32
+    # linear in grad_out (exact per roi; the order rois add into a pixel is not fixed run to run)
+    assert (b2 - 2.0 * b1).abs().max().item() <= 1e-5 * b2.abs().max().item()
     lhs = (fx.double() * g1.double()).sum().item()
     rhs = (x.double() * b1.double()).sum().item()
     assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), abs(rhs), 1.0)
