@@ -93,7 +93,8 @@ def stalls(src, dst, top=25):
     txt = subprocess.run(["ncu", "-i", src, "--page", "source", "--csv", "--print-source", "sass"],
                          capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
-    name, hdr, data = rows[0][1], rows[1], rows[2:]
+    starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"] + [len(rows)]
+    name, hdr, data = rows[0][1], rows[1], [r for r in rows[2:starts[1]] if len(r) > 10]
     ix = {h: i for i, h in enumerate(hdr)}
     keys = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
     tot = {k: sum(int(r[ix[k]] or 0) for r in data) for k in keys}

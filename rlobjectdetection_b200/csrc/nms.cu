@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(64)
 // ----------------------------------------------------------------------------------------
 // scan kernel: one CTA (256 threads) per segment.
 // ----------------------------------------------------------------------------------------
-constexpr int kScanThreads = 256;
+constexpr int kScanThreads = 1024;
 
 __global__ void __launch_bounds__(kScanThreads)
     k_nms_scan(NmsSegs segs, int max_keep, const unsigned long long *__restrict__ mask,
@@ -86,8 +86,13 @@ __global__ void __launch_bounds__(kScanThreads)
   for (int w = t; w < nblk; w += kScanThreads) remv[w] = 0ull;
   if (t == 0) s_total = 0;
   __syncthreads();
+  unsigned long long dnext = (t < 64 && nblk > 0) ? m[t] : 0ull;  // diagonal tile of block 0
   for (int k = 0; k < nblk; ++k) {
-    if (t < 64) diag[t] = m[(size_t)k * npad + k * 64 + t];
+    if (t < 64) {
+      diag[t] = dnext;
+      // the next diagonal tile travels while this block is resolved and pushed
+      if (k + 1 < nblk) dnext = m[(size_t)(k + 1) * npad + (k + 1) * 64 + t];
+    }
     __syncthreads();
     if (t == 0) {
       unsigned long long r = remv[k];
@@ -127,17 +132,32 @@ __global__ void __launch_bounds__(kScanThreads)
       o.emit(seg, off, rank, k * 64 + t, segs);
     }
     if (max_keep > 0 && total >= max_keep) break;  // CTA-uniform
-    // OR the kept rows of this block into the removed-bitmap of all later blocks
+    // OR the kept rows of this block into the removed-bitmap of all later blocks: 32 warps,
+    // every warp issues the loads of up to four column blocks before it reduces any of them
+    // (the scan is a chain of L2 round trips; this keeps one round trip per 128 column blocks)
     const bool k0 = (kb >> lane) & 1ull, k1 = (kb >> (lane + 32)) & 1ull;
-    for (int w = k + 1 + warp; w < nblk; w += kScanThreads / 32) {
-      const unsigned long long *row = m + (size_t)w * npad + k * 64;
-      unsigned long long v = 0ull;
-      if (k0) v = row[lane];
-      if (k1) v |= row[lane + 32];
-      unsigned lo = (unsigned)v, hi = (unsigned)(v >> 32);
-      lo = __reduce_or_sync(0xffffffffu, lo);
-      hi = __reduce_or_sync(0xffffffffu, hi);
-      if (lane == 0) remv[w] |= ((unsigned long long)hi << 32) | lo;
+    constexpr int kWarps = kScanThreads / 32;
+    for (int w0 = k + 1 + warp; w0 < nblk; w0 += 4 * kWarps) {
+      unsigned long long v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int w = w0 + u * kWarps;
+        v[u] = 0ull;
+        if (w < nblk) {
+          const unsigned long long *row = m + (size_t)w * npad + k * 64;
+          if (k0) v[u] = row[lane];
+          if (k1) v[u] |= row[lane + 32];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int w = w0 + u * kWarps;
+        if (w < nblk) {
+          const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)v[u]);
+          const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(v[u] >> 32));
+          if (lane == 0) remv[w] |= ((unsigned long long)hi << 32) | lo;
+        }
+      }
     }
     __syncthreads();
   }
@@ -252,7 +272,7 @@ __global__ void __launch_bounds__(kSmallThreads)
 // smem: float4 kbox[max_keep]; float kSa[max_keep].
 // ----------------------------------------------------------------------------------------
 constexpr int kLazyThreads = 512;
-constexpr int kLazyMaxKeep = 512;
+constexpr int kLazyMaxKeep = 512;  // beyond: one CTA testing 64 candidates against K kept boxes is slower than the all-SM mask
 
 __global__ void __launch_bounds__(kLazyThreads)
     k_nms_lazy(NmsSegs segs, float thresh, int max_keep, NmsOut o) {
@@ -388,6 +408,8 @@ int nms_launch(const NmsSegs &segs, int nseg, int max_seg, float thresh, int max
   if (max_keep > 0 && max_keep <= kLazyMaxKeep && !force_large) {
     // bounded keeps (proposal layer): kept-list walk, no n x n mask, no workspace
     const size_t smem = (size_t)max_keep * (sizeof(float4) + sizeof(float));
+    if (smem > 48 * 1024)
+      cudaFuncSetAttribute(k_nms_lazy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     RLOD_LAUNCH(RLOD_KERNEL_NMS_LAZY, st,
                 k_nms_lazy<<<nseg, kLazyThreads, smem, st>>>(segs, thresh, max_keep, out));
     return launch_status();

@@ -10,18 +10,16 @@
 //      sample grid (row index + row ratio per ph, column index + column ratio per pw),
 //      computed once with the reference's exact fp32/fp64 expression order, plus per-image
 //      roi lists.  The hot kernels never touch roi coordinates again.
-//   2. forward (k_align8_fwd_planes): a CTA owns 4 consecutive channel planes of ONE image,
-//      pulls them HBM -> shared memory once (coalesced, interleaved per pixel so that lanes
-//      of different channels never share a bank) and then serves EVERY roi of that image
-//      from shared memory.  The feature map is read from HBM exactly once, all bilinear taps
-//      are LDS, and each (roi, 4 channels) result is staged in shared memory and leaves as
-//      ONE 784-byte bulk async store (TMA engine).  No 8x8 intermediate tensor exists.
-//   3. backward (k_align8_bwd_walk): see the kernel; the old description below is kept short:
-//      a CTA owns 4 gradient planes in
-//      shared memory exclusively, walks the image's rois, and accumulates with plain
-//      LDS/FADD/STS (segmented warp-shuffle reduction resolves intra-roi collisions), so
-//      there is not a single atomic and the result is deterministic.  grad_in is written
-//      once, coalesced; no memset is needed.
+//   2. forward (k_align8_fwd_walk): a CTA owns 4 consecutive channel planes of ONE image,
+//      pulls them HBM -> shared memory once (async copies, interleaved per pixel) and serves
+//      EVERY roi of that image from shared memory: 4 rois per warp, 4 channels per LDS.128,
+//      per-roi orientation + tap order chosen so that the requests are bank-conflict-free,
+//      2x2 pooling fused, each (roi, 4 channels) result leaves as ONE 784-byte bulk async
+//      store (TMA engine).  The feature map is read from HBM exactly once and no 8x8
+//      intermediate tensor exists.
+//   3. backward (k_align8_bwd_walk): the transpose -- gradient planes accumulated in shared
+//      memory under per-row spin locks, grad_out tiles by bulk async load, grad_in written
+//      once, coalesced; no global atomics, no memset.
 //   Generic kernels (any grid size / channel count / plane size, and RoIAlignMax backward)
 //   cover everything the fast paths do not.
 #include "rlod_common.cuh"
@@ -386,6 +384,7 @@ __device__ __forceinline__ unsigned tap_order_search(const int *L, const int *R,
     }
     const unsigned c = (unsigned)(bank_multiplicity<WIDE>(ff) + bank_multiplicity<WIDE>(ss));
     best = min(best, (c << 8) | (unsigned)(lane | (j << 5)));
+    if (__any_sync(0xffffffffu, c == 2u)) break;  // conflict-free: cannot be beaten
   }
   return best;
 }
