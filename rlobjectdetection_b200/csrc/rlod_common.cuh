@@ -80,6 +80,32 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   }
 }
 
+// bulk async store shared -> global (TMA engine, SASS: UBLKCP), tracked by bulk groups
+__device__ __forceinline__ void bulk_s2g_nocommit(void *dst_gmem, const void *src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem),
+               "r"(smem_u32(src_smem)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+__device__ __forceinline__ float4 lds128(uint32_t smem_addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_addr));
+  return v;
+}
+
+// shared-memory row pitch (pixels) of the plane kernels: the smallest odd number >= W + 1
+__host__ __device__ __forceinline__ int walk_pitch(int W) { return (W + 1) | 1; }
+
 // streaming (evict-first) 128-bit store / load: outputs and one-shot inputs must not push
 // the feature planes out of L2
 __device__ __forceinline__ void st_stream4(float *p, float4 v) {

@@ -22,45 +22,9 @@
 //      once, coalesced; no global atomics, no memset.
 //   Generic kernels (any grid size / channel count / plane size, and RoIAlignMax backward)
 //   cover everything the fast paths do not.
-#include "rlod_common.cuh"
+#include "roi_lists.cuh"
 
 namespace rlod {
-
-// ----------------------------------------------------------------------------------------
-// workspace layout
-// ----------------------------------------------------------------------------------------
-struct AlignWs {
-  int *flag;     // [4]   flag[0] != 0: rois are not grouped by image
-  int *img_off;  // [B+1] roi list offsets per image
-  int *cursor;   // [B]
-  int *order;    // [R]   roi ids grouped by image (stable)
-  int *roi_b;    // [R]   batch index (0 when out of range: the plan is all-invalid then)
-  int *plan;     // [R * words]
-  int *ext;      // [R * 32] forward-kernel record (8x8 grids only)
-  int *order2;   // [R]   `order` with every image's list partitioned by walk mode (stable)
-  size_t bytes;
-};
-
-static AlignWs carve_align_ws(void *base, int B, int R, int GH, int GW) {
-  AlignWs w;
-  size_t off = 0;
-  char *p = (char *)base;
-  auto take = [&](size_t n) {
-    char *q = p ? p + off : nullptr;
-    off += align_up(n, 128);
-    return q;
-  };
-  w.flag = (int *)take(4 * sizeof(int));
-  w.img_off = (int *)take((size_t)(B + 1) * sizeof(int));
-  w.cursor = (int *)take((size_t)(B > 0 ? B : 1) * sizeof(int));
-  w.order = (int *)take((size_t)(R > 0 ? R : 1) * sizeof(int));
-  w.roi_b = (int *)take((size_t)(R > 0 ? R : 1) * sizeof(int));
-  w.plan = (int *)take((size_t)(R > 0 ? R : 1) * (size_t)(2 * GH + 2 * GW) * sizeof(int));
-  w.ext = (int *)take((GH == 8 && GW == 8) ? (size_t)(R > 0 ? R : 1) * 32 * sizeof(int) : 0);
-  w.order2 = (int *)take((GH == 8 && GW == 8) ? (size_t)(R > 0 ? R : 1) * sizeof(int) : 0);
-  w.bytes = off;
-  return w;
-}
 
 // ----------------------------------------------------------------------------------------
 // plan kernel.  One thread per (roi, slot): slot < GH is a sample row, else a sample column.
@@ -106,72 +70,7 @@ __global__ void k_roi_plan(const float *__restrict__ rois, int R, int B, int H, 
     pl[2 * GH + 2 * p] = idx;
     pl[2 * GH + 2 * p + 1] = __float_as_int(ratio);
   }
-  if (slot == 0) {
-    // roi lists under the assumption that rois are grouped by image (what _ProposalLayer
-    // emits); k_roi_group_fixup redoes them when the flag is raised.
-    ws.roi_b[r] = b;
-    ws.order[r] = r;
-    int prev;
-    if (r == 0) {
-      prev = -1;
-    } else {
-      const float pf = rois[(size_t)(r - 1) * 5];
-      const int pi = (int)pf;
-      prev = ((pf >= 0.f) && (pi < B)) ? pi : 0;
-    }
-    if (b < prev) atomicOr(ws.flag, 1);
-    for (int q = prev + 1; q <= b; ++q) ws.img_off[q] = r;
-    if (r == R - 1)
-      for (int q = b + 1; q <= B; ++q) ws.img_off[q] = R;
-  }
-}
-
-// one warp: stable counting sort of roi ids by image, only when the rois were not grouped
-__global__ void k_roi_group_fixup(int R, int B, AlignWs ws) {
-  if (ws.flag[0] == 0) return;
-  const int lane = threadIdx.x;
-  const unsigned full = 0xffffffffu;
-  for (int b = lane; b < B; b += 32) ws.cursor[b] = 0;
-  __syncwarp();
-  for (int base = 0; base < R; base += 32) {
-    const int r = base + lane;
-    const int b = r < R ? ws.roi_b[r] : -1 - lane;
-    const unsigned peers = __match_any_sync(full, b);
-    if (r < R && lane == __ffs(peers) - 1) ws.cursor[b] += __popc(peers);
-    __syncwarp();
-  }
-  // exclusive scan over images, 32 at a time
-  int carry = 0;
-  for (int base = 0; base < B; base += 32) {
-    const int b = base + lane;
-    const int c = b < B ? ws.cursor[b] : 0;
-    int inc = c;
-    for (int d = 1; d < 32; d <<= 1) {
-      const int t = __shfl_up_sync(full, inc, d);
-      if (lane >= d) inc += t;
-    }
-    if (b < B) {
-      ws.img_off[b] = carry + inc - c;
-      ws.cursor[b] = carry + inc - c;
-    }
-    carry += __shfl_sync(full, inc, 31);
-  }
-  if (lane == 0) ws.img_off[B] = carry;
-  __syncwarp();
-  for (int base = 0; base < R; base += 32) {
-    const int r = base + lane;
-    const int b = r < R ? ws.roi_b[r] : -1 - lane;
-    const unsigned peers = __match_any_sync(full, b);
-    const int leader = __ffs(peers) - 1;
-    int cur = 0;
-    if (r < R && lane == leader) {
-      cur = ws.cursor[b];
-      ws.cursor[b] = cur + __popc(peers);
-    }
-    cur = __shfl_sync(full, cur, leader);
-    if (r < R) ws.order[cur + __popc(peers & ((1u << lane) - 1u))] = r;
-    __syncwarp();
-  }
+  if (slot == 0) roi_list_mark(rois, r, R, B, b, ws);
 }
 
 // ----------------------------------------------------------------------------------------
@@ -302,7 +201,6 @@ __device__ __forceinline__ void load_plan8(const int *__restrict__ plan, int r, 
 constexpr int kWalkWarps = 8;
 constexpr int kWalkThreads = kWalkWarps * 32;
 
-__host__ __device__ __forceinline__ int walk_pitch(int W) { return (W + 1) | 1; }
 
 // Walk plan over the line pairs (L[t], L[t] + 1), t = 0..7.  Two register slots a, b hold
 // interpolated lines; a position loads only the lines neither slot holds, and when the pair
@@ -496,32 +394,6 @@ __global__ void __launch_bounds__(128)
   e[17 + 2 * t] = __float_as_int(sw ? 1.f - w : w);
 }
 
-// one warp per image: stable counting sort of its roi list by a small key taken from the
-// record -- forward: the walk mode (word 0 bit 30), so that the four rois a warp serves
-// together stage with the same strides; backward: the longest run of lanes that share a
-// column (word 16 bits 20-22), so that a narrow roi does not impose its extra scatter rounds
-// on three wide ones.
-__global__ void k_roi_order_by_key(const int *__restrict__ ext, const int *__restrict__ order,
-                                   const int *__restrict__ img_off, int word, int shift, int nkeys,
-                                   int *__restrict__ order2) {
-  const int b = blockIdx.x, lane = threadIdx.x;
-  const int r0 = img_off[b], r1 = img_off[b + 1];
-  const unsigned full = 0xffffffffu, below = (1u << lane) - 1u;
-  int start = r0;
-  for (int key = 0; key < nkeys; ++key) {
-    int c = start;
-    for (int base = r0; base < r1; base += 32) {
-      const int i = base + lane;
-      const int r = i < r1 ? order[i] : 0;
-      const bool hit = i < r1 && ((ext[(size_t)r * 32 + word] >> shift) & (nkeys - 1)) == key;
-      const unsigned m = __ballot_sync(full, hit);
-      if (hit) order2[c + __popc(m & below)] = r;
-      c += __popc(m);
-    }
-    start = c;
-  }
-}
-
 struct WalkRec {
   int w[8];     // packed walk positions
   float rt[8];  // walk ratios
@@ -547,23 +419,6 @@ __device__ __forceinline__ void walk_rec_load(const int *__restrict__ ext, int r
   const int2 l = __ldg(reinterpret_cast<const int2 *>(ext + (size_t)r * 32 + 16) + k);
   p.la = l.x;
   p.wa = __int_as_float(l.y);
-}
-
-// bulk async store shared -> global (TMA engine, SASS: UBLKCP), tracked by bulk groups
-__device__ __forceinline__ void bulk_s2g_nocommit(void *dst_gmem, const void *src_smem, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem),
-               "r"(smem_u32(src_smem)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit() {
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-template <int N>
-__device__ __forceinline__ void bulk_wait_read() {
-  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ void fence_async_smem() {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
 // One walk position for 4 channels, fully predicated on two flag bits of this lane's roi:

@@ -1,0 +1,142 @@
+// Per-image roi lists shared by the RoIAlign and RoIPool plane kernels: workspace layout, the
+// "rois are grouped by image" fast path with its fix-up, and the per-image counting sort by a
+// small key.  Kernels are static: every .cu that includes this header gets its own copy.
+#pragma once
+#include "rlod_common.cuh"
+
+namespace rlod {
+
+// ----------------------------------------------------------------------------------------
+// workspace layout
+// ----------------------------------------------------------------------------------------
+struct AlignWs {
+  int *flag;     // [4]   flag[0] != 0: rois are not grouped by image
+  int *img_off;  // [B+1] roi list offsets per image
+  int *cursor;   // [B]
+  int *order;    // [R]   roi ids grouped by image (stable)
+  int *roi_b;    // [R]   batch index (0 when out of range: the plan is all-invalid then)
+  int *plan;     // [R * words]
+  int *ext;      // [R * 32] forward-kernel record (8x8 grids only)
+  int *order2;   // [R]   `order` with every image's list partitioned by walk mode (stable)
+  size_t bytes;
+};
+
+static inline AlignWs carve_align_ws(void *base, int B, int R, int GH, int GW) {
+  AlignWs w;
+  size_t off = 0;
+  char *p = (char *)base;
+  auto take = [&](size_t n) {
+    char *q = p ? p + off : nullptr;
+    off += align_up(n, 128);
+    return q;
+  };
+  w.flag = (int *)take(4 * sizeof(int));
+  w.img_off = (int *)take((size_t)(B + 1) * sizeof(int));
+  w.cursor = (int *)take((size_t)(B > 0 ? B : 1) * sizeof(int));
+  w.order = (int *)take((size_t)(R > 0 ? R : 1) * sizeof(int));
+  w.roi_b = (int *)take((size_t)(R > 0 ? R : 1) * sizeof(int));
+  w.plan = (int *)take((size_t)(R > 0 ? R : 1) * (size_t)(2 * GH + 2 * GW) * sizeof(int));
+  w.ext = (int *)take((GH == 8 && GW == 8) ? (size_t)(R > 0 ? R : 1) * 32 * sizeof(int) : 0);
+  w.order2 = (int *)take((GH == 8 && GW == 8) ? (size_t)(R > 0 ? R : 1) * sizeof(int) : 0);
+  w.bytes = off;
+  return w;
+}
+
+
+// Called by one thread per roi r (b = its validated batch index): roi lists under the
+// assumption that rois are grouped by image (what _ProposalLayer emits); k_roi_group_fixup
+// redoes them when the flag is raised.
+__device__ __forceinline__ void roi_list_mark(const float *__restrict__ rois, int r, int R, int B, int b,
+                                              const AlignWs &ws) {
+  ws.roi_b[r] = b;
+  ws.order[r] = r;
+  int prev;
+  if (r == 0) {
+    prev = -1;
+  } else {
+    const float pf = rois[(size_t)(r - 1) * 5];
+    const int pi = (int)pf;
+    prev = ((pf >= 0.f) && (pi < B)) ? pi : 0;
+  }
+  if (b < prev) atomicOr(ws.flag, 1);
+  for (int q = prev + 1; q <= b; ++q) ws.img_off[q] = r;
+  if (r == R - 1)
+    for (int q = b + 1; q <= B; ++q) ws.img_off[q] = R;
+}
+
+// one warp: stable counting sort of roi ids by image, only when the rois were not grouped
+static __global__ void k_roi_group_fixup(int R, int B, AlignWs ws) {
+  if (ws.flag[0] == 0) return;
+  const int lane = threadIdx.x;
+  const unsigned full = 0xffffffffu;
+  for (int b = lane; b < B; b += 32) ws.cursor[b] = 0;
+  __syncwarp();
+  for (int base = 0; base < R; base += 32) {
+    const int r = base + lane;
+    const int b = r < R ? ws.roi_b[r] : -1 - lane;
+    const unsigned peers = __match_any_sync(full, b);
+    if (r < R && lane == __ffs(peers) - 1) ws.cursor[b] += __popc(peers);
+    __syncwarp();
+  }
+  // exclusive scan over images, 32 at a time
+  int carry = 0;
+  for (int base = 0; base < B; base += 32) {
+    const int b = base + lane;
+    const int c = b < B ? ws.cursor[b] : 0;
+    int inc = c;
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(full, inc, d);
+      if (lane >= d) inc += t;
+    }
+    if (b < B) {
+      ws.img_off[b] = carry + inc - c;
+      ws.cursor[b] = carry + inc - c;
+    }
+    carry += __shfl_sync(full, inc, 31);
+  }
+  if (lane == 0) ws.img_off[B] = carry;
+  __syncwarp();
+  for (int base = 0; base < R; base += 32) {
+    const int r = base + lane;
+    const int b = r < R ? ws.roi_b[r] : -1 - lane;
+    const unsigned peers = __match_any_sync(full, b);
+    const int leader = __ffs(peers) - 1;
+    int cur = 0;
+    if (r < R && lane == leader) {
+      cur = ws.cursor[b];
+      ws.cursor[b] = cur + __popc(peers);
+    }
+    cur = __shfl_sync(full, cur, leader);
+    if (r < R) ws.order[cur + __popc(peers & ((1u << lane) - 1u))] = r;
+    __syncwarp();
+  }
+}
+
+// one warp per image: stable counting sort of its roi list by a small key taken from the
+// record -- forward: the walk mode (word 0 bit 30), so that the four rois a warp serves
+// together stage with the same strides; backward: the longest run of lanes that share a
+// column (word 16 bits 20-22), so that a narrow roi does not impose its extra scatter rounds
+// on three wide ones.
+static __global__ void k_roi_order_by_key(const int *__restrict__ ext, const int *__restrict__ order,
+                                   const int *__restrict__ img_off, int word, int shift, int nkeys,
+                                   int *__restrict__ order2) {
+  const int b = blockIdx.x, lane = threadIdx.x;
+  const int r0 = img_off[b], r1 = img_off[b + 1];
+  const unsigned full = 0xffffffffu, below = (1u << lane) - 1u;
+  int start = r0;
+  for (int key = 0; key < nkeys; ++key) {
+    int c = start;
+    for (int base = r0; base < r1; base += 32) {
+      const int i = base + lane;
+      const int r = i < r1 ? order[i] : 0;
+      const bool hit = i < r1 && ((ext[(size_t)r * 32 + word] >> shift) & (nkeys - 1)) == key;
+      const unsigned m = __ballot_sync(full, hit);
+      if (hit) order2[c + __popc(m & below)] = r;
+      c += __popc(m);
+    }
+    start = c;
+  }
+}
+
+
+}  // namespace rlod

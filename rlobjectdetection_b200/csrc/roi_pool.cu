@@ -10,9 +10,170 @@
 // ALL R rois (O(B*C*H*W*R)); here the saved argmax turns it into a single pass over the
 // R*C*ph*pw gradients with at most one fp32 RED each -- the only work that exists -- while
 // keeping the gather's visiting rules, so malformed rois lose their gradient exactly as there.
-#include "rlod_common.cuh"
+#include "roi_lists.cuh"
 
 namespace rlod {
+
+// ----------------------------------------------------------------------------------------
+// fast forward for 7x7 bins: CTA = (image, 4 channel planes resident in shared memory), like
+// the RoIAlign forward.  The planes are read from HBM once (async copies, 4 channels
+// interleaved per pixel); a warp serves 4 rois per iteration, lane k of a roi owns output
+// column k and scans its bins row by row (LDS.128 = 4 channels per pixel), keeping the first
+// maximum in (h, w) scan order with strict '>' exactly like the reference
+// (roi_pooling_kernel.cu:73-90).  out and argmax leave as one 784-byte bulk async store
+// each per (roi, 4 channels).
+// k_pool_plan: one thread per roi, the reference's bin arithmetic (:45-66) once per roi:
+//   record[0..6] hstart, [7..13] hend, [14..20] wstart, [21..27] wend (already clipped),
+//   [28] batch index or -1, [29] max rows of a bin, [30] max columns of a bin, [31] size key.
+// ----------------------------------------------------------------------------------------
+constexpr int kPoolWarps = 8;
+constexpr int kPoolThreads = kPoolWarps * 32;
+constexpr int kPoolSlot = 200;  // floats per staged tile slot (196 used), = 8 (mod 32)
+
+__global__ void k_pool_plan(const float *__restrict__ rois, int R, int B, int H, int W, float scale,
+                            AlignWs ws) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const float *roi = rois + (size_t)r * 5;
+  const float bf = roi[0];
+  const int bi = (int)bf;
+  const bool bvalid = (bf >= 0.f) && (bi < B);
+  const int roi_start_w = (int)roundf(__fmul_rn(roi[1], scale));
+  const int roi_start_h = (int)roundf(__fmul_rn(roi[2], scale));
+  const int roi_end_w = (int)roundf(__fmul_rn(roi[3], scale));
+  const int roi_end_h = (int)roundf(__fmul_rn(roi[4], scale));
+  const int roi_width = max(roi_end_w - roi_start_w + 1, 1);
+  const int roi_height = max(roi_end_h - roi_start_h + 1, 1);
+  const float bin_h = __fdiv_rn((float)roi_height, 7.f);
+  const float bin_w = __fdiv_rn((float)roi_width, 7.f);
+  int *e = ws.plan + (size_t)r * 32;
+  int mr = 0, mc = 0;
+  for (int p = 0; p < 7; ++p) {
+    int hstart = (int)floorf(__fmul_rn((float)p, bin_h));
+    int wstart = (int)floorf(__fmul_rn((float)p, bin_w));
+    int hend = (int)ceilf(__fmul_rn((float)(p + 1), bin_h));
+    int wend = (int)ceilf(__fmul_rn((float)(p + 1), bin_w));
+    hstart = min(max(hstart + roi_start_h, 0), H);
+    hend = min(max(hend + roi_start_h, 0), H);
+    wstart = min(max(wstart + roi_start_w, 0), W);
+    wend = min(max(wend + roi_start_w, 0), W);
+    e[p] = hstart, e[7 + p] = hend, e[14 + p] = wstart, e[21 + p] = wend;
+    mr = max(mr, hend - hstart), mc = max(mc, wend - wstart);
+  }
+  e[28] = bvalid ? bi : -1;
+  e[29] = bvalid ? mr : 0;
+  e[30] = bvalid ? mc : 0;
+  // size key (8 classes) so that the four rois a warp serves together scan similar windows
+  const int area = bvalid ? mr * mc : 0;
+  e[31] = area <= 1 ? 0 : min(7, 32 - __clz(area - 1));
+  roi_list_mark(rois, r, R, B, bvalid ? bi : 0, ws);
+}
+
+__global__ void __launch_bounds__(kPoolThreads, 2)
+    k_roi_pool7_fwd_planes(const float *__restrict__ feat, const int *__restrict__ rec,
+                           const int *__restrict__ order, const int *__restrict__ img_off, int C,
+                           int H, int W, int P, int n_chunks, float *__restrict__ out,
+                           int *__restrict__ argmax) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float4 *planes4 = reinterpret_cast<float4 *>(smem_raw);
+  const int HW = H * W;
+  float *stage = reinterpret_cast<float *>(planes4 + H * P);  // [warps][4 slots][2 tiles][kPoolSlot]
+  const int b = blockIdx.x / n_chunks, chunk = blockIdx.x - b * n_chunks;
+  const int r0 = img_off[b], r1 = img_off[b + 1];
+  if (r0 >= r1) return;
+  const float *src = feat + ((size_t)b * C + (size_t)chunk * 4) * HW;
+  {
+    const int c = threadIdx.x & 3;
+    constexpr int kStep = kPoolThreads / 4;
+    int p = threadIdx.x >> 2;
+    int y = p / W, x = p - y * W;
+    const int dy = kStep / W, dx = kStep - dy * W;
+    const float *sc = src + (size_t)c * HW;
+    const uint32_t pb0 = smem_u32(planes4) + 4u * c;
+    for (; p < HW; p += kStep) {
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(pb0 + 16u * (uint32_t)(y * P + x)), "l"(sc + p)
+                   : "memory");
+      x += dx, y += dy;
+      if (x >= W) x -= W, ++y;
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k = lane & 7, slot = lane >> 3;
+  const uint32_t pbase = smem_u32(planes4);
+  float *tile_v = stage + ((warp * 4 + slot) * 2) * kPoolSlot;
+  int *tile_i = reinterpret_cast<int *>(tile_v + kPoolSlot);
+  const int n_groups = (r1 - r0 + 3) >> 2;
+  const int chan_base = (b * C + chunk * 4) * HW;  // flat NCHW index of this CTA's first plane
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  for (int g = warp, it = 0; g < n_groups; g += kPoolWarps, ++it) {
+    const int kk = r0 + 4 * g + slot;
+    const int r = kk < r1 ? __ldg(order + kk) : -1;
+    // this lane's column bin, the roi's row bins
+    int hs[7], he[7], ws = 0, we = 0, mr = 0, mc = 0;
+#pragma unroll
+    for (int p = 0; p < 7; ++p) hs[p] = 0, he[p] = 0;
+    if (r >= 0) {
+      const int *e = rec + (size_t)r * 32;
+      const int4 a0 = __ldg(reinterpret_cast<const int4 *>(e)), a1 = __ldg(reinterpret_cast<const int4 *>(e) + 1);
+      const int4 a2 = __ldg(reinterpret_cast<const int4 *>(e) + 2), a3 = __ldg(reinterpret_cast<const int4 *>(e) + 3);
+      hs[0] = a0.x, hs[1] = a0.y, hs[2] = a0.z, hs[3] = a0.w, hs[4] = a1.x, hs[5] = a1.y, hs[6] = a1.z;
+      he[0] = a1.w, he[1] = a2.x, he[2] = a2.y, he[3] = a2.z, he[4] = a2.w, he[5] = a3.x, he[6] = a3.y;
+      if (k < 7) ws = __ldg(e + 14 + k), we = __ldg(e + 21 + k);
+      if (__ldg(e + 28) >= 0) mr = __ldg(e + 29), mc = __ldg(e + 30);
+      else we = ws;  // batch index out of range: every bin empty
+    }
+    const int mrw = __reduce_max_sync(0xffffffffu, mr), mcw = __reduce_max_sync(0xffffffffu, mc);
+    // the staging tiles were handed to the bulk-copy engine one iteration ago
+    if (it >= 1) {
+      if (k == 0) bulk_wait_read<0>();
+      __syncwarp();
+    }
+#pragma unroll
+    for (int ph = 0; ph < 7; ++ph) {
+      float4 mv = make_float4(-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f);
+      int4 mi = make_int4(-1, -1, -1, -1);
+      const int h0 = hs[ph], h1 = he[ph];
+      for (int dh = 0; dh < mrw; ++dh) {
+        const int h = h0 + dh;
+        for (int dw = 0; dw < mcw; ++dw) {
+          const int w = ws + dw;
+          if (h < h1 && w < we) {
+            const float4 v = lds128(pbase + 16u * (uint32_t)(h * P + w));
+            const int pix = h * W + w;
+            if (v.x > mv.x) mv.x = v.x, mi.x = pix;
+            if (v.y > mv.y) mv.y = v.y, mi.y = pix;
+            if (v.z > mv.z) mv.z = v.z, mi.z = pix;
+            if (v.w > mv.w) mv.w = v.w, mi.w = pix;
+          }
+        }
+      }
+      if (k < 7) {
+        // empty bin: 0 / -1 (roi_pooling_kernel.cu:67-72); else flat index into the NCHW tensor
+        const bool empty = !(h1 > h0 && we > ws);
+        float *qv = tile_v + ph * 7 + k;
+        int *qi = tile_i + ph * 7 + k;
+        qv[0] = empty ? 0.f : mv.x, qv[49] = empty ? 0.f : mv.y, qv[98] = empty ? 0.f : mv.z, qv[147] = empty ? 0.f : mv.w;
+        qi[0] = mi.x < 0 ? -1 : chan_base + mi.x, qi[49] = mi.y < 0 ? -1 : chan_base + HW + mi.y;
+        qi[98] = mi.z < 0 ? -1 : chan_base + 2 * HW + mi.z, qi[147] = mi.w < 0 ? -1 : chan_base + 3 * HW + mi.w;
+      }
+    }
+    fence_async_smem();
+    __syncwarp();
+    if (k == 0) {
+      if (r >= 0) {
+        const size_t o = ((size_t)r * C + (size_t)chunk * 4) * 49;
+        bulk_s2g_nocommit(out + o, tile_v, 196 * 4);
+        if (argmax) bulk_s2g_nocommit(argmax + o, tile_i, 196 * 4);
+      }
+      bulk_commit();
+    }
+  }
+  if (k == 0) bulk_wait_read<0>();
+}
+
 
 __global__ void __launch_bounds__(256)
     k_roi_pool_fwd(const float *__restrict__ feat, const float *__restrict__ rois, int B, int C,
@@ -105,17 +266,44 @@ __global__ void __launch_bounds__(256)
 
 using namespace rlod;
 
+RLOD_API size_t rlod_roi_pool_workspace_bytes(int B, int R) {
+  if (B < 0 || R < 0) return 0;
+  return carve_align_ws(nullptr, B, R, 8, 8).bytes;
+}
+
 RLOD_API int rlod_roi_pool_forward(const float *feat, const float *rois, int B, int C, int H,
                                    int W, int R, int ph, int pw, float spatial_scale, float *out,
-                                   int *argmax, rlod_stream_t stream) {
+                                   int *argmax, void *workspace, size_t workspace_bytes,
+                                   rlod_stream_t stream) {
   if (B < 0 || C < 0 || H < 1 || W < 1 || R < 0 || ph < 1 || pw < 1) return RLOD_EINVAL;
   if ((long long)B * C * H * W >= (1LL << 31)) return RLOD_EUNSUPPORTED;  // int argmax
   if (R == 0 || C == 0) return RLOD_OK;
   if (!feat || !rois || !out) return RLOD_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  // plane kernel: 7x7 bins, 4-channel chunks, planes + staging fit one CTA, enough rois per image
+  const int P = walk_pitch(W);
+  const size_t smem = (size_t)16 * H * P + (size_t)kPoolWarps * 4 * 2 * kPoolSlot * sizeof(float);
+  AlignWs ws = carve_align_ws(workspace, B, R, 8, 8);
+  const bool fast = ph == 7 && pw == 7 && (C % 4) == 0 && B >= 1 && smem <= (size_t)kMaxSmemPerCta &&
+                    workspace && workspace_bytes >= ws.bytes && ((uintptr_t)out % 16) == 0 &&
+                    (!argmax || ((uintptr_t)argmax % 16) == 0) && R >= 2 * B;
+  if (fast) {
+    cudaMemsetAsync(ws.flag, 0, 4 * sizeof(int), st);
+    RLOD_LAUNCH(RLOD_KERNEL_ROI_PLAN, st, k_pool_plan<<<(unsigned)cdiv(R, 128), 128, 0, st>>>(rois, R, B, H, W, spatial_scale, ws));
+    RLOD_LAUNCH(RLOD_KERNEL_ROI_PLAN, st, k_roi_group_fixup<<<1, 32, 0, st>>>(R, B, ws));
+    RLOD_LAUNCH(RLOD_KERNEL_ROI_PLAN, st,
+                k_roi_order_by_key<<<B, 32, 0, st>>>(ws.plan, ws.order, ws.img_off, 31, 0, 8, ws.order2));
+    const int n_chunks = C / 4;
+    cudaFuncSetAttribute(k_roi_pool7_fwd_planes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    RLOD_LAUNCH(RLOD_KERNEL_POOL_FWD, st,
+                k_roi_pool7_fwd_planes<<<(unsigned)(B * n_chunks), kPoolThreads, smem, st>>>(
+                    feat, ws.plan, ws.order2, ws.img_off, C, H, W, P, n_chunks, out, argmax));
+    return launch_status();
+  }
   const long long total = (long long)R * C * ph * pw;
   const long long blocks = cdiv(total, 256);
   const unsigned grid = (unsigned)(blocks < (1LL << 30) ? blocks : (1LL << 30));
-  RLOD_LAUNCH(RLOD_KERNEL_POOL_FWD, (cudaStream_t)stream, k_roi_pool_fwd<<<grid, 256, 0, (cudaStream_t)stream>>>(feat, rois, B, C, H, W, ph, pw,
+  RLOD_LAUNCH(RLOD_KERNEL_POOL_FWD, st, k_roi_pool_fwd<<<grid, 256, 0, st>>>(feat, rois, B, C, H, W, ph, pw,
                                                          spatial_scale, total, out, argmax));
   return launch_status();
 }

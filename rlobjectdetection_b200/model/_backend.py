@@ -41,7 +41,8 @@ SIGNATURES = {
     "rlod_roi_align_forward": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P, _P, _Z, _P]),
     "rlod_roi_align_backward": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _I, _I, _P, _P,
                                      _Z, _P]),
-    "rlod_roi_pool_forward": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P]),
+    "rlod_roi_pool_workspace_bytes": (_Z, [_I, _I]),
+    "rlod_roi_pool_forward": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P, _Z, _P]),
     "rlod_roi_pool_backward": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P, _P]),
     "rlod_proposal_workspace_bytes": (_Z, [_I, _I, _I, _I, _I, _I]),
     "rlod_proposal_forward": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P,
@@ -227,10 +228,12 @@ def roi_pool_forward(features, rois, ph, pw, scale):
     R = rois.size(0)
     out = torch.empty(R, C, ph, pw, dtype=torch.float32, device=features.device)
     argmax = torch.empty(R, C, ph, pw, dtype=torch.int32, device=features.device)
+    l = lib()
     with torch.cuda.device(features.device):
-        check(lib().rlod_roi_pool_forward(ptr(features), ptr(rois), B, C, H, W, R, ph, pw,
-                                          float(scale), ptr(out), ptr(argmax),
-                                          stream_of(features)), "rlod_roi_pool_forward")
+        ws = workspace(l.rlod_roi_pool_workspace_bytes(B, R), features.device)
+        check(l.rlod_roi_pool_forward(ptr(features), ptr(rois), B, C, H, W, R, ph, pw,
+                                      float(scale), ptr(out), ptr(argmax), ptr(ws), ws.numel(),
+                                      stream_of(features)), "rlod_roi_pool_forward")
     return out, argmax
 
 
