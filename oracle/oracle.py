@@ -369,6 +369,46 @@ def move_from_act(bboxes, preds, targets, act, maxk):
 # ----------------------------------------------------------------------------------------
 # the compiled reference itself (oracle/_ref, built from /root/reference in place)
 # ----------------------------------------------------------------------------------------
+def detect_postprocess(rois, cls_prob, bbox_pred, im_info, thresh=0.0, nms_thresh=0.3, max_per_image=100,
+                       stds=None, means=None, class_agnostic=False):
+    """Test-time post-processing, RCNN_bases/test_net.py:244-307, for a batch (the reference
+    runs batch 1).  Returns all_boxes[b][j] = (k, 5) float32 arrays [x1,y1,x2,y2,score]; class 0
+    is always empty.  Sort ties: lower roi index first (torch.sort order is unpinned)."""
+    rois, cls_prob, im_info = _f32(rois), _f32(cls_prob), _f32(im_info)
+    B, N, K = cls_prob.shape
+    out = []
+    for b in range(B):
+        boxes = rois[b, :, 1:5]
+        if bbox_pred is not None:
+            d = _f32(bbox_pred)[b].reshape(N, -1)
+            if stds is not None:  # :251-260
+                d = (d.reshape(-1, 4) * np.asarray(stds, np.float32) + np.asarray(means, np.float32)).reshape(N, -1)
+            pred = bbox_transform_inv(boxes[None], d[None])           # :262
+            pred = clip_boxes(pred, im_info[b:b + 1])[0]              # :263
+        else:
+            pred = np.tile(boxes, (1, K))                             # :266
+        pred = (pred / im_info[b, 2]).astype(np.float32)              # :268
+        per_class = [np.zeros((0, 5), np.float32)]
+        for j in range(1, K):                                         # :277-297
+            inds = np.nonzero(cls_prob[b, :, j] > np.float32(thresh))[0]
+            if inds.size == 0:
+                per_class.append(np.zeros((0, 5), np.float32))
+                continue
+            sc = cls_prob[b, inds, j]
+            order = np.argsort(-sc.astype(np.float64), kind="stable")
+            cb = pred[inds] if class_agnostic else pred[inds][:, 4 * j:4 * j + 4]
+            dets = np.concatenate([cb, sc[:, None]], 1).astype(np.float32)[order]
+            keep = nms(dets, nms_thresh)
+            per_class.append(dets[keep])
+        if max_per_image > 0:                                         # :299-307
+            sc = np.concatenate([c[:, 4] for c in per_class[1:]])
+            if sc.size > max_per_image:
+                th = np.sort(sc)[-max_per_image]
+                per_class = [c[c[:, 4] >= th] if i else c for i, c in enumerate(per_class)]
+        out.append(per_class)
+    return out
+
+
 def ref_maskapi():
     path = os.path.join(_HERE, "_ref", "libmaskapi.so")
     return ctypes.CDLL(path) if os.path.exists(path) else None

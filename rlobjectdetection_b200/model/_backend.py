@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(CSRC, "librlod_sm100a.so")
 POOL_NONE, POOL_AVG, POOL_MAX = 0, 1, 2
 KERNELS = ["align_fwd", "align_bwd", "align_fwd_generic", "align_bwd_generic", "roi_plan", "nms_mask",
            "nms_scan", "nms_small", "proposal_sort", "pool_fwd", "pool_bwd", "boxes", "reward", "move",
-           "nms_lazy"]
+           "nms_lazy", "detect"]
 IOU_COCO, IOU_RCNN = 0, 1
 SORT_MAX = 16384  # rlod_proposal_forward: min(pre_nms_topN, H*W*A) limit
 
@@ -54,6 +54,7 @@ SIGNATURES = {
     "rlod_action_reward": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _F, _P, _P, _P,
                                 _P]),
     "rlod_move_from_act": (_I, [_P, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "rlod_detect_postprocess": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _F, _F, _I, _P, _P, _P]),
 }
 
 _LIB = None
@@ -332,3 +333,32 @@ def move_from_act(boxes, preds, targets, act, maxk, corners=False):
                                        ptr(act), B, N, A, int(maxk), ptr(correct),
                                        stream_of(boxes)), "rlod_move_from_act")
     return correct
+
+
+def detect_postprocess(rois, cls_prob, bbox_pred, im_info, thresh=0.0, nms_thresh=0.3, max_per_image=100,
+                       stds=None, means=None, class_agnostic=False):
+    """rlod_detect_postprocess: the per-class threshold / decode / sort / NMS / cap loop of
+    test_net.py:244-307 for a whole batch.  Returns dets (B,K,N,5) and counts (B,K) int32 on the
+    device; class j of image b = dets[b, j, :counts[b, j]] (rows [x1,y1,x2,y2,score])."""
+    require_cuda("detect_postprocess", rois, cls_prob, bbox_pred, im_info)
+    rois, cls_prob, im_info = f32c(rois), f32c(cls_prob), f32c(im_info)
+    if rois.dim() != 3 or rois.size(2) != 5 or cls_prob.dim() != 3:
+        raise ValueError("rois must be (B, N, 5) and cls_prob (B, N, K)")
+    B, N, K = cls_prob.shape
+    if bbox_pred is not None:
+        bbox_pred = f32c(bbox_pred).view(B, N, -1)
+        if bbox_pred.size(2) != (4 if class_agnostic else 4 * K):
+            raise ValueError("bbox_pred must be (B, N, 4K), or (B, N, 4) when class_agnostic")
+    dets = torch.zeros(B, K, N, 5, dtype=torch.float32, device=rois.device)
+    counts = torch.zeros(B, K, dtype=torch.int32, device=rois.device)
+    arr = (ctypes.c_float * 4)
+    s = arr(*[float(v) for v in stds]) if stds is not None else None
+    m = arr(*[float(v) for v in means]) if means is not None else None
+    if (s is None) != (m is None):
+        raise ValueError("stds and means go together")
+    with torch.cuda.device(rois.device):
+        check(lib().rlod_detect_postprocess(ptr(rois), ptr(cls_prob), ptr(bbox_pred), ptr(im_info), B, N, K,
+                                            int(bool(class_agnostic)), s, m, float(thresh), float(nms_thresh),
+                                            int(max_per_image), ptr(dets), ptr(counts), stream_of(rois)),
+              "rlod_detect_postprocess")
+    return dets, counts

@@ -1,5 +1,5 @@
 """The configuration keys the hot path reads, under the reference's names
-(lib/model/utils/config.py:141-147, 175, 191-199, 283-298).  Only these keys are provided:
+(lib/model/utils/config.py:112-119, 141-147, 175, 182, 191-199, 283-298).  Only these keys are provided:
 the reference's dataset / solver / yaml machinery is out of scope.  `cfg` is an attribute
 dict, so `cfg[cfg_key].RPN_PRE_NMS_TOP_N` (proposal_layer.py:72-75) and `cfg.POOLING_SIZE`
 (faster_rcnn.py:33-34) work unchanged; `cfg_from_list` accepts the same flat key/value list as
@@ -20,9 +20,12 @@ class AttrDict(dict):
 
 cfg = AttrDict(
     TRAIN=AttrDict(RPN_NMS_THRESH=0.7, RPN_PRE_NMS_TOP_N=12000, RPN_POST_NMS_TOP_N=2000,
-                   RPN_MIN_SIZE=8),
+                   RPN_MIN_SIZE=8,
+                   # test_net.py:251-260 un-normalises bbox_pred with these (config.py:112-119)
+                   BBOX_NORMALIZE_TARGETS_PRECOMPUTED=True, BBOX_NORMALIZE_MEANS=(0.0, 0.0, 0.0, 0.0),
+                   BBOX_NORMALIZE_STDS=(0.1, 0.1, 0.2, 0.2)),
     TEST=AttrDict(NMS=0.3, RPN_NMS_THRESH=0.7, RPN_PRE_NMS_TOP_N=6000, RPN_POST_NMS_TOP_N=300,
-                  RPN_MIN_SIZE=16),
+                  RPN_MIN_SIZE=16, BBOX_REG=True),
     POOLING_MODE="align",  # the reference defaults to 'crop' (:283); roi_crop is out of scope
     POOLING_SIZE=7,
     MAX_NUM_GT_BOXES=20,

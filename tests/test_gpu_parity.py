@@ -498,3 +498,49 @@ def test_hotpath_step_matches_oracle_chain(orc):
           orc.roi_align(feat.numpy(), refined.reshape(-1, 5), 7, 7, 1 / 16.0, pool_mode=orc.POOL_AVG))
     close(out["grad_feat"].cpu().numpy(),
           orc.roi_align_bwd(gp.numpy(), feat.numpy(), refined.reshape(-1, 5), 7, 7, 1 / 16.0, pool_mode=orc.POOL_AVG))
+
+
+# ------------------------------------------------------------------------------------------
+# test-time post-processing (f1): threshold / decode / clip / sort / per-class NMS / cap
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["c21", "c9", "agn"])
+def test_detect_postprocess_golden(orc, tag):
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_detect.npz"))
+    N, K, agn, cap = (int(v) for v in g[f"{tag}_cfg"])
+    dets, counts = be.detect_postprocess(cu(g[f"{tag}_rois"]), cu(g[f"{tag}_cls_prob"]), cu(g[f"{tag}_bbox_pred"]),
+                                         cu(g[f"{tag}_im_info"]), thresh=float(g[f"{tag}_thresh"]), nms_thresh=0.3,
+                                         max_per_image=cap, stds=(0.1, 0.1, 0.2, 0.2), means=(0.0, 0.0, 0.0, 0.0),
+                                         class_agnostic=bool(agn))
+    c = counts.cpu().numpy()[0]
+    assert list(c) == list(g[f"{tag}_counts"])  # keep decisions bit-exact
+    d = dets.cpu().numpy()[0]
+    got = np.concatenate([d[j, :c[j]] for j in range(K)], 0)
+    ref = g[f"{tag}_dets"]
+    assert np.array_equal(got[:, 4], ref[:, 4])
+    np.testing.assert_allclose(got[:, :4], ref[:, :4], rtol=3e-6, atol=2e-4)
+
+
+def test_detect_postprocess_c5_size(orc):
+    # config 5: 64 images x 81 classes x 300 boxes, thr 0.3: keep lists vs the oracle
+    from rlobjectdetection_b200.detections import postprocess_detections, to_all_boxes
+    B, N, K = 64, 300, 81
+    g = torch.Generator().manual_seed(77)
+    rois = torch.cat([torch.arange(B).float()[:, None, None].expand(B, N, 1),
+                      torch.stack([syn.random_boxes(g, N, 600, 1000, 24.0, 300.0) for _ in range(B)], 0)], 2).contiguous()
+    cls_prob = torch.softmax(torch.randn(B, N, K, generator=g) * 3.0, 2).contiguous()
+    bbox_pred = (torch.randn(B, N, 4 * K, generator=g) * 0.5).contiguous()
+    im_info = torch.tensor([[600.0, 1000.0, 1.6]]).repeat(B, 1)
+    dets, counts = postprocess_detections(cu(rois), cu(cls_prob), cu(bbox_pred), cu(im_info), thresh=0.05)
+    ab = to_all_boxes(dets, counts)
+    sub = [0, 17, 63]
+    ref = orc.detect_postprocess(rois[sub].numpy(), cls_prob[sub].numpy(), bbox_pred[sub].numpy(), im_info[sub].numpy(),
+                                 thresh=0.05, nms_thresh=0.3, max_per_image=100, stds=(0.1, 0.1, 0.2, 0.2),
+                                 means=(0.0, 0.0, 0.0, 0.0))
+    for k, b in enumerate(sub):
+        for j in range(K):
+            assert ab[j][b].shape == ref[k][j].shape, (b, j)
+            assert np.array_equal(ab[j][b][:, 4], ref[k][j][:, 4])
+            np.testing.assert_allclose(ab[j][b][:, :4], ref[k][j][:, :4], rtol=3e-6, atol=2e-4)
+    c = counts.cpu().numpy()
+    assert (c[:, 0] == 0).all() and (c.sum(1) >= 100).all()  # the cap keeps ties with >=

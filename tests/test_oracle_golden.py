@@ -82,3 +82,19 @@ def test_ref_maskapi_when_present(orc, golden):
     gt = np.concatenate([rng.random((50, 2)) * 300, rng.random((50, 2)) * 100], 1)
     cr = (rng.random(50) < 0.2).astype(np.uint8)
     np.testing.assert_array_equal(orc.bbiou(dt, gt, cr), orc.ref_bbiou(dt, gt, cr))
+
+
+@pytest.mark.parametrize("tag", ["c21", "c9", "agn"])
+def test_detect_postprocess(orc, tag):
+    """test_net.py:244-307 executed with the reference's own decode / clip / sort
+    (tests/golden/make_golden_detect.py) vs the oracle restatement."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_detect.npz"))
+    N, K, agn, cap = (int(v) for v in g[f"{tag}_cfg"])
+    ab = orc.detect_postprocess(g[f"{tag}_rois"], g[f"{tag}_cls_prob"], g[f"{tag}_bbox_pred"], g[f"{tag}_im_info"],
+                                thresh=float(g[f"{tag}_thresh"]), nms_thresh=0.3, max_per_image=cap,
+                                stds=(0.1, 0.1, 0.2, 0.2), means=(0.0, 0.0, 0.0, 0.0), class_agnostic=bool(agn))[0]
+    assert [len(a) for a in ab] == list(g[f"{tag}_counts"])
+    got = np.concatenate(ab, 0)
+    np.testing.assert_allclose(got, g[f"{tag}_dets"], rtol=1e-6, atol=1e-4)
+    assert np.array_equal(got[:, 4], g[f"{tag}_dets"][:, 4])  # scores pass through untouched
