@@ -268,13 +268,40 @@ def run_ours(args, rank, local_rank, world):
     h2d = sum(t.numel() * t.element_size() for t in host)
     d2h = result_host.numel() * result_host.element_size()
 
-    def e2e_step():
-        d_in = [t.to(dev, non_blocking=True) for t in host]
-        _, gathered = device_step(d_in)
-        result_host.copy_(gathered, non_blocking=True)
-        torch.cuda.current_stream().synchronize()  # the caller reads the detections
+    # Every step copies ITS inputs host -> device and ITS result device -> host inside the timed
+    # region.  The copies run on their own stream into double-buffered device tensors, so step
+    # i+1's upload overlaps step i's kernels (what a serving loop does); the caller-visible
+    # result of step i is complete (synchronised) before step i+1's kernels are enqueued.
+    copy_stream = torch.cuda.Stream(device=dev)
+    main_stream = torch.cuda.current_stream()
+    bufs = [[torch.empty_like(t, device=dev) for t in host] for _ in range(2)]
+    up_done = [torch.cuda.Event(), torch.cuda.Event()]
+    free = [torch.cuda.Event(), torch.cuda.Event()]
+    state = {"i": 0, "primed": False}
 
-    e2e_steps = max(2, min(args.steps, 10))
+    def upload(slot):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(free[slot])  # the step that last read this buffer is done
+            for dst, src in zip(bufs[slot], host):
+                dst.copy_(src, non_blocking=True)
+            up_done[slot].record(copy_stream)
+
+    def e2e_step():
+        i = state["i"]
+        slot = i & 1
+        if not state["primed"]:
+            free[0].record(main_stream), free[1].record(main_stream)
+            upload(slot)
+            state["primed"] = True
+        upload(slot ^ 1)                     # next step's inputs travel while this step computes
+        main_stream.wait_event(up_done[slot])
+        _, gathered = device_step(bufs[slot])
+        free[slot].record(main_stream)
+        result_host.copy_(gathered, non_blocking=True)
+        main_stream.synchronize()            # the caller reads the detections
+        state["i"] = i + 1
+
+    e2e_steps = max(2, min(args.steps, 20))
     ms_e2e = timed(e2e_step, e2e_steps, 2)
     e2e_value = global_batch * e2e_steps / (ms_e2e * 1e-3)
 

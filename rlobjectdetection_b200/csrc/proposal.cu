@@ -10,6 +10,7 @@
 //       2. compact the selected keys and bitonic-sort them in shared memory, three network
 //          levels per pass (all composite keys are distinct, so the order is exactly "score
 //          descending, ties by lower anchor index" = a stable descending sort);
+//   k_proposal_decode  one thread per selected anchor of the whole batch:
 //       3. decode (bbox_transform_inv, bbox_transform.py:77-103) + clip (clip_boxes,
 //          :125-133) only the selected anchors, anchors generated arithmetically from the
 //          (A,4) base table (:80-93), deltas gathered from channel 4a+k; every fp32 op rounds
@@ -41,6 +42,13 @@ struct PropArgs {
   int *order_out;                    // (B, pre) or NULL
   float *props_out;                  // (B, pre, 4) or NULL
 };
+
+// 0xffffffff when a <= b, else 0: one instruction, so `count -= le_mask(...)` is two
+__device__ __forceinline__ unsigned le_mask(uint32_t a, uint32_t b) {
+  unsigned r;
+  asm("set.le.u32.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
 
 // compare-exchange of a bitonic network: ascending when up
 __device__ __forceinline__ void cmpex(unsigned long long &x, unsigned long long &y, bool up) {
@@ -137,7 +145,7 @@ __global__ void __launch_bounds__(kSortThreads) k_proposal_sort_decode(PropArgs 
 #pragma unroll 4
       for (int q = t; q < n4; q += kSortThreads) {
         const uint4 v = k4[q];
-        c0 += v.x <= mid, c1 += v.y <= mid, c2 += v.z <= mid, c3 += v.w <= mid;
+        c0 -= le_mask(v.x, mid), c1 -= le_mask(v.y, mid), c2 -= le_mask(v.z, mid), c3 -= le_mask(v.w, mid);
       }
       for (int e = (n4 << 2) + t; e < KA; e += kSortThreads) c0 += skeys[e] <= mid;
       return finish_count((c0 + c1) + (c2 + c3));
@@ -212,13 +220,22 @@ __global__ void __launch_bounds__(kSortThreads) k_proposal_sort_decode(PropArgs 
     }
   }
 
-  // decode + clip the selected anchors in sorted order
+  // the sorted keys go back to the global scratch row: decoding is embarrassingly parallel
+  // and runs as its own launch over ALL images' boxes (this kernel has one CTA per image)
+  for (int i = t; i < M; i += kSortThreads) sel[i] = keys[sidx(i)];
+}
+
+// decode + clip the selected anchors in sorted order: one thread per (image, rank)
+__global__ void __launch_bounds__(256) k_proposal_decode(PropArgs a, int mp) {
+  const int M = a.pre, HW = a.H * a.W;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (long long)a.B * M) return;
+  const int b = (int)(gid / M), i = (int)(gid - (long long)b * M);
   const float imh = a.im_info[b * 3 + 0], imw = a.im_info[b * 3 + 1];
   const float xmax = __fsub_rn(imw, 1.f), ymax = __fsub_rn(imh, 1.f);
   const float *dl = a.deltas + (size_t)b * 4 * a.A * HW;
-#pragma unroll 4
-  for (int i = t; i < M; i += kSortThreads) {
-    const int idx = (int)(unsigned)(keys[sidx(i)] & 0xffffffffull);
+  {
+    const int idx = (int)(unsigned)(a.sel[(size_t)b * mp + i] & 0xffffffffull);
     const int an = idx % a.A, pix = idx / a.A;
     const int y = pix / a.W, x = pix - y * a.W;
     const float sx = (float)(x * a.feat_stride), sy = (float)(y * a.feat_stride);
@@ -324,6 +341,8 @@ RLOD_API int rlod_proposal_forward(const float *scores, const float *deltas, con
   cudaFuncSetAttribute(k_proposal_sort_decode, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)smem);
   RLOD_LAUNCH(RLOD_KERNEL_PROPOSAL_SORT, st, k_proposal_sort_decode<<<B, kSortThreads, smem, st>>>(pa, mp));
+  RLOD_LAUNCH(RLOD_KERNEL_PROPOSAL_SORT, st,
+              k_proposal_decode<<<(unsigned)cdiv((long long)B * pre, 256), 256, 0, st>>>(pa, mp));
   int rc = launch_status();
   if (rc) return rc;
 
