@@ -296,21 +296,43 @@ __device__ __forceinline__ int tap_order_natural(const int *L, const int *R, int
 }
 
 // one warp per roi
-__global__ void __launch_bounds__(128)
-    k_roi_plan8_walk(const int *__restrict__ plan, int R, int H, int W, int P, int bwd,
-                     int *__restrict__ ext) {
+__global__ void __launch_bounds__(128, 6)
+    k_roi_plan8_walk(const float *__restrict__ rois, int R, int B, int H, int W, int P, float scale,
+                     int bwd, AlignWs ws) {
   const int r = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (r >= R) return;
-  const int *pl = plan + (size_t)r * 32;
-  int *e = ext + (size_t)r * 32;
+  int *e = ws.ext + (size_t)r * 32;
+  // the separable 8x8 sample grid (k_roi_plan's arithmetic): lanes 0-7 the sample rows, lanes
+  // 8-15 the sample columns, then every lane gets all sixteen by shuffle
+  int my_idx = -1, my_ratio = 0;
+  {
+    const float *roi = rois + (size_t)r * 5;
+    const float bf = __ldg(roi);
+    const int bi = (int)bf;
+    const bool bvalid = (bf >= 0.f) && (bi < B);
+    const bool is_row = lane < 8;
+    const int p = lane & 7;
+    const int dim = is_row ? H : W;
+    const float c0 = is_row ? __ldg(roi + 2) : __ldg(roi + 1);
+    const float c1 = is_row ? __ldg(roi + 4) : __ldg(roi + 3);
+    const float start = __fmul_rn(c0, scale);
+    const float size = fmaxf(__fadd_rn(__fmaf_rn(c1, scale, -start), 1.f), 0.f);
+    const float bin = (float)((double)size / 7.);
+    const float pos = __fmaf_rn((float)p, bin, start);
+    if (lane < 16 && bvalid && (pos >= 0.f) && (pos < (float)dim)) {
+      my_idx = (int)fminf(floorf(pos), (float)(dim - 2));
+      my_ratio = __float_as_int(__fsub_rn(pos, (float)my_idx));
+    }
+    if (lane == 0) roi_list_mark(rois, r, R, B, bvalid ? bi : 0, ws);
+  }
   int row[8], col[8];
   bool colv[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const int hs = __ldg(pl + i), ws = __ldg(pl + 16 + 2 * i);
+    const int hs = __shfl_sync(0xffffffffu, my_idx, i), wsx = __shfl_sync(0xffffffffu, my_idx, 8 + i);
     row[i] = hs >= 0 ? hs : H;  // zero rows H, H+1
-    colv[i] = ws >= 0;
-    col[i] = ws >= 0 ? ws : W;  // zero column
+    colv[i] = wsx >= 0;
+    col[i] = wsx >= 0 ? wsx : W;  // zero column
   }
   int nl[2], ra[8], rb[8], ca[8], cb[8];
   const int fl_rows = walk_slots(row, ra, rb, nl[0]), fl_cols = walk_slots(col, ca, cb, nl[1]);
@@ -346,14 +368,15 @@ __global__ void __launch_bounds__(128)
   }
   best = __reduce_min_sync(0xffffffffu, best);
   const int mode = (best >> 8) & 1, bits = best & 255;
+  // lane t < 8 computed sample row t itself; sample column t sits in lane 8 + t
+  const int wsx = __shfl_sync(0xffffffffu, my_idx, 8 + (lane & 7)), wrt = __shfl_sync(0xffffffffu, my_ratio, 8 + (lane & 7));
   if (lane >= 8) return;
   // lane t writes walk position t and lane-axis entry t; pixel offsets (bytes / 16) stay
   // below 8192 (host-checked)
   const int t = lane;
-  const int hs = __ldg(pl + t), ws = __ldg(pl + 16 + 2 * t);
-  const int rowt = hs >= 0 ? hs : H, colt = ws >= 0 ? ws : W;
-  const int hrt = hs >= 0 ? __ldg(pl + 8 + t) : 0, wrt = ws >= 0 ? __ldg(pl + 16 + 2 * t + 1) : 0;
-  const int colt1 = ws >= 0 ? colt + 1 : colt;
+  const int hs = my_idx, hrt = my_ratio;
+  const int rowt = hs >= 0 ? hs : H, colt = wsx >= 0 ? wsx : W;
+  const int colt1 = wsx >= 0 ? colt + 1 : colt;
   int sa = 0, sb = 0;  // the lines slots a / b hold at walk position t
 #pragma unroll
   for (int i = 0; i < 8; ++i)
@@ -986,8 +1009,6 @@ RLOD_API int rlod_roi_align_forward(const float *feat, const float *rois, int B,
   AlignWs ws = carve_align_ws(workspace, B, R, GH, GW);
   if (workspace_bytes < ws.bytes) return RLOD_ENOSPC;
   cudaStream_t st = (cudaStream_t)stream;
-  rc = build_plan(rois, B, H, W, R, GH, GW, spatial_scale, ws, st);
-  if (rc) return rc;
 
   const size_t smem = fwd_walk_smem(H, W, pool_mode);
   const bool fast = GH == 8 && GW == 8 && (C % 4) == 0 && smem <= (size_t)kMaxSmemPerCta &&
@@ -996,16 +1017,17 @@ RLOD_API int rlod_roi_align_forward(const float *feat, const float *rois, int B,
     const int n_chunks = C / 4;
     const unsigned grid = (unsigned)(B * n_chunks);
     const int P = walk_pitch(W);
+    // one launch: sample grid + orientation / tap-order search + walk record + roi lists
+    cudaMemsetAsync(ws.flag, 0, 4 * sizeof(int), st);
     RLOD_LAUNCH(RLOD_KERNEL_ROI_PLAN, st,
-                k_roi_plan8_walk<<<(unsigned)cdiv(R, 4), 128, 0, st>>>(ws.plan, R, H, W, P, 0, ws.ext));
-    RLOD_LAUNCH(RLOD_KERNEL_ROI_PLAN, st,
-                k_roi_order_by_key<<<B, 32, 0, st>>>(ws.ext, ws.order, ws.img_off, 0, 30, 2, ws.order2));
+                k_roi_plan8_walk<<<(unsigned)cdiv(R, 4), 128, 0, st>>>(rois, R, B, H, W, P, spatial_scale, 0, ws));
+    RLOD_LAUNCH(RLOD_KERNEL_ROI_PLAN, st, k_roi_group_fixup<<<1, 32, 0, st>>>(R, B, ws));
 #define RLOD_LAUNCH_FWD(POOL)                                                                  \
   do {                                                                                         \
     cudaFuncSetAttribute(k_align8_fwd_walk<POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                          (int)smem);                                                           \
     ProfScope _ps(RLOD_KERNEL_ALIGN_FWD, st);                                                  \
-    k_align8_fwd_walk<POOL><<<grid, kWalkThreads, smem, st>>>(feat, ws.ext, ws.order2,         \
+    k_align8_fwd_walk<POOL><<<grid, kWalkThreads, smem, st>>>(feat, ws.ext, ws.order,          \
                                                               ws.img_off, C, H, W, P,          \
                                                               n_chunks, out);                  \
   } while (0)
@@ -1018,6 +1040,8 @@ RLOD_API int rlod_roi_align_forward(const float *feat, const float *rois, int B,
 #undef RLOD_LAUNCH_FWD
     return launch_status();
   }
+  rc = build_plan(rois, B, H, W, R, GH, GW, spatial_scale, ws, st);
+  if (rc) return rc;
   const long long total = (long long)R * C * ah * aw;
   const unsigned grid = (unsigned)(cdiv(total, 256) < (1LL << 30) ? cdiv(total, 256) : (1LL << 30));
   if (pool_mode == RLOD_POOL_NONE)
@@ -1053,9 +1077,6 @@ RLOD_API int rlod_roi_align_backward(const float *grad_out, const float *rois, c
   const int GW = pool_mode == RLOD_POOL_NONE ? aw : aw + 1;
   AlignWs ws = carve_align_ws(workspace, B, R, GH, GW);
   if (workspace_bytes < ws.bytes) return RLOD_ENOSPC;
-  rc = build_plan(rois, B, H, W, R, GH, GW, spatial_scale, ws, st);
-  if (rc) return rc;
-
   const int P = walk_pitch(W);
   const size_t smem = fwd_walk_smem(H, W, pool_mode) + (size_t)((H + 2 + 3) & ~3) * sizeof(int) +
                       (size_t)kWalkWarps * 2 * sizeof(uint64_t);
@@ -1063,10 +1084,12 @@ RLOD_API int rlod_roi_align_backward(const float *grad_out, const float *rois, c
                     ((uintptr_t)grad_out % 16) == 0 && smem <= (size_t)kMaxSmemPerCta &&
                     (H + 2) * P <= 8192 && H + 2 <= 64 * 4 && R >= 2 * B;
   if (fast) {
+    cudaMemsetAsync(ws.flag, 0, 4 * sizeof(int), st);
     RLOD_LAUNCH(RLOD_KERNEL_ROI_PLAN, st,
-                k_roi_plan8_walk<<<(unsigned)cdiv(R, 4), 128, 0, st>>>(ws.plan, R, H, W, P, 1, ws.ext));
+                k_roi_plan8_walk<<<(unsigned)cdiv(R, 4), 128, 0, st>>>(rois, R, B, H, W, P, spatial_scale, 1, ws));
+    RLOD_LAUNCH(RLOD_KERNEL_ROI_PLAN, st, k_roi_group_fixup<<<1, 32, 0, st>>>(R, B, ws));
     RLOD_LAUNCH(RLOD_KERNEL_ROI_PLAN, st,
-                k_roi_order_by_key<<<B, 32, 0, st>>>(ws.ext, ws.order, ws.img_off, 16, 20, 8, ws.order2));
+                k_roi_order_by_key<<<B, kOrderThreads, 0, st>>>(ws.ext, ws.order, ws.img_off, 16, 20, 8, ws.order2));
     const int n_chunks = C / 4;
     const unsigned grid = (unsigned)(B * n_chunks);
     const int lock_mul = (65536 + P - 1) / P;  // row = (pixel offset * lock_mul) >> 16, exact for rows < 2^16 / P
@@ -1086,6 +1109,8 @@ RLOD_API int rlod_roi_align_backward(const float *grad_out, const float *rois, c
 #undef RLOD_LAUNCH_BWD
     return launch_status();
   }
+  rc = build_plan(rois, B, H, W, R, GH, GW, spatial_scale, ws, st);
+  if (rc) return rc;
   if (!accumulate) cudaMemsetAsync(grad_in, 0, gin_bytes, st);
   const int IH = pool_mode == RLOD_POOL_MAX ? ah : GH, IW = pool_mode == RLOD_POOL_MAX ? aw : GW;
   const long long total = (long long)R * C * IH * IW;

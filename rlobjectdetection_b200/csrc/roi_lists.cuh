@@ -117,26 +117,58 @@ static __global__ void k_roi_group_fixup(int R, int B, AlignWs ws) {
 // together stage with the same strides; backward: the longest run of lanes that share a
 // column (word 16 bits 20-22), so that a narrow roi does not impose its extra scatter rounds
 // on three wide ones.
-static __global__ void k_roi_order_by_key(const int *__restrict__ ext, const int *__restrict__ order,
-                                   const int *__restrict__ img_off, int word, int shift, int nkeys,
-                                   int *__restrict__ order2) {
-  const int b = blockIdx.x, lane = threadIdx.x;
-  const int r0 = img_off[b], r1 = img_off[b + 1];
-  const unsigned full = 0xffffffffu, below = (1u << lane) - 1u;
-  int start = r0;
-  for (int key = 0; key < nkeys; ++key) {
-    int c = start;
-    for (int base = r0; base < r1; base += 32) {
-      const int i = base + lane;
-      const int r = i < r1 ? order[i] : 0;
-      const bool hit = i < r1 && ((ext[(size_t)r * 32 + word] >> shift) & (nkeys - 1)) == key;
-      const unsigned m = __ballot_sync(full, hit);
-      if (hit) order2[c + __popc(m & below)] = r;
-      c += __popc(m);
+constexpr int kOrderThreads = 256;
+constexpr int kOrderMaxRois = 2048;  // per image, held in shared memory; longer lists take the slow path
+static __global__ void __launch_bounds__(kOrderThreads)
+    k_roi_order_by_key(const int *__restrict__ ext, const int *__restrict__ order,
+                       const int *__restrict__ img_off, int word, int shift, int nkeys,
+                       int *__restrict__ order2) {
+  // one CTA per image: all keys are fetched at once (one dependent pair of loads for the whole
+  // list) into shared memory, a per-key count gives the key offsets, then every roi finds its
+  // rank among the rois of its key that precede it (stable)
+  __shared__ unsigned short s_key[kOrderMaxRois];
+  __shared__ int s_tot[8], s_base[8];
+  const int b = blockIdx.x, t = threadIdx.x, lane = t & 31;
+  const int r0 = img_off[b], r1 = img_off[b + 1], n = r1 - r0;
+  const unsigned full = 0xffffffffu;
+  if (n > kOrderMaxRois) {
+    // slow path (one warp): stable counting sort, key by key
+    if (t >= 32) return;
+    const unsigned below = (1u << lane) - 1u;
+    int start = r0;
+    for (int key = 0; key < nkeys; ++key) {
+      int c = start;
+      for (int base = r0; base < r1; base += 32) {
+        const int i = base + lane;
+        const int r = i < r1 ? order[i] : 0;
+        const bool hit = i < r1 && ((ext[(size_t)r * 32 + word] >> shift) & (nkeys - 1)) == key;
+        const unsigned m = __ballot_sync(full, hit);
+        if (hit) order2[c + __popc(m & below)] = r;
+        c += __popc(m);
+      }
+      start = c;
     }
-    start = c;
+    return;
+  }
+  if (t < 8) s_tot[t] = 0;
+  __syncthreads();
+  for (int i = t; i < n; i += kOrderThreads) {
+    const int key = (ext[(size_t)order[r0 + i] * 32 + word] >> shift) & (nkeys - 1);
+    s_key[i] = (unsigned short)key;
+    atomicAdd(&s_tot[key], 1);
+  }
+  __syncthreads();
+  if (t == 0) {
+    int acc = 0;
+    for (int k = 0; k < nkeys; ++k) s_base[k] = acc, acc += s_tot[k];
+  }
+  __syncthreads();
+  for (int i = t; i < n; i += kOrderThreads) {
+    const int key = s_key[i];
+    int rank = 0;
+    for (int q = 0; q < i; ++q) rank += s_key[q] == key;  // n is a few hundred: a short scan
+    order2[r0 + s_base[key] + rank] = order[r0 + i];
   }
 }
-
 
 }  // namespace rlod

@@ -292,7 +292,7 @@ RLOD_API int rlod_roi_pool_forward(const float *feat, const float *rois, int B, 
     RLOD_LAUNCH(RLOD_KERNEL_ROI_PLAN, st, k_pool_plan<<<(unsigned)cdiv(R, 128), 128, 0, st>>>(rois, R, B, H, W, spatial_scale, ws));
     RLOD_LAUNCH(RLOD_KERNEL_ROI_PLAN, st, k_roi_group_fixup<<<1, 32, 0, st>>>(R, B, ws));
     RLOD_LAUNCH(RLOD_KERNEL_ROI_PLAN, st,
-                k_roi_order_by_key<<<B, 32, 0, st>>>(ws.plan, ws.order, ws.img_off, 31, 0, 8, ws.order2));
+                k_roi_order_by_key<<<B, kOrderThreads, 0, st>>>(ws.plan, ws.order, ws.img_off, 31, 0, 8, ws.order2));
     const int n_chunks = C / 4;
     cudaFuncSetAttribute(k_roi_pool7_fwd_planes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     RLOD_LAUNCH(RLOD_KERNEL_POOL_FWD, st,
