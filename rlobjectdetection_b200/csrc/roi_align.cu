@@ -827,6 +827,7 @@ __global__ void __launch_bounds__(kWalkThreads, 2)
   float *stage = reinterpret_cast<float *>(planes4 + (H + 2) * P);
   int *locks = reinterpret_cast<int *>(stage + kWalkWarps * 2 * 4 * SLOT);
   uint64_t *bars = reinterpret_cast<uint64_t *>(locks + ((H + 2 + 3) & ~3));  // [kWalkWarps][2]
+  int *s_next = reinterpret_cast<int *>(bars + 2 * kWalkWarps);
 
   const int b = blockIdx.x / n_chunks, chunk = blockIdx.x - b * n_chunks;
   const int r0 = img_off[b], r1 = img_off[b + 1];
@@ -837,6 +838,7 @@ __global__ void __launch_bounds__(kWalkThreads, 2)
   // planes: zero, or the caller's gradient when accumulating
   for (int p = threadIdx.x; p < (H + 2) * P; p += kWalkThreads) planes4[p] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int p = threadIdx.x; p < H + 2; p += kWalkThreads) locks[p] = 0;
+  if (threadIdx.x == 0) *s_next = kWalkWarps;
   if (lane == 0) {
     mbar_init(bars + 2 * warp, 1);
     mbar_init(bars + 2 * warp + 1, 1);
@@ -873,21 +875,30 @@ __global__ void __launch_bounds__(kWalkThreads, 2)
   auto prefetch_rec = [&](int rr) {
     if (rr >= 0 && k == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(ext + (size_t)rr * 32));
   };
-  int r = roi_of(warp);
-  int rn = roi_of(warp + kWalkWarps);
+  // groups are claimed from a shared counter (the cost of a group varies with lock retries and
+  // rank rounds), two ahead: one whose tiles are in flight, one whose roi ids are being read
+  auto claim = [&]() {
+    int v = 0;
+    if (lane == 0) v = atomicAdd(s_next, 1);
+    return __shfl_sync(0xffffffffu, v, 0);
+  };
+  int g = warp, gn = claim();
+  int r = roi_of(g);
+  int rn = roi_of(gn);
   prefetch_rec(r);
-  if (warp < n_groups) issue_tiles(r, 0);
+  if (g < n_groups) issue_tiles(r, 0);
 
-  for (int g = warp, it = 0; g < n_groups; g += kWalkWarps, ++it) {
+  for (int it = 0; g < n_groups; ++it) {
     WalkRec cur;
     walk_rec_clear(cur);
     if (r >= 0) walk_rec_load(ext, r, k, cur);
     prefetch_rec(rn);
-    const int rnn = roi_of(g + 2 * kWalkWarps);
+    const int gnn = claim();
+    const int rnn = roi_of(gnn);
     const int buf = it & 1;
     // next group's tiles go into the other buffer: its last reads (previous iteration) are
     // ordered before this point by the warp barriers of the flushes
-    if (g + kWalkWarps < n_groups) issue_tiles(rn, buf ^ 1);
+    if (gn < n_groups) issue_tiles(rn, buf ^ 1);
     mbar_wait(bars + 2 * warp + buf, (uint32_t)((it >> 1) & 1));
 
     // ---- sample gradients of this lane's column, 4 channels, one sample row at a time --------
@@ -945,8 +956,8 @@ __global__ void __launch_bounds__(kWalkThreads, 2)
     }
     flush(da, r >= 0, (uint32_t)cur.w[7] & 0x1fff0u);
     flush(db, r >= 0, ((uint32_t)cur.w[7] >> 13) & 0x1fff0u);
-    r = rn;
-    rn = rnn;
+    g = gn, gn = gnn;
+    r = rn, rn = rnn;
   }
   __syncthreads();
   // planes -> HBM, coalesced per channel plane
@@ -1079,7 +1090,7 @@ RLOD_API int rlod_roi_align_backward(const float *grad_out, const float *rois, c
   if (workspace_bytes < ws.bytes) return RLOD_ENOSPC;
   const int P = walk_pitch(W);
   const size_t smem = fwd_walk_smem(H, W, pool_mode) + (size_t)((H + 2 + 3) & ~3) * sizeof(int) +
-                      (size_t)kWalkWarps * 2 * sizeof(uint64_t);
+                      (size_t)kWalkWarps * 2 * sizeof(uint64_t) + 16;
   const bool fast = GH == 8 && GW == 8 && (C % 4) == 0 && pool_mode != RLOD_POOL_MAX &&
                     ((uintptr_t)grad_out % 16) == 0 && smem <= (size_t)kMaxSmemPerCta &&
                     (H + 2) * P <= 8192 && H + 2 <= 64 * 4 && R >= 2 * B;
