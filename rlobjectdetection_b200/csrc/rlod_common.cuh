@@ -106,6 +106,30 @@ __device__ __forceinline__ float4 lds128(uint32_t smem_addr) {
 // shared-memory row pitch (pixels) of the plane kernels: the smallest odd number >= W + 1
 __host__ __device__ __forceinline__ int walk_pitch(int W) { return (W + 1) | 1; }
 
+// HBM -> shared memory fill of the plane kernels: 4 channel planes (HW floats apart at src)
+// land interleaved per pixel, planes4[y * P + x] = (c0, c1, c2, c3), with 4-byte async copies
+// (LDGSTS): the interleave happens in flight, nothing is staged in registers and the whole read
+// of the CTA is outstanding at once.  A warp takes whole rows; its lanes are (pixel 0..7,
+// channel 0..3), so one instruction writes one contiguous 128-byte line of shared memory and
+// reads four 32-byte runs, and the addresses advance by constants (no div / wrap per element).
+// The caller commits nothing else to the async group and must cp.async.wait_group 0 +
+// __syncthreads() before reading.
+template <int THREADS>
+__device__ __forceinline__ void fill_planes4_async(float4 *planes4, const float *__restrict__ src, int H,
+                                                   int W, int P, int HW) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int px = lane >> 2, c = lane & 3;
+  const float *sc = src + (size_t)c * HW + px;
+  const uint32_t d0 = smem_u32(planes4) + 16u * (uint32_t)px + 4u * (uint32_t)c;
+  for (int y = warp; y < H; y += THREADS / 32) {
+    const float *s = sc + (size_t)y * W;
+    uint32_t d = d0 + 16u * (uint32_t)(y * P);
+    for (int x = px; x < W; x += 8, s += 8, d += 128u)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(s) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
 // streaming (evict-first) 128-bit store / load: outputs and one-shot inputs must not push
 // the feature planes out of L2
 __device__ __forceinline__ void st_stream4(float *p, float4 v) {

@@ -24,6 +24,10 @@
 //   cover everything the fast paths do not.
 #include "roi_lists.cuh"
 
+#ifndef RLOD_ABL
+#define RLOD_ABL 0  // ablation switch for profiling experiments only (tools/ablate.sh)
+#endif
+
 namespace rlod {
 
 // ----------------------------------------------------------------------------------------
@@ -536,7 +540,7 @@ template <int POOL>
 __global__ void __launch_bounds__(kWalkThreads, 2)
     k_align8_fwd_walk(const float *__restrict__ feat, const int *__restrict__ ext,
                       const int *__restrict__ order, const int *__restrict__ img_off, int C,
-                      int H, int W, int P, int n_chunks, float *__restrict__ out) {
+                      int H, int W, int P, int n_chunks, int tma_fill, float *__restrict__ out) {
   constexpr int OW = POOL == RLOD_POOL_NONE ? 8 : 7;
   constexpr int OHW = OW * OW;                            // 64 | 49
   constexpr int STG = 4 * OHW;                            // floats per (roi, 4 channels)
@@ -550,26 +554,73 @@ __global__ void __launch_bounds__(kWalkThreads, 2)
   const int r0 = img_off[b], r1 = img_off[b + 1];
   if (r0 >= r1) return;
   const float *src = feat + ((size_t)b * C + (size_t)chunk * 4) * HW;
-  // HBM -> shared memory with 4-byte async copies (LDGSTS): the channel interleave happens in
-  // flight, nothing is staged in registers and the CTA's whole 4-plane read is outstanding at
-  // once instead of a few loads per thread.  Consecutive lanes take the 4 channels of one
-  // pixel, then the next pixel: a warp writes one contiguous 128-byte line of shared memory
-  // and reads four full 32-byte sectors.
-  {
-    const int c = threadIdx.x & 3;
-    constexpr int kStep = kWalkThreads / 4;  // pixels per sweep of the CTA
-    int p = threadIdx.x >> 2;
-    int y = p / W, x = p - y * W;
-    const int dy = kStep / W, dx = kStep - dy * W;
-    const float *sc = src + (size_t)c * HW;
-    const uint32_t pb0 = smem_u32(planes4) + 4u * c;
-    for (; p < HW; p += kStep) {
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(pb0 + 16u * (uint32_t)(y * P + x)), "l"(sc + p)
-                   : "memory");
-      x += dx, y += dy;
-      if (x >= W) x -= W, ++y;
+  // ---- fill: the CTA's 4 planes, HBM -> shared memory, interleaved per pixel ---------------
+  // Fast way (tma_fill): four bulk async copies (TMA engine: a plane is one contiguous run, no
+  // per-sector request tracking in the LSU) land the planes PLANAR -- planes 1..3 in the output
+  // staging area, which is idle until the first roi, plane 0 at the tail of the plane region
+  // -- and the threads interleave them in place, batch by batch (the host checked that a batch
+  // never overwrites plane-0 pixels that are still unread).  A plane starts on an 8-byte
+  // boundary when H*W is even but not a multiple of 4: the copy starts 8 bytes early (skew).
+  // Fallback: 4-byte async copies (LDGSTS), interleaved in flight.
+  uint64_t *fill_bar = reinterpret_cast<uint64_t *>(stage + kWalkWarps * 2 * 4 * SLOT);
+#if RLOD_ABL != 1
+  if (tma_fill) {
+    const uint32_t plane_copy = (uint32_t)((HW * 4 + 8 + 15) & ~15);  // bytes per bulk copy (skew <= 8)
+    unsigned char *buf[4];
+    buf[0] = smem_raw + (size_t)(H + 2) * P * 16 - plane_copy;
+    for (int c = 1; c < 4; ++c) buf[c] = reinterpret_cast<unsigned char *>(stage) + (size_t)(c - 1) * plane_copy;
+    if (threadIdx.x == 0) {
+      mbar_init(fill_bar, 1);
+      uint32_t total = 0;
+      for (int c = 0; c < 4; ++c) {
+        const uint32_t skew = (uint32_t)((size_t)c * HW * 4) & 15u;
+        total += (skew + (uint32_t)HW * 4 + 15u) & ~15u;
+      }
+      mbar_expect_tx(fill_bar, total);
+      for (int c = 0; c < 4; ++c) {
+        const uint32_t skew = (uint32_t)((size_t)c * HW * 4) & 15u;
+        bulk_g2s(buf[c], reinterpret_cast<const char *>(src + (size_t)c * HW) - skew,
+                 (skew + (uint32_t)HW * 4 + 15u) & ~15u, fill_bar);
+      }
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
+    __syncthreads();  // barrier initialised before anyone polls it
+    mbar_wait(fill_bar, 0);
+    const float *pl[4];
+    for (int c = 0; c < 4; ++c)
+      pl[c] = reinterpret_cast<const float *>(buf[c] + ((uint32_t)((size_t)c * HW * 4) & 15u));
+    constexpr int kPer = 4;  // pixels per thread and batch
+    for (int base = 0; base < HW; base += kWalkThreads * kPer) {
+      float4 v[kPer];
+#pragma unroll
+      for (int q = 0; q < kPer; ++q) {
+        const int p = base + q * kWalkThreads + threadIdx.x;
+        if (p < HW) v[q] = make_float4(pl[0][p], pl[1][p], pl[2][p], pl[3][p]);
+      }
+      __syncthreads();  // plane-0 pixels of this batch are in registers before the region is written
+#pragma unroll
+      for (int q = 0; q < kPer; ++q) {
+        const int p = base + q * kWalkThreads + threadIdx.x;
+        if (p < HW) {
+          const int y = p / W, x = p - y * W;
+          planes4[y * P + x] = v[q];
+        }
+      }
+    }
+    __syncthreads();  // staging and the plane tail are free again
+  } else {
+    fill_planes4_async<kWalkThreads>(planes4, src, H, W, P, HW);
+  }
+#endif
+  // The CTA that will run on this SM slot one CTA-lifetime from now reads cold planes from HBM
+  // while its warps can do nothing else: pull those planes into L2 now (same bytes, earlier).
+  {
+    const unsigned nb2 = blockIdx.x + 2u * (unsigned)kSmCount;
+    if (nb2 < gridDim.x) {
+      const unsigned b2 = nb2 / (unsigned)n_chunks, c2 = nb2 - b2 * (unsigned)n_chunks;
+      const char *nx = reinterpret_cast<const char *>(feat + ((size_t)b2 * C + (size_t)c2 * 4) * HW);
+      for (int i = threadIdx.x * 128; i < 4 * HW * 4; i += kWalkThreads * 128)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + i));
+    }
   }
   {
     const int padw = P - W;  // zero columns W .. P-1 of the data rows, then the two zero rows
@@ -621,7 +672,7 @@ __global__ void __launch_bounds__(kWalkThreads, 2)
   {                                                                                         \
     const uint32_t pa = cbase + ((uint32_t)cur.w[T] & 0x1fff0u);                            \
     const uint32_t pa2 = cbase + (((uint32_t)cur.w[T] >> 13) & 0x1fff0u);                   \
-    walk_step(t0, t1, s[T], taps[(T) & 1], pa, pa + da, pa2, pa2 + da, cur.wa, cur.rt[T], cur.w[T]); \
+    walk_step(t0, t1, s[T], taps[(T) & 1], pa, pa + da, pa2, pa2 + da, cur.wa, cur.rt[T], RLOD_ABL == 3 ? (cur.w[T] & ~3) : cur.w[T]); \
   }
     // output of walk position T: NONE stores the sample itself; AVG / MAX pool 2x2 stride 1,
     // along the walk axis in registers and along the lane axis with one shuffle per value
@@ -657,8 +708,10 @@ __global__ void __launch_bounds__(kWalkThreads, 2)
     fence_async_smem();
     __syncwarp();
     if (k == 0) {
+#if RLOD_ABL != 2
       if (r >= 0)
         bulk_s2g_nocommit(out + ((size_t)r * C + (size_t)chunk * 4) * OHW, sbuf, (uint32_t)(STG * sizeof(float)));
+#endif
       bulk_commit();
     }
     cur = nxt;
@@ -996,6 +1049,27 @@ static size_t fwd_walk_smem(int H, int W, int pool_mode) {
   return (size_t)16 * (size_t)(H + 2) * walk_pitch(W) + (size_t)kWalkWarps * 2 * 4 * slot * 4;
 }
 
+// Can the forward kernel fill its planes with bulk copies + in-place interleave?  Needs 8-byte
+// aligned planes (H*W even), three planar planes inside the staging area, and no batch of the
+// interleave writing over plane-0 pixels that are still unread (see the kernel).
+static bool fwd_tma_fill_ok(const float *feat, int H, int W, int pool_mode) {
+  const int HW = H * W, P = walk_pitch(W);
+  if ((HW & 1) || ((uintptr_t)feat % 16) != 0) return false;
+  const size_t plane_copy = ((size_t)HW * 4 + 8 + 15) & ~(size_t)15;
+  const int slot = pool_mode == RLOD_POOL_NONE ? 264 : 200;
+  if (3 * plane_copy > (size_t)kWalkWarps * 2 * 4 * slot * 4) return false;
+  const size_t region = (size_t)16 * (H + 2) * P;
+  if (plane_copy > region) return false;
+  const size_t tail = region - plane_copy;  // plane 0 (copy start; its pixel q is at >= tail + 4q)
+  const int batch = kWalkThreads * 4;
+  for (int base = 0; base < HW; base += batch) {
+    const int last = (base + batch < HW ? base + batch : HW) - 1;  // last pixel written by this batch
+    const size_t wr_end = (size_t)16 * ((size_t)(last / W) * P + last % W + 1);
+    if (wr_end > tail + (size_t)4 * (last + 1)) return false;  // would hit an unread plane-0 pixel
+  }
+  return true;
+}
+
 }  // namespace rlod
 
 using namespace rlod;
@@ -1021,10 +1095,11 @@ RLOD_API int rlod_roi_align_forward(const float *feat, const float *rois, int B,
   if (workspace_bytes < ws.bytes) return RLOD_ENOSPC;
   cudaStream_t st = (cudaStream_t)stream;
 
-  const size_t smem = fwd_walk_smem(H, W, pool_mode);
+  const size_t smem = fwd_walk_smem(H, W, pool_mode) + 16;  // + the fill mbarrier
   const bool fast = GH == 8 && GW == 8 && (C % 4) == 0 && smem <= (size_t)kMaxSmemPerCta &&
                     (H + 2) * walk_pitch(W) <= 8192 && ((uintptr_t)out % 16) == 0 && R >= 2 * B;
   if (fast) {
+    const int tma_fill = fwd_tma_fill_ok(feat, H, W, pool_mode) ? 1 : 0;
     const int n_chunks = C / 4;
     const unsigned grid = (unsigned)(B * n_chunks);
     const int P = walk_pitch(W);
@@ -1040,7 +1115,7 @@ RLOD_API int rlod_roi_align_forward(const float *feat, const float *rois, int B,
     ProfScope _ps(RLOD_KERNEL_ALIGN_FWD, st);                                                  \
     k_align8_fwd_walk<POOL><<<grid, kWalkThreads, smem, st>>>(feat, ws.ext, ws.order,          \
                                                               ws.img_off, C, H, W, P,          \
-                                                              n_chunks, out);                  \
+                                                              n_chunks, tma_fill, out);        \
   } while (0)
     if (pool_mode == RLOD_POOL_NONE)
       RLOD_LAUNCH_FWD(RLOD_POOL_NONE);

@@ -82,22 +82,7 @@ __global__ void __launch_bounds__(kPoolThreads, 2)
   const int r0 = img_off[b], r1 = img_off[b + 1];
   if (r0 >= r1) return;
   const float *src = feat + ((size_t)b * C + (size_t)chunk * 4) * HW;
-  {
-    const int c = threadIdx.x & 3;
-    constexpr int kStep = kPoolThreads / 4;
-    int p = threadIdx.x >> 2;
-    int y = p / W, x = p - y * W;
-    const int dy = kStep / W, dx = kStep - dy * W;
-    const float *sc = src + (size_t)c * HW;
-    const uint32_t pb0 = smem_u32(planes4) + 4u * c;
-    for (; p < HW; p += kStep) {
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(pb0 + 16u * (uint32_t)(y * P + x)), "l"(sc + p)
-                   : "memory");
-      x += dx, y += dy;
-      if (x >= W) x -= W, ++y;
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  }
+  fill_planes4_async<kPoolThreads>(planes4, src, H, W, P, HW);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k = lane & 7, slot = lane >> 3;
   const uint32_t pbase = smem_u32(planes4);
