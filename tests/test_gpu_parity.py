@@ -161,6 +161,8 @@ def _align_case(seed, B, C, H, W, n_per, stride=16.0, shuffle=False):
     dict(B=2, C=6, H=19, W=23, n_per=12, p=7),        # C % 4 != 0 -> generic
     dict(B=2, C=8, H=16, W=16, n_per=9, p=3),         # other pooled size -> generic
     dict(B=2, C=4, H=12, W=40, n_per=10, p=7, shuffle=True),  # rois not grouped by image
+    dict(B=2, C=8, H=21, W=31, n_per=12, p=7),        # H*W odd: planes are 4-byte aligned only -> LDGSTS fill
+    dict(B=1, C=4, H=96, W=90, n_per=16, p=7),        # (H+2)*pitch > 8192 pixels -> generic kernels
 ])
 def test_roi_align_forward(orc, case, mode):
     p = case["p"]
@@ -183,6 +185,23 @@ def test_roi_align_forward_bad_batch_index(orc):
     close(out[good], ref)
 
 
+def test_roi_align_images_without_rois_and_empty_input(orc):
+    # images 0 and 2 of 3 have no roi at all (their CTAs return at once); R == 0 is a no-op
+    feat, rois = _align_case(6, 3, 8, 20, 30, 10)
+    only1 = rois[rois[:, 0] == 1].contiguous()
+    ref = orc.roi_align(feat.numpy(), only1.numpy(), 7, 7, 1 / 16.0, pool_mode=orc.POOL_AVG)
+    out = be.roi_align_forward(cu(feat), cu(only1), 7, 7, 1 / 16.0, be.POOL_AVG)
+    close(out.cpu().numpy(), ref)
+    g = torch.Generator().manual_seed(9)
+    gout = torch.randn(only1.size(0), 8, 7, 7, generator=g)
+    gref = orc.roi_align_bwd(gout.numpy(), feat.numpy(), only1.numpy(), 7, 7, 1 / 16.0, pool_mode=orc.POOL_AVG)
+    gin = be.roi_align_backward(cu(gout), cu(only1), None, tuple(feat.shape), 7, 7, 1 / 16.0, be.POOL_AVG)
+    close(gin.cpu().numpy(), gref)
+    assert (gin[0] == 0).all() and (gin[2] == 0).all()
+    empty = be.roi_align_forward(cu(feat), cu(torch.zeros(0, 5)), 7, 7, 1 / 16.0, be.POOL_AVG)
+    assert tuple(empty.shape) == (0, 8, 7, 7)
+
+
 def test_roi_align_c2_full_size(orc):
     # config 2: Res-101 C4 at 600x1000 -> (4,1024,38,63), 4 x 256 rois, 7x7
     feat, rois = _align_case(1, 4, 1024, 38, 63, 256)
@@ -198,6 +217,7 @@ def test_roi_align_c2_full_size(orc):
     dict(B=2, C=6, H=19, W=23, n_per=12, p=7),
     dict(B=2, C=8, H=16, W=16, n_per=9, p=3),
     dict(B=2, C=4, H=50, W=75, n_per=30, p=7, shuffle=True),
+    dict(B=2, C=8, H=21, W=31, n_per=12, p=7),
 ])
 def test_roi_align_backward(orc, case, mode):
     p = case["p"]
