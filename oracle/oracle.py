@@ -369,6 +369,30 @@ def move_from_act(bboxes, preds, targets, act, maxk):
 # ----------------------------------------------------------------------------------------
 # the compiled reference itself (oracle/_ref, built from /root/reference in place)
 # ----------------------------------------------------------------------------------------
+def rl_labels(dets, det_cat, ndet, gt, gt_cat, crowd, ngt, act, iou_thres=0.0, pos_wratio=1.0, neg_wratio=1.0):
+    """Label tensor (B,N,A,3) = (act_id, label, weight) of a collated RL batch:
+    lib/datasets/RL_coco_dataset.py:107-137 per box (category-specific gt, none -> [[0,0,0,0]],
+    bbIou fp64) + the zero padding of lib/datasets/RL_coco_loader.py:66-72."""
+    dets, gt = np.asarray(dets, np.float64), np.asarray(gt, np.float64)
+    B, N = dets.shape[:2]
+    A = act.shape[0]
+    out = np.zeros((B, N, A, 3), np.float32)
+    for b in range(B):
+        for n in range(int(ndet[b])):
+            bbox = dets[b, n, :4]
+            w, h = bbox[2], bbox[3]
+            sel = [g for g in range(int(ngt[b])) if int(gt_cat[b, g]) == int(det_cat[b, n])]
+            gtb = gt[b, sel] if sel else np.zeros((1, 4))
+            cr = np.asarray([crowd[b, g] for g in sel], np.uint8) if sel else np.zeros(1, np.uint8)
+            o0 = bbiou(bbox[None], gtb, cr).max()
+            for a in range(A):
+                nb = bbox + act[a].astype(np.float64) * np.array([w, h, w, h])
+                d = bbiou(nb[None], gtb, cr).max() - o0
+                pos = d > iou_thres
+                out[b, n, a] = (a, 1.0 if pos else -1.0, np.exp(abs(d)) * (pos_wratio if pos else neg_wratio))
+    return out
+
+
 def detect_postprocess(rois, cls_prob, bbox_pred, im_info, thresh=0.0, nms_thresh=0.3, max_per_image=100,
                        stds=None, means=None, class_agnostic=False):
     """Test-time post-processing, RCNN_bases/test_net.py:244-307, for a batch (the reference

@@ -116,6 +116,62 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// k_rl_labels: the label tensor of one collated RL batch, straight in the layout
+// COCODataLoader._collate_fn hands to the model (lib/datasets/RL_coco_loader.py:19-76):
+// labels (B, N, A, 3) = (act_id, label, weight), zero rows for padded boxes.  Per box only the
+// ground truth of ITS category counts (RL_coco_dataset.py:108-117: gt_boxes[img_id, cat_id]);
+// none -> the single all-zero gt.  IoU = pycocotools bbIou, fp64 (xywh boxes).
+__global__ void __launch_bounds__(256)
+    k_rl_labels(const float *__restrict__ dets, int det_stride, const int *__restrict__ det_cat,
+                const int *__restrict__ ndet, const float *__restrict__ gt, const int *__restrict__ gt_cat,
+                const unsigned char *__restrict__ crowd, const int *__restrict__ ngt,
+                const float *__restrict__ act, int B, int N, int A, int G, float iou_thres,
+                float pos_wratio, float neg_wratio, float *__restrict__ labels) {
+  const long long total = (long long)B * N * A;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int a = (int)(idx % A);
+    const long long bn = idx / A;
+    const int b = (int)(bn / N), n = (int)(bn - (long long)b * N);
+    float *o = labels + idx * 3;
+    if (ndet && n >= __ldg(ndet + b)) {
+      o[0] = 0.f, o[1] = 0.f, o[2] = 0.f;  // collate pads with zeros (:70-72)
+      continue;
+    }
+    const float *bx = dets + bn * det_stride;
+    const int cat = det_cat ? __ldg(det_cat + bn) : 0;
+    int ng = ngt ? __ldg(ngt + b) : G;
+    if (ng > G) ng = G;
+    const double dt[4] = {(double)__ldg(bx), (double)__ldg(bx + 1), (double)__ldg(bx + 2), (double)__ldg(bx + 3)};
+    const double w = dt[2], h = dt[3];
+    const double nb[4] = {__dadd_rn(dt[0], __dmul_rn((double)__ldg(act + a * 4), w)),
+                          __dadd_rn(dt[1], __dmul_rn((double)__ldg(act + a * 4 + 1), h)),
+                          __dadd_rn(dt[2], __dmul_rn((double)__ldg(act + a * 4 + 2), w)),
+                          __dadd_rn(dt[3], __dmul_rn((double)__ldg(act + a * 4 + 3), h))};
+    double bo = -INFINITY, bn_ = -INFINITY;
+    bool any = false;
+    for (int g = 0; g < ng; ++g) {
+      if (gt_cat && __ldg(gt_cat + (size_t)b * G + g) != cat) continue;
+      const float *gp = gt + ((size_t)b * G + g) * 4;
+      const double Gb[4] = {(double)__ldg(gp), (double)__ldg(gp + 1), (double)__ldg(gp + 2), (double)__ldg(gp + 3)};
+      const bool cr = crowd ? (crowd[(size_t)b * G + g] != 0) : false;
+      const double o0 = bbiou_f64(dt, Gb, cr), o1 = bbiou_f64(nb, Gb, cr);
+      if (o0 > bo) bo = o0;
+      if (o1 > bn_) bn_ = o1;
+      any = true;
+    }
+    if (!any) {
+      const double z[4] = {0., 0., 0., 0.};
+      bo = bbiou_f64(dt, z, false), bn_ = bbiou_f64(nb, z, false);
+    }
+    const double r = __dsub_rn(bn_, bo);
+    const bool pos = r > (double)iou_thres;
+    o[0] = (float)a;
+    o[1] = pos ? 1.f : -1.f;
+    o[2] = (float)(exp(fabs(r)) * (double)(pos ? pos_wratio : neg_wratio));
+  }
+}
+
 // float -> uint32 whose ascending order is the float's descending order
 __device__ __forceinline__ uint32_t desc_key32(float f) {
   uint32_t u = __float_as_uint(f);
@@ -235,5 +291,23 @@ RLOD_API int rlod_move_from_act(float *boxes, int box_stride, int corners, const
   k_move_from_act<<<B, kMoveThreads, (size_t)np2 * sizeof(unsigned long long),
                     (cudaStream_t)stream>>>(boxes, box_stride, corners, preds, targets, act, N, A,
                                             maxk, np2, correct);
+  return launch_status();
+}
+
+RLOD_API int rlod_rl_labels(const float *dets, int det_stride, const int *det_cat, const int *ndet,
+                            const float *gt, const int *gt_cat, const unsigned char *crowd,
+                            const int *ngt, const float *act, int B, int N, int A, int G,
+                            float iou_thres, float pos_wratio, float neg_wratio, float *labels,
+                            rlod_stream_t stream) {
+  if (B < 0 || N < 0 || A < 0 || G < 0 || det_stride < 4) return RLOD_EINVAL;
+  if (B == 0 || N == 0 || A == 0) return RLOD_OK;
+  if (!dets || !act || !labels || (G > 0 && !gt)) return RLOD_EINVAL;
+  const long long total = (long long)B * N * A;
+  const long long blocks = (total + 255) / 256;
+  const unsigned grid = (unsigned)(blocks < (1LL << 20) ? blocks : (1LL << 20));
+  RLOD_LAUNCH(RLOD_KERNEL_REWARD, (cudaStream_t)stream,
+              k_rl_labels<<<grid, 256, 0, (cudaStream_t)stream>>>(dets, det_stride, det_cat, ndet, gt, gt_cat, crowd,
+                                                                 ngt, act, B, N, A, G, iou_thres, pos_wratio,
+                                                                 neg_wratio, labels));
   return launch_status();
 }

@@ -54,6 +54,7 @@ SIGNATURES = {
     "rlod_action_reward": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _F, _P, _P, _P,
                                 _P]),
     "rlod_move_from_act": (_I, [_P, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "rlod_rl_labels": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _F, _P, _P]),
     "rlod_detect_postprocess": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _F, _F, _I, _P, _P, _P]),
 }
 
@@ -362,3 +363,22 @@ def detect_postprocess(rois, cls_prob, bbox_pred, im_info, thresh=0.0, nms_thres
                                             int(max_per_image), ptr(dets), ptr(counts), stream_of(rois)),
               "rlod_detect_postprocess")
     return dets, counts
+
+
+def rl_labels(dets, gt, act, det_cat=None, ndet=None, gt_cat=None, crowd=None, ngt=None, iou_thres=0.0,
+              pos_wratio=1.0, neg_wratio=1.0):
+    """rlod_rl_labels: labels (B,N,A,3) = (act_id, label, weight) of a collated RL batch.
+    dets (B,N,>=4) xywh rows, gt (B,G,4) xywh; categories int32; crowd uint8."""
+    require_cuda("rl_labels", dets, gt, act)
+    dets, gt, act = f32c(dets), f32c(gt), f32c(act)
+    B, N, S = dets.shape
+    G, A = gt.size(1), act.size(0)
+    i32 = lambda t: None if t is None else t.to(device=dets.device, dtype=torch.int32).contiguous()  # noqa: E731
+    det_cat, ndet, gt_cat, ngt = i32(det_cat), i32(ndet), i32(gt_cat), i32(ngt)
+    crowd = None if crowd is None else crowd.to(device=dets.device, dtype=torch.uint8).contiguous()
+    labels = torch.empty(B, N, A, 3, dtype=torch.float32, device=dets.device)
+    with torch.cuda.device(dets.device):
+        check(lib().rlod_rl_labels(ptr(dets), S, ptr(det_cat), ptr(ndet), ptr(gt), ptr(gt_cat), ptr(crowd), ptr(ngt),
+                                   ptr(act), B, N, A, G, float(iou_thres), float(pos_wratio), float(neg_wratio),
+                                   ptr(labels), stream_of(dets)), "rlod_rl_labels")
+    return labels

@@ -564,3 +564,65 @@ def test_detect_postprocess_c5_size(orc):
             np.testing.assert_allclose(ab[j][b][:, :4], ref[k][j][:, :4], rtol=3e-6, atol=2e-4)
     c = counts.cpu().numpy()
     assert (c[:, 0] == 0).all() and (c.sum(1) >= 100).all()  # the cap keeps ties with >=
+
+
+# ------------------------------------------------------------------------------------------
+# RL batch generation + eval glue (f2)
+# ------------------------------------------------------------------------------------------
+def test_rl_generate_labels_vs_reference_collate(orc):
+    import os
+    from rlobjectdetection_b200.model.Reinforcement.action import Action
+    from rlobjectdetection_b200.rl_step import generate_labels
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_rl.npz"))
+    action = Action([0.5, 0.25])
+    bboxes, labels = generate_labels(action, cu(g["dets"]), cu(g["det_score"]), cu(g["det_cat"]), cu(g["det_img"]),
+                                     cu(g["ndet"]), cu(g["gt"]), cu(g["gt_cat"]), iscrowd=cu(g["crowd"]), ngt=cu(g["ngt"]),
+                                     pos_wratio=float(g["wratio"][0]), neg_wratio=float(g["wratio"][1]))
+    lab, ref = labels.cpu().numpy(), g["padded_labels"]
+    assert np.array_equal(lab[..., :2], ref[..., :2])                      # act ids and +-1 labels bit-exact
+    np.testing.assert_allclose(lab[..., 2], ref[..., 2], rtol=2e-7)        # fp64 weight rounded to fp32
+    np.testing.assert_allclose(bboxes.cpu().numpy(), g["padded_bboxes"], rtol=0, atol=0)
+
+
+def test_rl_labels_c3_size(orc):
+    # config 3: 8 images x 300 boxes x 16 actions x 20 gt, 5 categories
+    from rlobjectdetection_b200.model.Reinforcement.action import Action
+    B, N, G = 8, 300, 20
+    g = torch.Generator().manual_seed(31)
+    dets = syn.to_xywh(torch.stack([syn.random_boxes(g, N, 800, 1200) for _ in range(B)], 0))
+    gt, crowd = syn.gt_boxes(32, B, G, 800, 1200)
+    gt = syn.to_xywh(gt)
+    det_cat = torch.randint(0, 5, (B, N), generator=g, dtype=torch.int32)
+    gt_cat = torch.randint(0, 5, (B, G), generator=g, dtype=torch.int32)
+    ndet = torch.tensor([300, 299, 0, 150, 300, 1, 300, 300], dtype=torch.int32)
+    ngt = torch.tensor([20, 0, 5, 20, 20, 20, 3, 20], dtype=torch.int32)
+    act = Action([0.5, 0.25])
+    lab = be.rl_labels(cu(dets), cu(gt), act.table(DEV), det_cat=cu(det_cat), ndet=cu(ndet), gt_cat=cu(gt_cat),
+                       crowd=cu(crowd), ngt=cu(ngt), pos_wratio=1.5, neg_wratio=0.5).cpu().numpy()
+    sub = [0, 1, 2, 5]
+    ref = orc.rl_labels(dets[sub].numpy(), det_cat[sub].numpy(), ndet[sub].numpy(), gt[sub].numpy(), gt_cat[sub].numpy(),
+                        crowd[sub].numpy(), ngt[sub].numpy(), act.actDeltas, 0.0, 1.5, 0.5)
+    assert np.array_equal(lab[sub][..., :2], ref[..., :2])
+    np.testing.assert_allclose(lab[sub][..., 2], ref[..., 2], rtol=2e-7)
+
+
+def test_rl_eval_step_matches_reference_sequence(orc, golden):
+    # trainval_net.py:202-221 = xyxy -> xywh, Action.move_from_act(maxk=1), / scale; move_from_act itself
+    # is pinned by the golden vectors of the reference's Action (test_move_from_act_vs_golden)
+    from rlobjectdetection_b200.model.Reinforcement.action import Action
+    from rlobjectdetection_b200.rl_step import eval_step
+    act = Action([0.5, 0.25])
+    xywh = golden["move_in_boxes"]
+    b, n, _ = xywh.shape
+    rows = np.zeros((b, n, 8), np.float32)
+    rows[:, :, 0] = np.arange(b)[:, None]
+    rows[:, :, 1:3] = xywh[:, :, :2]
+    rows[:, :, 3:5] = xywh[:, :, :2] + xywh[:, :, 2:]
+    scale = np.array([1.0, 1.6, 0.5], np.float32)
+    out, moved = eval_step(act, cu(rows), cu(golden["move_preds"]), cu(golden["move_targets"]), cu(scale), maxk=1)
+    ref_in = rows[:, :, 1:5].copy()
+    ref_in[:, :, 2] -= ref_in[:, :, 0]
+    ref_in[:, :, 3] -= ref_in[:, :, 1]
+    ref, prec = orc.move_from_act(ref_in, golden["move_preds"], golden["move_targets"], act.actDeltas, 1)
+    np.testing.assert_allclose(out.cpu().numpy()[:, :, 1:5], ref / scale[:, None, None], rtol=1e-6, atol=1e-5)
+    assert int(moved.item()) == int(round(prec * b * 1 / 100.0))

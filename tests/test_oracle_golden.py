@@ -98,3 +98,14 @@ def test_detect_postprocess(orc, tag):
     got = np.concatenate(ab, 0)
     np.testing.assert_allclose(got, g[f"{tag}_dets"], rtol=1e-6, atol=1e-4)
     assert np.array_equal(got[:, 4], g[f"{tag}_dets"][:, 4])  # scores pass through untouched
+
+
+def test_rl_labels_vs_reference_collate(orc):
+    """One collated RL batch from the reference's own _collate_fn + label loop
+    (tests/golden/make_golden_rl.py) vs the oracle restatement."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_rl.npz"))
+    lab = orc.rl_labels(g["dets"], g["det_cat"], g["ndet"], g["gt"], g["gt_cat"], g["crowd"], g["ngt"], g["act"],
+                        iou_thres=0.0, pos_wratio=float(g["wratio"][0]), neg_wratio=float(g["wratio"][1]))
+    assert np.array_equal(lab[..., :2], g["padded_labels"][..., :2])
+    np.testing.assert_allclose(lab[..., 2], g["padded_labels"][..., 2], rtol=2e-7)
