@@ -471,7 +471,37 @@ def run_ops(args):
     add("RoIPool fwd C2", pb, ours, lg)
     ours = time_us(lambda: be.roi_pool_backward(gout, am, rois, (B, C, H, W), 7, 7, 1 / 16.0))
     add("RoIPool bwd C2", pb, ours, lgb, "legacy = O(B*C*H*W*R) gather")
-    del feat, rois, gout, out, am
+    # RoICrop (POOLING_MODE 'crop'): 14x14 sampling grid + 2x2 max pool, C2 shape
+    gxy = be.affine_grid(rois, (H, W), 14, True)
+    gyx = torch.stack([gxy[..., 1], gxy[..., 0]], 3).contiguous()
+    cb = 4 * (B * C * H * W + R * 14 * 14 * 2 + R * C * 14 * 14)
+    ours = time_us(lambda: be.roi_crop_forward(feat, gyx))
+    gout14 = torch.randn(R, C, 14, 14, device=dev)
+    ours_b = time_us(lambda: be.roi_crop_backward(gout14, gyx, (B, C, H, W)))
+    lgf = lgb2 = None
+    if leg is not None and hasattr(leg, "BilinearSamplerBHWD_updateOutput_cuda_kernel"):
+        I = ctypes.c_int
+        lf = leg.BilinearSamplerBHWD_updateOutput_cuda_kernel
+        lf.restype, lf.argtypes = I, [I] * 8 + [P, I, I, I, I, P, I, I, I, I, P, I, I, I, I, P]
+        lb = leg.BilinearSamplerBHWD_updateGradInput_cuda_kernel
+        lb.restype, lb.argtypes = I, [I] * 8 + [P, I, I, I, I, P, I, I, I, I, P, I, I, I, I, P, I, I, I, I, P, I, I, I, I, P]
+        o14 = torch.empty(R, C, 14, 14, device=dev)
+        gs_ = (gyx.stride(0), gyx.stride(3), gyx.stride(1), gyx.stride(2))
+
+        def legacy_crop():
+            o14.zero_()  # functions/roi_crop.py:11
+            lf(C, 14, 14, R, C, H, W, B, dp(feat), *feat.stride(), dp(gyx), *gs_, dp(o14), *o14.stride(), st())
+        lgf = time_us(legacy_crop, iters=8, warm=2)
+        gfe, ggr = torch.empty(B, C, H, W, device=dev), torch.zeros_like(gyx)
+
+        def legacy_crop_bwd():
+            gfe.zero_()
+            lb(C, 14, 14, R, C, H, W, B, dp(feat), *feat.stride(), dp(gyx), *gs_, dp(gfe), *gfe.stride(), dp(ggr), *gs_,
+               dp(gout14), *gout14.stride(), st())
+        lgb2 = time_us(legacy_crop_bwd, iters=4, warm=1)
+    add("RoICrop 14x14 fwd C2", cb, ours, lgf)
+    add("RoICrop 14x14 bwd C2", cb, ours_b, lgb2)
+    del feat, rois, gout, out, am, gout14, gxy, gyx
     align_case("C4", 24, 1024, 50, 75, 300, 3)
 
     # NMS, C1 size: 12000 sorted boxes, thr 0.7

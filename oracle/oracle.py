@@ -369,6 +369,82 @@ def move_from_act(bboxes, preds, targets, act, maxk):
 # ----------------------------------------------------------------------------------------
 # the compiled reference itself (oracle/_ref, built from /root/reference in place)
 # ----------------------------------------------------------------------------------------
+def affine_grid(rois, H, W, g, align_corners=True):
+    """_affine_grid_gen, lib/model/utils/net_utils.py:143-165 (theta from roi / 16; base grid
+    linspace(-1, 1, g), or its torch >= 1.3 default (2j+1)/g - 1) -> (R, g, g, 2) = (x, y)."""
+    rois = _f32(rois)
+    f = np.float32
+    x1, y1, x2, y2 = (rois[:, i] / f(16.0) for i in (1, 2, 3, 4))
+    t00 = (x2 - x1) / f(W - 1)
+    t02 = (x1 + x2 - f(W) + f(1)) / f(W - 1)
+    t11 = (y2 - y1) / f(H - 1)
+    t12 = (y1 + y2 - f(H) + f(1)) / f(H - 1)
+    if align_corners:
+        base = np.linspace(-1.0, 1.0, g).astype(np.float32) if g > 1 else np.array([-1.0], np.float32)
+    else:
+        base = ((2 * np.arange(g) + 1).astype(np.float32) / f(g) - f(1)).astype(np.float32)
+    x = (base[None, None, :].astype(np.float64) * t00[:, None, None] + t02[:, None, None]).astype(np.float32)
+    y = (base[None, :, None].astype(np.float64) * t11[:, None, None] + t12[:, None, None]).astype(np.float32)
+    return np.stack([np.broadcast_to(x, (len(rois), g, g)), np.broadcast_to(y, (len(rois), g, g))], 3).astype(np.float32)
+
+
+def _crop_taps(grid_yx, H, W):
+    f = np.float32
+    yf, xf = grid_yx[..., 0].astype(np.float32), grid_yx[..., 1].astype(np.float32)
+    xc = ((xf + f(1)) * f(W - 1)) / f(2)      # getTopLeft, roi_crop_cuda_kernel.cu:11-23
+    yc = ((yf + f(1)) * f(H - 1)) / f(2)
+    x0, y0 = np.floor(xc), np.floor(yc)
+    xw, yw = f(1) - (xc - x0), f(1) - (yc - y0)
+    return x0.astype(np.int64), y0.astype(np.int64), xw.astype(np.float32), yw.astype(np.float32)
+
+
+def roi_crop(feat, grid_yx):
+    """BilinearSamplerBHWD forward, roi_crop_cuda_kernel.cu:47-118; image of roi r = r // (R // B)."""
+    feat, grid_yx = _f32(feat), _f32(grid_yx)
+    B, C, H, W = feat.shape
+    R, gh, gw, _ = grid_yx.shape
+    per = R // B
+    x0, y0, xw, yw = _crop_taps(grid_yx, H, W)
+    out = np.zeros((R, C, gh, gw), np.float32)
+    f = np.float32
+    for r in range(R):
+        b = r // per
+        if b >= B:
+            continue
+        acc = np.zeros((C, gh, gw), np.float32)
+        for dy, dx, wgt in ((0, 0, xw[r] * yw[r]), (0, 1, (f(1) - xw[r]) * yw[r]), (1, 0, xw[r] * (f(1) - yw[r])),
+                            (1, 1, (f(1) - xw[r]) * (f(1) - yw[r]))):
+            yy, xx = y0[r] + dy, x0[r] + dx
+            ok = (yy >= 0) & (yy <= H - 1) & (xx >= 0) & (xx <= W - 1)
+            v = feat[b][:, np.clip(yy, 0, H - 1), np.clip(xx, 0, W - 1)] * ok[None]
+            acc = (acc + wgt.astype(np.float32)[None] * v.astype(np.float32)).astype(np.float32)
+        out[r] = acc
+    return out
+
+
+def roi_crop_bwd(grad_out, grid_yx, feat_shape):
+    """:120-199, accumulated in fp64 (the reference's atomicAdd order is not fixed)."""
+    grad_out, grid_yx = _f32(grad_out), _f32(grid_yx)
+    B, C, H, W = feat_shape
+    R, gh, gw, _ = grid_yx.shape
+    per = R // B
+    x0, y0, xw, yw = _crop_taps(grid_yx, H, W)
+    gin = np.zeros((B, C, H, W), np.float64)
+    f = np.float32
+    for r in range(R):
+        b = r // per
+        if b >= B:
+            continue
+        for dy, dx, wgt in ((0, 0, xw[r] * yw[r]), (0, 1, (f(1) - xw[r]) * yw[r]), (1, 0, xw[r] * (f(1) - yw[r])),
+                            (1, 1, (f(1) - xw[r]) * (f(1) - yw[r]))):
+            yy, xx = y0[r] + dy, x0[r] + dx
+            ok = (yy >= 0) & (yy <= H - 1) & (xx >= 0) & (xx <= W - 1)
+            contrib = (wgt.astype(np.float32)[None] * grad_out[r]).astype(np.float32)
+            for c in range(C):
+                np.add.at(gin[b, c], (np.clip(yy, 0, H - 1)[ok], np.clip(xx, 0, W - 1)[ok]), contrib[c][ok])
+    return gin
+
+
 def rl_labels(dets, det_cat, ndet, gt, gt_cat, crowd, ngt, act, iou_thres=0.0, pos_wratio=1.0, neg_wratio=1.0):
     """Label tensor (B,N,A,3) = (act_id, label, weight) of a collated RL batch:
     lib/datasets/RL_coco_dataset.py:107-137 per box (category-specific gt, none -> [[0,0,0,0]],

@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(CSRC, "librlod_sm100a.so")
 POOL_NONE, POOL_AVG, POOL_MAX = 0, 1, 2
 KERNELS = ["align_fwd", "align_bwd", "align_fwd_generic", "align_bwd_generic", "roi_plan", "nms_mask",
            "nms_scan", "nms_small", "proposal_sort", "pool_fwd", "pool_bwd", "boxes", "reward", "move",
-           "nms_lazy", "detect"]
+           "nms_lazy", "detect", "crop"]
 IOU_COCO, IOU_RCNN = 0, 1
 SORT_MAX = 16384  # rlod_proposal_forward: min(pre_nms_topN, H*W*A) limit
 
@@ -54,6 +54,9 @@ SIGNATURES = {
     "rlod_action_reward": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _F, _P, _P, _P,
                                 _P]),
     "rlod_move_from_act": (_I, [_P, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "rlod_affine_grid": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
+    "rlod_roi_crop_forward": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "rlod_roi_crop_backward": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "rlod_rl_labels": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _F, _P, _P]),
     "rlod_detect_postprocess": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _F, _F, _I, _P, _P, _P]),
 }
@@ -382,3 +385,43 @@ def rl_labels(dets, gt, act, det_cat=None, ndet=None, gt_cat=None, crowd=None, n
                                    ptr(act), B, N, A, G, float(iou_thres), float(pos_wratio), float(neg_wratio),
                                    ptr(labels), stream_of(dets)), "rlod_rl_labels")
     return labels
+
+
+def affine_grid(rois, input_size, grid_size, align_corners=True):
+    """rlod_affine_grid: rois (R,5) -> grid_xy (R,g,g,2)."""
+    require_cuda("_affine_grid_gen", rois)
+    rois = f32c(rois)
+    R = rois.size(0)
+    grid = torch.empty(R, grid_size, grid_size, 2, dtype=torch.float32, device=rois.device)
+    with torch.cuda.device(rois.device):
+        check(lib().rlod_affine_grid(ptr(rois), R, int(input_size[0]), int(input_size[1]), int(grid_size),
+                                     int(bool(align_corners)), ptr(grid), stream_of(rois)), "rlod_affine_grid")
+    return grid
+
+
+def roi_crop_forward(features, grid_yx):
+    require_cuda("_RoICrop", features, grid_yx)
+    features, grid_yx = f32c(features), f32c(grid_yx)
+    B, C, H, W = features.shape
+    R, gh, gw, two = grid_yx.shape
+    if two != 2:
+        raise ValueError("grid must be (R, gh, gw, 2) = (y, x)")
+    out = torch.empty(R, C, gh, gw, dtype=torch.float32, device=features.device)
+    with torch.cuda.device(features.device):
+        check(lib().rlod_roi_crop_forward(ptr(features), ptr(grid_yx), B, C, H, W, R, gh, gw, ptr(out),
+                                          stream_of(features)), "rlod_roi_crop_forward")
+    return out
+
+
+def roi_crop_backward(grad_out, grid_yx, feature_size, grad_in=None):
+    require_cuda("_RoICrop backward", grad_out, grid_yx)
+    grad_out, grid_yx = f32c(grad_out), f32c(grid_yx)
+    B, C, H, W = feature_size
+    R, gh, gw, _ = grid_yx.shape
+    accumulate = grad_in is not None
+    if grad_in is None:
+        grad_in = torch.empty(B, C, H, W, dtype=torch.float32, device=grad_out.device)
+    with torch.cuda.device(grad_out.device):
+        check(lib().rlod_roi_crop_backward(ptr(grad_out), ptr(grid_yx), B, C, H, W, R, gh, gw, int(accumulate),
+                                           ptr(grad_in), stream_of(grad_out)), "rlod_roi_crop_backward")
+    return grad_in

@@ -26,7 +26,8 @@ cfg = AttrDict(
                    BBOX_NORMALIZE_STDS=(0.1, 0.1, 0.2, 0.2)),
     TEST=AttrDict(NMS=0.3, RPN_NMS_THRESH=0.7, RPN_PRE_NMS_TOP_N=6000, RPN_POST_NMS_TOP_N=300,
                   RPN_MIN_SIZE=16, BBOX_REG=True),
-    POOLING_MODE="align",  # the reference defaults to 'crop' (:283); roi_crop is out of scope
+    POOLING_MODE="align",  # the reference defaults to 'crop' (:283); all three modes are provided
+    CROP_RESIZE_WITH_MAX_POOL=True,
     POOLING_SIZE=7,
     MAX_NUM_GT_BOXES=20,
     ANCHOR_SCALES=[8, 16, 32],

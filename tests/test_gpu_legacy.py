@@ -152,3 +152,50 @@ def test_roi_pool_vs_legacy(orc, legacy, shape):
                                bref, rtol=1e-5, atol=1e-5 * bscale)
     gin = be.roi_pool_backward(gout, am, r, (B, C, H, W), 7, 7, 1 / 16.0).cpu().numpy()
     np.testing.assert_allclose(gin, bref, rtol=1e-5, atol=1e-5 * bscale)
+
+
+def test_roi_crop_vs_legacy(orc, legacy):
+    """BilinearSamplerBHWD launchers of the reference (roi_crop_cuda_kernel.cu:205-330), compiled
+    unchanged: oracle and new kernels against them."""
+    if not hasattr(legacy, "BilinearSamplerBHWD_updateOutput_cuda_kernel"):
+        pytest.skip("libref_legacy.so was built without roi_crop")
+    I = ctypes.c_int
+    fwd = legacy.BilinearSamplerBHWD_updateOutput_cuda_kernel
+    fwd.restype = I
+    fwd.argtypes = [I] * 8 + [P, I, I, I, I, P, I, I, I, I, P, I, I, I, I, P]
+    bwd = legacy.BilinearSamplerBHWD_updateGradInput_cuda_kernel
+    bwd.restype = I
+    bwd.argtypes = [I] * 8 + [P, I, I, I, I, P, I, I, I, I, P, I, I, I, I, P, I, I, I, I, P, I, I, I, I, P]
+    B, C, H, W, n_per, gs = 2, 12, 20, 31, 11, 14
+    feat, rois = _case(41, B, C, H, W, n_per)
+    R = rois.size(0)
+    grid_xy = orc.affine_grid(rois.numpy(), H, W, gs, True)
+    grid_yx = torch.from_numpy(np.ascontiguousarray(np.stack([grid_xy[..., 1], grid_xy[..., 0]], 3)))
+    f, gy = feat.to(DEV), grid_yx.to(DEV)
+    out = torch.zeros(R, C, gs, gs, device=DEV)
+    torch.cuda.synchronize()
+    # argument order of roi_crop_cuda.c:21-44: sizes, then (data, stride0, stride1, stride2, stride3) of
+    # input / grids (stride 0, 3, 1, 2) / output
+    assert fwd(C, gs, gs, R, C, H, W, B, dp(f), *f.stride(), dp(gy), gy.stride(0), gy.stride(3), gy.stride(1), gy.stride(2),
+               dp(out), *out.stride(), None) == 1
+    torch.cuda.synchronize()
+    ref = out.cpu().numpy()
+    scale = np.abs(ref).max()
+    np.testing.assert_allclose(orc.roi_crop(feat.numpy(), grid_yx.numpy()), ref, rtol=1e-5, atol=1e-6 * scale)
+    ours = be.roi_crop_forward(f, gy).cpu().numpy()
+    np.testing.assert_allclose(ours, ref, rtol=1e-6, atol=1e-6 * scale)
+    gout = torch.randn(R, C, gs, gs, generator=torch.Generator().manual_seed(7)).to(DEV)
+    gin_ref = torch.zeros(B, C, H, W, device=DEV)
+    ggrid = torch.zeros_like(gy)
+    torch.cuda.synchronize()
+    assert bwd(C, gs, gs, R, C, H, W, B, dp(f), *f.stride(), dp(gy), gy.stride(0), gy.stride(3), gy.stride(1), gy.stride(2),
+               dp(gin_ref), *gin_ref.stride(), dp(ggrid), ggrid.stride(0), ggrid.stride(3), ggrid.stride(1), ggrid.stride(2),
+               dp(gout), *gout.stride(), None) == 1
+    torch.cuda.synchronize()
+    assert float(ggrid.abs().max()) == 0.0  # the reference stores no grid gradient
+    bref = gin_ref.cpu().numpy()
+    bscale = np.abs(bref).max()
+    gin = be.roi_crop_backward(gout, gy, (B, C, H, W)).cpu().numpy()
+    np.testing.assert_allclose(gin, bref, rtol=1e-5, atol=1e-5 * bscale)
+    np.testing.assert_allclose(orc.roi_crop_bwd(gout.cpu().numpy(), grid_yx.numpy(), (B, C, H, W)), bref, rtol=1e-5,
+                               atol=1e-5 * bscale)

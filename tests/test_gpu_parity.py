@@ -626,3 +626,51 @@ def test_rl_eval_step_matches_reference_sequence(orc, golden):
     ref, prec = orc.move_from_act(ref_in, golden["move_preds"], golden["move_targets"], act.actDeltas, 1)
     np.testing.assert_allclose(out.cpu().numpy()[:, :, 1:5], ref / scale[:, None, None], rtol=1e-6, atol=1e-5)
     assert int(moved.item()) == int(round(prec * b * 1 / 100.0))
+
+
+# ------------------------------------------------------------------------------------------
+# RoICrop, POOLING_MODE 'crop' (f4)
+# ------------------------------------------------------------------------------------------
+def _crop_case(seed, B, C, H, W, n_per, gs):
+    g = torch.Generator().manual_seed(seed)
+    feat = torch.randn(B, C, H, W, generator=g)
+    rois = syn.rois_for_batch(seed + 1, B, n_per, H * 16.0, W * 16.0)
+    return feat, rois
+
+
+@pytest.mark.parametrize("case", [dict(B=2, C=6, H=20, W=31, n_per=9, gs=14), dict(B=3, C=16, H=38, W=63, n_per=20, gs=14),
+                                  dict(B=1, C=3, H=5, W=6, n_per=8, gs=7)])
+def test_roi_crop_forward_backward(orc, case):
+    from rlobjectdetection_b200.model.utils.net_utils import _affine_grid_gen
+    feat, rois = _crop_case(8, case["B"], case["C"], case["H"], case["W"], case["n_per"], case["gs"])
+    H, W, gs = case["H"], case["W"], case["gs"]
+    for ac in (True, False):
+        grid = _affine_grid_gen(cu(rois), (H, W), gs, align_corners=ac).cpu().numpy()
+        np.testing.assert_allclose(grid, orc.affine_grid(rois.numpy(), H, W, gs, ac), rtol=0, atol=2e-6)
+    grid_xy = orc.affine_grid(rois.numpy(), H, W, gs, True)
+    grid_yx = np.ascontiguousarray(np.stack([grid_xy[..., 1], grid_xy[..., 0]], 3))
+    out = be.roi_crop_forward(cu(feat), cu(grid_yx)).cpu().numpy()
+    ref = orc.roi_crop(feat.numpy(), grid_yx)
+    close(out, ref, what="roi_crop fwd")
+    g = torch.Generator().manual_seed(5)
+    gout = torch.randn(*out.shape, generator=g)
+    gin = be.roi_crop_backward(cu(gout), cu(grid_yx), tuple(feat.shape)).cpu().numpy()
+    close(gin, orc.roi_crop_bwd(gout.numpy(), grid_yx, tuple(feat.shape)), what="roi_crop bwd")
+
+
+def test_roi_crop_module_and_crop_pool(orc):
+    from rlobjectdetection_b200.model.roi_crop.modules.roi_crop import _RoICrop
+    from rlobjectdetection_b200.model.utils.net_utils import crop_pool
+    feat, rois = _crop_case(9, 2, 8, 20, 31, 10, 14)
+    f = cu(feat).requires_grad_(True)
+    pooled = crop_pool(f, cu(rois), pooling_size=7, max_pool=True)
+    assert tuple(pooled.shape) == (20, 8, 7, 7)
+    grid_xy = orc.affine_grid(rois.numpy(), 20, 31, 14, True)
+    grid_yx = np.ascontiguousarray(np.stack([grid_xy[..., 1], grid_xy[..., 0]], 3))
+    ref14 = orc.roi_crop(feat.numpy(), grid_yx)
+    ref = ref14.reshape(20, 8, 7, 2, 7, 2).max(axis=(3, 5))
+    close(pooled.detach().cpu().numpy(), ref, what="crop_pool")
+    pooled.sum().backward()
+    assert f.grad is not None and torch.isfinite(f.grad).all()
+    out = _RoICrop()(cu(feat), cu(grid_yx))
+    close(out.cpu().numpy(), ref14)

@@ -109,3 +109,32 @@ def test_rl_labels_vs_reference_collate(orc):
                         iou_thres=0.0, pos_wratio=float(g["wratio"][0]), neg_wratio=float(g["wratio"][1]))
     assert np.array_equal(lab[..., :2], g["padded_labels"][..., :2])
     np.testing.assert_allclose(lab[..., 2], g["padded_labels"][..., 2], rtol=2e-7)
+
+
+def test_affine_grid_and_roi_crop_vs_torch(orc):
+    """POOLING_MODE 'crop': the grid is pinned to torch.nn.functional.affine_grid (the call the
+    reference makes, net_utils.py:163) in both of its historical behaviours, and the sampler to
+    grid_sample(align_corners=True, zeros padding), which is the arithmetic of
+    roi_crop_cuda_kernel.cu:11-23,87-113."""
+    import torch
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(3)
+    R, H, W, gs = 9, 20, 31, 14
+    x1, y1 = torch.rand(R, generator=g) * 300, torch.rand(R, generator=g) * 200
+    rois = torch.stack([torch.zeros(R), x1, y1, x1 + torch.rand(R, generator=g) * 250, y1 + torch.rand(R, generator=g) * 200], 1)
+    rois[0] = torch.tensor([0, -40.0, -30.0, 600.0, 400.0])  # partly outside the map
+    a, b, c, d = (rois[:, i:i + 1] / 16.0 for i in (1, 2, 3, 4))
+    zero = torch.zeros_like(a)
+    theta = torch.cat([(c - a) / (W - 1), zero, (a + c - W + 1) / (W - 1), zero, (d - b) / (H - 1),
+                       (b + d - H + 1) / (H - 1)], 1).view(-1, 2, 3)          # net_utils.py:155-161
+    for ac in (True, False):
+        ref = F.affine_grid(theta, torch.Size((R, 1, gs, gs)), align_corners=ac).numpy()
+        np.testing.assert_allclose(orc.affine_grid(rois.numpy(), H, W, gs, ac), ref, rtol=0, atol=2e-6)
+    grid_xy = torch.from_numpy(orc.affine_grid(rois.numpy(), H, W, gs, True))
+    feat = torch.randn(3, 5, H, W, generator=g)
+    grid_yx = torch.stack([grid_xy[..., 1], grid_xy[..., 0]], 3).contiguous()
+    out = orc.roi_crop(feat.numpy(), grid_yx.numpy())
+    per = R // 3
+    ref = torch.cat([F.grid_sample(feat[r // per:r // per + 1], grid_xy[r:r + 1], mode="bilinear", padding_mode="zeros",
+                                   align_corners=True) for r in range(R)], 0).numpy()
+    np.testing.assert_allclose(out, ref, rtol=1e-5, atol=1e-5)
