@@ -369,6 +369,130 @@ def move_from_act(bboxes, preds, targets, act, maxk):
 # ----------------------------------------------------------------------------------------
 # the compiled reference itself (oracle/_ref, built from /root/reference in place)
 # ----------------------------------------------------------------------------------------
+def bbox_transform_batch(ex, gt):
+    """bbox_transform.py:44-75 (3-d form), fp32 op by op."""
+    ex, gt = _f32(ex), _f32(gt)
+    f = np.float32
+    ew, eh = ex[..., 2] - ex[..., 0] + f(1), ex[..., 3] - ex[..., 1] + f(1)
+    ecx, ecy = ex[..., 0] + f(0.5) * ew, ex[..., 1] + f(0.5) * eh
+    gw, gh = gt[..., 2] - gt[..., 0] + f(1), gt[..., 3] - gt[..., 1] + f(1)
+    gcx, gcy = gt[..., 0] + f(0.5) * gw, gt[..., 1] + f(0.5) * gh
+    return np.stack([(gcx - ecx) / ew, (gcy - ecy) / eh, np.log(gw / ew), np.log(gh / eh)], -1).astype(np.float32)
+
+
+def proposal_target(all_rois, gt_boxes, fg_keys, bg_u, rois_per_image, fg_rois_per_image, fg_thresh=0.5, bg_hi=0.5,
+                    bg_lo=0.1, means=(0, 0, 0, 0), stds=(0.1, 0.1, 0.2, 0.2), inside_w=(1, 1, 1, 1)):
+    """_ProposalTargetLayer.forward, proposal_target_layer_cascade.py:33-213, with the RNG factored
+    out: permutation(n) := stable argsort of the fg candidates' keys, rand(k) := bg_u[:k]."""
+    all_rois, gt_boxes = _f32(all_rois), _f32(gt_boxes)
+    B, N, _ = all_rois.shape
+    app = np.zeros_like(gt_boxes)
+    app[:, :, 1:5] = gt_boxes[:, :, :4]
+    cand = np.concatenate([all_rois, app], 1)                                   # :41-44
+    ov = bbox_overlaps_batch(cand, gt_boxes)                                    # :132
+    R = rois_per_image
+    rois_b = np.zeros((B, R, 5), np.float32)
+    labels_b = np.zeros((B, R), np.float32)
+    gt_b = np.zeros((B, R, 5), np.float32)
+    status = np.zeros(B, np.int32)
+    for i in range(B):
+        mx, asg = ov[i].max(1), ov[i].argmax(1)
+        labels = gt_boxes[i, asg, 4]
+        fg = np.nonzero(mx >= np.float32(fg_thresh))[0]
+        bg = np.nonzero((mx < np.float32(bg_hi)) & (mx >= np.float32(bg_lo)))[0]
+        u = bg_u[i].astype(np.float64)
+        if fg.size > 0 and bg.size > 0:
+            k = min(fg_rois_per_image, fg.size)
+            perm = np.argsort(fg_keys[i][fg], kind="stable")
+            fg = fg[perm[:k]]
+            bg = bg[np.floor(u[:R - k] * bg.size).astype(np.int64)]
+            nfg = k
+        elif fg.size > 0:
+            fg = fg[np.floor(u[:R] * fg.size).astype(np.int64)]
+            bg, nfg = bg[:0], R
+        elif bg.size > 0:
+            bg = bg[np.floor(u[:R] * bg.size).astype(np.int64)]
+            fg, nfg = fg[:0], 0
+        else:
+            status[i] = 1
+            rois_b[i, :, 0] = i
+            continue
+        keep = np.concatenate([fg, bg])
+        labels_b[i] = labels[keep]
+        labels_b[i, nfg:] = 0
+        rois_b[i] = cand[i, keep]
+        rois_b[i, :, 0] = i
+        gt_b[i] = gt_boxes[i, asg[keep]]
+    tg = bbox_transform_batch(rois_b[:, :, 1:5], gt_b[:, :, :4])
+    if means is not None:
+        tg = ((tg - _f32(means)) / _f32(stds)).astype(np.float32)
+    pos = labels_b > 0
+    targets = np.where(pos[..., None], tg, np.float32(0)).astype(np.float32)
+    targets[status == 1] = 0
+    inside = np.where(pos[..., None], _f32(inside_w), np.float32(0)).astype(np.float32)
+    return rois_b, labels_b, targets, inside, (inside > 0).astype(np.float32), status
+
+
+def anchor_target(gt_boxes, im_info, anchors, keys, H, W, feat_stride=16, pos_ov=0.7, neg_ov=0.3, clobber=False,
+                  fg_fraction=0.5, batchsize=256, inside_w=1.0):
+    """_AnchorTargetLayer.forward, anchor_target_layer.py:48-192 (RPN_POSITIVE_WEIGHT < 0), RNG
+    factored out: permutation(n) := stable argsort of the members' keys."""
+    gt_boxes, anchors = _f32(gt_boxes), _f32(anchors)
+    B, A = gt_boxes.shape[0], anchors.shape[0]
+    sx, sy = np.meshgrid(np.arange(W) * feat_stride, np.arange(H) * feat_stride)
+    shifts = np.vstack((sx.ravel(), sy.ravel(), sx.ravel(), sy.ravel())).transpose().astype(np.float32)
+    allanc = (anchors[None] + shifts[:, None]).reshape(-1, 4)
+    total = allanc.shape[0]
+    keep = ((allanc[:, 0] >= 0) & (allanc[:, 1] >= 0) & (allanc[:, 2] < int(im_info[0][1])) &
+            (allanc[:, 3] < int(im_info[0][0])))
+    inds = np.nonzero(keep)[0]
+    anc = allanc[inds]
+    labels = np.full((B, inds.size), -1, np.float32)
+    ov = bbox_overlaps_batch(anc, gt_boxes)
+    mx, amx = ov.max(2), ov.argmax(2)
+    gmx = ov.max(1)
+    if not clobber:
+        labels[mx < np.float32(neg_ov)] = 0
+    gmx[gmx == 0] = np.float32(1e-5)
+    k = (ov == gmx[:, None, :]).sum(2)
+    labels[k > 0] = 1
+    labels[mx >= np.float32(pos_ov)] = 1
+    if clobber:
+        labels[mx < np.float32(neg_ov)] = 0
+    num_fg = int(fg_fraction * batchsize)
+    sum_fg, sum_bg = (labels == 1).sum(1), (labels == 0).sum(1)
+    for i in range(B):
+        kk = keys[i][inds]
+        if sum_fg[i] > num_fg:
+            fg = np.nonzero(labels[i] == 1)[0]
+            perm = np.argsort(kk[fg], kind="stable")
+            labels[i][fg[perm[:fg.size - num_fg]]] = -1
+        num_bg = batchsize - sum_fg[i]
+        if sum_bg[i] > num_bg:
+            bg = np.nonzero(labels[i] == 0)[0]
+            perm = np.argsort(kk[bg], kind="stable")
+            labels[i][bg[perm[:bg.size - num_bg]]] = -1
+    tg = bbox_transform_batch(np.broadcast_to(anc[None], (B,) + anc.shape), gt_boxes[np.arange(B)[:, None], amx][:, :, :4])
+    iw = np.zeros_like(labels)
+    iw[labels == 1] = np.float32(inside_w)
+    num_examples = (labels[B - 1] >= 0).sum()                                 # :158, i leaked from the loop
+    w = np.float32(1.0) / np.float32(num_examples)
+    ow = np.zeros_like(labels)
+    ow[labels == 1] = w
+    ow[labels == 0] = w
+
+    def unmap(d, fill):
+        shape = (B, total) + d.shape[2:]
+        out = np.full(shape, fill, np.float32)
+        out[:, inds] = d
+        return out
+    L = unmap(labels, -1).reshape(B, H, W, A).transpose(0, 3, 1, 2).reshape(B, 1, A * H, W)
+    T = unmap(tg, 0).reshape(B, H, W, A * 4).transpose(0, 3, 1, 2)
+    IW = np.repeat(unmap(iw, 0)[:, :, None], 4, 2).reshape(B, H, W, 4 * A).transpose(0, 3, 1, 2)
+    OW = np.repeat(unmap(ow, 0)[:, :, None], 4, 2).reshape(B, H, W, 4 * A).transpose(0, 3, 1, 2)
+    return np.ascontiguousarray(L), np.ascontiguousarray(T), np.ascontiguousarray(IW), np.ascontiguousarray(OW)
+
+
 def affine_grid(rois, H, W, g, align_corners=True):
     """_affine_grid_gen, lib/model/utils/net_utils.py:143-165 (theta from roi / 16; base grid
     linspace(-1, 1, g), or its torch >= 1.3 default (2j+1)/g - 1) -> (R, g, g, 2) = (x, y)."""

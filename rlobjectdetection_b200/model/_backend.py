@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(CSRC, "librlod_sm100a.so")
 POOL_NONE, POOL_AVG, POOL_MAX = 0, 1, 2
 KERNELS = ["align_fwd", "align_bwd", "align_fwd_generic", "align_bwd_generic", "roi_plan", "nms_mask",
            "nms_scan", "nms_small", "proposal_sort", "pool_fwd", "pool_bwd", "boxes", "reward", "move",
-           "nms_lazy", "detect", "crop"]
+           "nms_lazy", "detect", "crop", "targets"]
 IOU_COCO, IOU_RCNN = 0, 1
 SORT_MAX = 16384  # rlod_proposal_forward: min(pre_nms_topN, H*W*A) limit
 
@@ -54,6 +54,10 @@ SIGNATURES = {
     "rlod_action_reward": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _F, _P, _P, _P,
                                 _P]),
     "rlod_move_from_act": (_I, [_P, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "rlod_proposal_target": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "rlod_anchor_target_workspace_bytes": (_Z, [_I, _I, _I, _I]),
+    "rlod_anchor_target": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _F, _I, _F, _I, _F, _F, _P, _P, _P, _P, _P,
+                                _Z, _P]),
     "rlod_affine_grid": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
     "rlod_roi_crop_forward": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "rlod_roi_crop_backward": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
@@ -425,3 +429,52 @@ def roi_crop_backward(grad_out, grid_yx, feature_size, grad_in=None):
         check(lib().rlod_roi_crop_backward(ptr(grad_out), ptr(grid_yx), B, C, H, W, R, gh, gw, int(accumulate),
                                            ptr(grad_in), stream_of(grad_out)), "rlod_roi_crop_backward")
     return grad_in
+
+
+def _f4(v):
+    return None if v is None else (ctypes.c_float * 4)(*[float(x) for x in v])
+
+
+def proposal_target(rois, gt_boxes, fg_keys, bg_u, rois_per_image, fg_rois_per_image, fg_thresh, bg_hi, bg_lo,
+                    means=None, stds=None, inside_weights=(1.0, 1.0, 1.0, 1.0)):
+    """rlod_proposal_target -> rois (B,R,5), labels (B,R), targets / inside / outside (B,R,4), status (B)."""
+    require_cuda("_ProposalTargetLayer", rois, gt_boxes, fg_keys, bg_u)
+    rois, gt_boxes, fg_keys, bg_u = f32c(rois), f32c(gt_boxes), f32c(fg_keys), f32c(bg_u)
+    B, N, _ = rois.shape
+    G, R = gt_boxes.size(1), int(rois_per_image)
+    if tuple(fg_keys.shape) != (B, N + G) or bg_u.size(0) != B or bg_u.size(1) < R:
+        raise ValueError("fg_keys must be (B, N+G) and bg_u (B, >= rois_per_image)")
+    bg_u = bg_u[:, :R].contiguous()
+    dev = rois.device
+    ro = torch.empty(B, R, 5, device=dev)
+    lab = torch.empty(B, R, device=dev)
+    tg, iw, ow = (torch.empty(B, R, 4, device=dev) for _ in range(3))
+    status = torch.empty(B, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().rlod_proposal_target(ptr(rois), ptr(gt_boxes), ptr(fg_keys), ptr(bg_u), B, N, G, R,
+                                         int(fg_rois_per_image), float(fg_thresh), float(bg_hi), float(bg_lo),
+                                         _f4(means), _f4(stds), _f4(inside_weights), ptr(ro), ptr(lab), ptr(tg), ptr(iw),
+                                         ptr(ow), ptr(status), stream_of(rois)), "rlod_proposal_target")
+    return ro, lab, tg, iw, ow, status
+
+
+def anchor_target(gt_boxes, im_info, anchors, keys, A, H, W, feat_stride, positive_overlap, negative_overlap,
+                  clobber_positives, fg_fraction, batchsize, inside_weight, positive_weight):
+    """rlod_anchor_target -> labels (B,1,A*H,W), bbox_targets / inside / outside (B,4A,H,W)."""
+    require_cuda("_AnchorTargetLayer", gt_boxes, im_info, anchors, keys)
+    gt_boxes, im_info, anchors, keys = f32c(gt_boxes), f32c(im_info), f32c(anchors), f32c(keys)
+    B, G, _ = gt_boxes.shape
+    if tuple(keys.shape) != (B, H * W * A):
+        raise ValueError("keys must be (B, H*W*A)")
+    dev = gt_boxes.device
+    labels = torch.empty(B, 1, A * H, W, device=dev)
+    tg, iw, ow = (torch.empty(B, 4 * A, H, W, device=dev) for _ in range(3))
+    l = lib()
+    with torch.cuda.device(dev):
+        ws = workspace(l.rlod_anchor_target_workspace_bytes(B, A, H, W), dev)
+        check(l.rlod_anchor_target(ptr(gt_boxes), ptr(im_info), ptr(anchors), ptr(keys), B, G, A, H, W, int(feat_stride),
+                                   float(positive_overlap), float(negative_overlap), int(bool(clobber_positives)),
+                                   float(fg_fraction), int(batchsize), float(inside_weight), float(positive_weight),
+                                   ptr(labels), ptr(tg), ptr(iw), ptr(ow), ptr(ws), ws.numel(), stream_of(gt_boxes)),
+              "rlod_anchor_target")
+    return labels, tg, iw, ow

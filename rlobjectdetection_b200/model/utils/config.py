@@ -21,6 +21,11 @@ class AttrDict(dict):
 cfg = AttrDict(
     TRAIN=AttrDict(RPN_NMS_THRESH=0.7, RPN_PRE_NMS_TOP_N=12000, RPN_POST_NMS_TOP_N=2000,
                    RPN_MIN_SIZE=8,
+                   # target layers (config.py:76-87, 114, 131-153)
+                   BATCH_SIZE=128, FG_FRACTION=0.25, FG_THRESH=0.5, BG_THRESH_HI=0.5, BG_THRESH_LO=0.1,
+                   BBOX_INSIDE_WEIGHTS=(1.0, 1.0, 1.0, 1.0), RPN_POSITIVE_OVERLAP=0.7, RPN_NEGATIVE_OVERLAP=0.3,
+                   RPN_CLOBBER_POSITIVES=False, RPN_FG_FRACTION=0.5, RPN_BATCHSIZE=256,
+                   RPN_BBOX_INSIDE_WEIGHTS=(1.0, 1.0, 1.0, 1.0), RPN_POSITIVE_WEIGHT=-1.0,
                    # test_net.py:251-260 un-normalises bbox_pred with these (config.py:112-119)
                    BBOX_NORMALIZE_TARGETS_PRECOMPUTED=True, BBOX_NORMALIZE_MEANS=(0.0, 0.0, 0.0, 0.0),
                    BBOX_NORMALIZE_STDS=(0.1, 0.1, 0.2, 0.2)),

@@ -674,3 +674,94 @@ def test_roi_crop_module_and_crop_pool(orc):
     assert f.grad is not None and torch.isfinite(f.grad).all()
     out = _RoICrop()(cu(feat), cu(grid_yx))
     close(out.cpu().numpy(), ref14)
+
+
+# ------------------------------------------------------------------------------------------
+# training-target layers (f3)
+# ------------------------------------------------------------------------------------------
+def test_proposal_target_layer_vs_reference(orc):
+    import os
+    from rlobjectdetection_b200.model.rpn.proposal_target_layer_cascade import _ProposalTargetLayer
+    from rlobjectdetection_b200.model.utils.config import cfg
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_targets.npz"))
+    old = cfg.TRAIN.BATCH_SIZE
+    cfg.TRAIN.BATCH_SIZE = int(g["pt_cfg"][0])
+    try:
+        layer = _ProposalTargetLayer(21)
+        ro, lab, tg, iw, ow = layer(cu(g["pt_rois"]), cu(g["pt_gt"]), None, fg_keys=cu(g["pt_fg_keys"]), bg_u=cu(g["pt_bg_u"]))
+    finally:
+        cfg.TRAIN.BATCH_SIZE = old
+    assert int(layer.last_status.sum().item()) == 0
+    assert np.array_equal(ro.cpu().numpy(), g["pt_out_rois"])          # same rois in the same order
+    assert np.array_equal(lab.cpu().numpy(), g["pt_out_labels"])
+    np.testing.assert_allclose(tg.cpu().numpy(), g["pt_out_targets"], rtol=1e-5, atol=1e-6)
+    assert np.array_equal(iw.cpu().numpy(), g["pt_out_inside"]) and np.array_equal(ow.cpu().numpy(), g["pt_out_outside"])
+
+
+def test_proposal_target_layer_train_size_and_corner_cases(orc):
+    # TRAIN size: 2000 rois + 20 gt, 128 per image; image 1 has no gt at all (only bg), image 2 only fg-able rois
+    B, N, G, R = 3, 2000, 20, 128
+    g = torch.Generator().manual_seed(13)
+    gt = torch.zeros(B, G, 5)
+    gt[0, :7, :4] = syn.random_boxes(g, 7, 600, 1000, 40.0, 300.0)
+    gt[0, :7, 4] = torch.arange(1, 8).float()
+    gt[2, :2, :4] = torch.tensor([[100.0, 100.0, 300.0, 300.0], [400.0, 50.0, 700.0, 350.0]])
+    gt[2, :2, 4] = torch.tensor([3.0, 9.0])
+    rois = torch.zeros(B, N, 5)
+    for b in range(B):
+        rois[b, :, 0] = b
+        rois[b, :, 1:] = syn.random_boxes(g, N, 600, 1000, 16.0, 400.0)
+    rois[2, :, 1:] = gt[2, torch.randint(0, 2, (N,), generator=g), :4] + torch.randn(N, 4, generator=g) * 3.0
+    fg_keys, bg_u = torch.rand(B, N + G, generator=g), torch.rand(B, R, generator=g)
+    out = be.proposal_target(cu(rois), cu(gt), cu(fg_keys), cu(bg_u), R, 32, 0.5, 0.5, 0.1, means=(0, 0, 0, 0),
+                             stds=(0.1, 0.1, 0.2, 0.2))
+    ref = orc.proposal_target(rois.numpy(), gt.numpy(), fg_keys.numpy(), bg_u.numpy(), R, 32)
+    names = ["rois", "labels", "targets", "inside", "outside", "status"]
+    for o, r, nm in zip(out, ref, names):
+        if nm == "targets":
+            np.testing.assert_allclose(o.cpu().numpy(), r, rtol=1e-5, atol=1e-6, err_msg=nm)
+        else:
+            assert np.array_equal(o.cpu().numpy(), r), nm
+
+
+def test_anchor_target_layer_vs_reference(orc):
+    import os
+    from rlobjectdetection_b200.model.rpn.anchor_target_layer import _AnchorTargetLayer
+    from rlobjectdetection_b200.model.utils.config import cfg
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_targets.npz"))
+    H, W, stride, bs = (int(v) for v in g["at_cfg"])
+    old = (cfg.TRAIN.RPN_BATCHSIZE, cfg.TRAIN.RPN_FG_FRACTION)
+    try:
+        cfg.TRAIN.RPN_BATCHSIZE = bs
+        layer = _AnchorTargetLayer(stride, [8, 16, 32], [0.5, 1, 2])
+        score = torch.zeros(2, 18, H, W, device=DEV)
+        for tag, frac in (("at", 0.5), ("at2", 0.1)):
+            cfg.TRAIN.RPN_FG_FRACTION = frac
+            L, T, IW, OW = layer((score, cu(g["at_gt"]), cu(g["at_im_info"]), None), keys=cu(g["at_keys"]))
+            assert np.array_equal(L.cpu().numpy(), g[f"{tag}_labels"]), tag
+            np.testing.assert_allclose(T.cpu().numpy(), g[f"{tag}_targets"], rtol=1e-5, atol=1e-6)
+            assert np.array_equal(IW.cpu().numpy(), g[f"{tag}_inside"])
+            np.testing.assert_allclose(OW.cpu().numpy(), g[f"{tag}_outside"], rtol=1e-6)
+    finally:
+        cfg.TRAIN.RPN_BATCHSIZE, cfg.TRAIN.RPN_FG_FRACTION = old
+
+
+def test_anchor_target_layer_c1_size(orc):
+    # VGG-16 600x1000: 37 x 62 map, 9 anchors, 20 gt, RPN batch 256
+    B, H, W, G, A = 2, 37, 62, 20, 9
+    g = torch.Generator().manual_seed(21)
+    gt = torch.zeros(B, G, 5)
+    for b, ng in enumerate((20, 4)):
+        gt[b, :ng, :4] = syn.random_boxes(g, ng, 600, 1000, 48.0, 400.0)
+        gt[b, :ng, 4] = torch.randint(1, 21, (ng,), generator=g).float()
+    im_info = torch.tensor([[600.0, 1000.0, 1.6]] * B)
+    keys = torch.rand(B, H * W * A, generator=g)
+    anchors = orc.generate_anchors(16, (0.5, 1, 2), (8, 16, 32)).astype(np.float32)
+    out = be.anchor_target(cu(gt), cu(im_info), cu(anchors), cu(keys), A, H, W, 16, 0.7, 0.3, False, 0.5, 256, 1.0, -1.0)
+    ref = orc.anchor_target(gt.numpy(), im_info.numpy(), anchors, keys.numpy(), H, W, 16)
+    assert np.array_equal(out[0].cpu().numpy(), ref[0])
+    np.testing.assert_allclose(out[1].cpu().numpy(), ref[1], rtol=1e-5, atol=1e-6)
+    assert np.array_equal(out[2].cpu().numpy(), ref[2])
+    np.testing.assert_allclose(out[3].cpu().numpy(), ref[3], rtol=1e-6)
+    lab = out[0].cpu().numpy()
+    assert ((lab == 1).sum(axis=(1, 2, 3)) <= 128).all() and ((lab >= 0).sum(axis=(1, 2, 3)) <= 256).all()

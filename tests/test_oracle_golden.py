@@ -138,3 +138,24 @@ def test_affine_grid_and_roi_crop_vs_torch(orc):
     ref = torch.cat([F.grid_sample(feat[r // per:r // per + 1], grid_xy[r:r + 1], mode="bilinear", padding_mode="zeros",
                                    align_corners=True) for r in range(R)], 0).numpy()
     np.testing.assert_allclose(out, ref, rtol=1e-5, atol=1e-5)
+
+
+def test_target_layers_vs_reference(orc):
+    """_ProposalTargetLayer / _AnchorTargetLayer executed unmodified with np.random patched to
+    recorded keys (tests/golden/make_golden_targets.py) vs the oracle ports."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_targets.npz"))
+    R, fgp = (int(v) for v in g["pt_cfg"])
+    ro, lab, tg, iw, ow, status = orc.proposal_target(g["pt_rois"], g["pt_gt"], g["pt_fg_keys"], g["pt_bg_u"], R, fgp)
+    assert (status == 0).all()
+    assert np.array_equal(ro, g["pt_out_rois"]) and np.array_equal(lab, g["pt_out_labels"])
+    np.testing.assert_allclose(tg, g["pt_out_targets"], rtol=1e-6, atol=1e-6)
+    assert np.array_equal(iw, g["pt_out_inside"]) and np.array_equal(ow, g["pt_out_outside"])
+    H, W, stride, bs = (int(v) for v in g["at_cfg"])
+    for tag, frac in (("at", 0.5), ("at2", 0.1)):
+        L, T, IW, OW = orc.anchor_target(g["at_gt"], g["at_im_info"], g["at_anchors"], g["at_keys"], H, W, stride,
+                                         fg_fraction=frac, batchsize=bs)
+        assert np.array_equal(L, g[f"{tag}_labels"])
+        np.testing.assert_allclose(T, g[f"{tag}_targets"], rtol=1e-6, atol=1e-6)
+        assert np.array_equal(IW, g[f"{tag}_inside"])
+        np.testing.assert_allclose(OW, g[f"{tag}_outside"], rtol=1e-7)
