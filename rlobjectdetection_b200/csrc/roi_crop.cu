@@ -14,6 +14,7 @@
 //                         r / (R / B) (the reference ignores the roi's batch column).
 //   rlod_roi_crop_backward :120-199: gradient w.r.t. the feature map (the reference computes no
 //                         grid gradient: its dot products are never stored).  One RED per tap.
+// (grid.y = C / 32 must stay below 65536: C < 2^21.)
 // Every fp32 operation rounds separately, in the reference's order.
 #include "rlod_common.cuh"
 
@@ -59,18 +60,27 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// CTA = (roi, chunk of channels).  A thread owns sample points of the roi's gh x gw grid: the
+// top-left tap offset, the four tap masks and the four weight products are computed ONCE and
+// reused for every channel of the chunk, so the per-channel work is 4 gathers (the roi's patch
+// of a plane: L1 / L2 hits, the image's planes stay L2-resident because its rois are launched
+// together), 7 fp32 ops in the reference's rounding order and one coalesced store -- no index
+// arithmetic per element.  Backward: the same walk with one RED per valid tap.
+constexpr int kCropThreads = 224;  // 7 warps: a 14 x 14 grid is 196 sample points
+constexpr int kCropChunk = 32;     // channels per CTA
+
 template <bool BWD>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kCropThreads)
     k_roi_crop(const float *__restrict__ feat_or_gout, const float *__restrict__ grid, int B, int C, int H,
                int W, int R, int gh, int gw, int roi_per_image, float *__restrict__ out_or_gfeat) {
-  const long long total = (long long)R * C * gh * gw;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int xo = (int)(idx % gw), yo = (int)((idx / gw) % gh);
-    const int c = (int)((idx / ((long long)gw * gh)) % C);
-    const int r = (int)(idx / ((long long)gw * gh * C));
-    const int b = r / roi_per_image;
-    const float *gp = grid + (((size_t)r * gh + yo) * gw + xo) * 2;
+  const int r = blockIdx.x, c0 = blockIdx.y * kCropChunk;
+  const int c1 = min(C, c0 + kCropChunk);
+  const int b = r / roi_per_image;
+  const int ghw = gh * gw;
+  const size_t HW = (size_t)H * W;
+  const bool valid_b = b >= 0 && b < B;
+  for (int p = threadIdx.x; p < ghw; p += kCropThreads) {
+    const float *gp = grid + ((size_t)r * ghw + p) * 2;
     const float yf = __ldg(gp), xf = __ldg(gp + 1);
     int x0, y0;
     float xw, yw;
@@ -78,30 +88,40 @@ __global__ void __launch_bounds__(256)
     crop_top_left(yf, H, y0, yw);
     const bool xin0 = x0 >= 0 && x0 <= W - 1, xin1 = x0 + 1 >= 0 && x0 + 1 <= W - 1;
     const bool yin0 = y0 >= 0 && y0 <= H - 1, yin1 = y0 + 1 >= 0 && y0 + 1 <= H - 1;
-    const bool valid_b = b >= 0 && b < B;
-    const size_t base = ((size_t)(valid_b ? b : 0) * C + c) * ((size_t)H * W);
+    const bool m00 = valid_b && xin0 && yin0, m01 = valid_b && xin1 && yin0;
+    const bool m10 = valid_b && xin0 && yin1, m11 = valid_b && xin1 && yin1;
+    const float ixw = __fsub_rn(1.f, xw), iyw = __fsub_rn(1.f, yw);
+    const float w00 = __fmul_rn(xw, yw), w01 = __fmul_rn(ixw, yw), w10 = __fmul_rn(xw, iyw), w11 = __fmul_rn(ixw, iyw);
+    // masked-off taps are never dereferenced: point them at the plane's first pixel
     const long long tl = (long long)y0 * W + x0;
+    const long long o00 = m00 ? tl : 0, o01 = m01 ? tl + 1 : 0, o10 = m10 ? tl + W : 0, o11 = m11 ? tl + W + 1 : 0;
+    const size_t plane0 = ((size_t)(valid_b ? b : 0) * C + c0) * HW;
+    const size_t io0 = ((size_t)r * C + c0) * ghw + p;  // out (fwd) / grad_out (bwd) element of channel c0
     if (!BWD) {
-      float v = 0.f;
-      if (valid_b && ((xin0 || xin1) && (yin0 || yin1))) {
-        const float *p = feat_or_gout + base;
-        const float a = (xin0 && yin0) ? __ldg(p + tl) : 0.f, bb = (xin1 && yin0) ? __ldg(p + tl + 1) : 0.f;
-        const float cc = (xin0 && yin1) ? __ldg(p + tl + W) : 0.f, d = (xin1 && yin1) ? __ldg(p + tl + W + 1) : 0.f;
-        const float ixw = __fsub_rn(1.f, xw), iyw = __fsub_rn(1.f, yw);
-        v = __fmul_rn(__fmul_rn(xw, yw), a);
-        v = __fadd_rn(v, __fmul_rn(__fmul_rn(ixw, yw), bb));
-        v = __fadd_rn(v, __fmul_rn(__fmul_rn(xw, iyw), cc));
-        v = __fadd_rn(v, __fmul_rn(__fmul_rn(ixw, iyw), d));
+      const float *pl = feat_or_gout + plane0;
+      float *o = out_or_gfeat + io0;
+#pragma unroll 4
+      for (int c = c0; c < c1; ++c, pl += HW, o += ghw) {
+        const float a = m00 ? __ldg(pl + o00) : 0.f, bb = m01 ? __ldg(pl + o01) : 0.f;
+        const float cc = m10 ? __ldg(pl + o10) : 0.f, d = m11 ? __ldg(pl + o11) : 0.f;
+        float v = __fmul_rn(w00, a);
+        v = __fadd_rn(v, __fmul_rn(w01, bb));
+        v = __fadd_rn(v, __fmul_rn(w10, cc));
+        v = __fadd_rn(v, __fmul_rn(w11, d));
+        // no tap inside the map (or a bad image index): the reference writes 0
+        __stcs(o, v);
       }
-      out_or_gfeat[idx] = v;
     } else if (valid_b) {
-      const float go = __ldg(feat_or_gout + idx);
-      float *p = out_or_gfeat + base;
-      const float ixw = __fsub_rn(1.f, xw), iyw = __fsub_rn(1.f, yw);
-      if (xin0 && yin0) atomicAdd(p + tl, __fmul_rn(__fmul_rn(xw, yw), go));
-      if (xin1 && yin0) atomicAdd(p + tl + 1, __fmul_rn(__fmul_rn(ixw, yw), go));
-      if (xin0 && yin1) atomicAdd(p + tl + W, __fmul_rn(__fmul_rn(xw, iyw), go));
-      if (xin1 && yin1) atomicAdd(p + tl + W + 1, __fmul_rn(__fmul_rn(ixw, iyw), go));
+      float *pl = out_or_gfeat + plane0;
+      const float *gq = feat_or_gout + io0;
+#pragma unroll 4
+      for (int c = c0; c < c1; ++c, pl += HW, gq += ghw) {
+        const float go = __ldcs(gq);
+        if (m00) atomicAdd(pl + o00, __fmul_rn(w00, go));
+        if (m01) atomicAdd(pl + o01, __fmul_rn(w01, go));
+        if (m10) atomicAdd(pl + o10, __fmul_rn(w10, go));
+        if (m11) atomicAdd(pl + o11, __fmul_rn(w11, go));
+      }
     }
   }
 }
@@ -135,8 +155,8 @@ RLOD_API int rlod_roi_crop_forward(const float *feat, const float *grid_yx, int 
   if (R < B) return RLOD_EINVAL;  // roiPerImage = R / B = 0 divides by zero in the reference
   cudaStream_t st = (cudaStream_t)stream;
   RLOD_LAUNCH(RLOD_KERNEL_CROP, st,
-              k_roi_crop<false><<<crop_grid((long long)R * C * gh * gw), 256, 0, st>>>(feat, grid_yx, B, C, H, W, R, gh, gw,
-                                                                                     R / B, out));
+              k_roi_crop<false><<<dim3((unsigned)R, (unsigned)((C + kCropChunk - 1) / kCropChunk)), kCropThreads, 0, st>>>(
+                  feat, grid_yx, B, C, H, W, R, gh, gw, R / B, out));
   return launch_status();
 }
 
@@ -151,7 +171,7 @@ RLOD_API int rlod_roi_crop_backward(const float *grad_out, const float *grid_yx,
   if (R == 0) return launch_status();
   if (!grad_out || !grid_yx || R < B) return RLOD_EINVAL;
   RLOD_LAUNCH(RLOD_KERNEL_CROP, st,
-              k_roi_crop<true><<<crop_grid((long long)R * C * gh * gw), 256, 0, st>>>(grad_out, grid_yx, B, C, H, W, R, gh, gw,
-                                                                                    R / B, grad_feat));
+              k_roi_crop<true><<<dim3((unsigned)R, (unsigned)((C + kCropChunk - 1) / kCropChunk)), kCropThreads, 0, st>>>(
+                  grad_out, grid_yx, B, C, H, W, R, gh, gw, R / B, grad_feat));
   return launch_status();
 }
