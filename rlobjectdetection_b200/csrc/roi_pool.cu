@@ -121,17 +121,28 @@ __global__ void __launch_bounds__(kPoolThreads, 2)
       float4 mv = make_float4(-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f);
       int4 mi = make_int4(-1, -1, -1, -1);
       const int h0 = hs[ph], h1 = he[ph];
+      // four pixels of a bin row per step: the loads are independent (predicated, a pixel outside
+      // the bin keeps the -FLT_MAX sentinel and can never win a strict '>'), then the compare
+      // chain in scan order
       for (int dh = 0; dh < mrw; ++dh) {
         const int h = h0 + dh;
-        for (int dw = 0; dw < mcw; ++dw) {
-          const int w = ws + dw;
-          if (h < h1 && w < we) {
-            const float4 v = lds128(pbase + 16u * (uint32_t)(h * P + w));
-            const int pix = h * W + w;
-            if (v.x > mv.x) mv.x = v.x, mi.x = pix;
-            if (v.y > mv.y) mv.y = v.y, mi.y = pix;
-            if (v.z > mv.z) mv.z = v.z, mi.z = pix;
-            if (v.w > mv.w) mv.w = v.w, mi.w = pix;
+        const bool rowok = h < h1;
+        const int rowpix = h * W + ws;
+        const uint32_t rowaddr = pbase + 16u * (uint32_t)(h * P + ws);
+        for (int dw = 0; dw < mcw; dw += 4) {
+          float4 v[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            v[j] = make_float4(-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f);
+            if (rowok && ws + dw + j < we) v[j] = lds128(rowaddr + 16u * (uint32_t)(dw + j));
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int pix = rowpix + dw + j;
+            if (v[j].x > mv.x) mv.x = v[j].x, mi.x = pix;
+            if (v[j].y > mv.y) mv.y = v[j].y, mi.y = pix;
+            if (v[j].z > mv.z) mv.z = v[j].z, mi.z = pix;
+            if (v[j].w > mv.w) mv.w = v[j].w, mi.w = pix;
           }
         }
       }
