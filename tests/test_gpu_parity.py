@@ -658,6 +658,34 @@ def test_roi_crop_forward_backward(orc, case):
     close(gin, orc.roi_crop_bwd(gout.numpy(), grid_yx, tuple(feat.shape)), what="roi_crop bwd")
 
 
+def test_roi_crop_backward_general_grids(orc):
+    """The backward gathers per patch pixel when a roi's grid is separable and monotone (what
+    _affine_grid_gen emits) and scatters otherwise: jittered (non-separable), mirrored (x2 < x1:
+    decreasing columns), far-outside and mixed batches must all match the oracle's scatter."""
+    B, C, H, W, n_per, gs = 2, 40, 20, 31, 12, 14
+    feat, rois = _crop_case(21, B, C, H, W, n_per, gs)
+    rois = rois.clone()
+    rois[1, [1, 3]] = rois[1, [3, 1]]            # mirrored in x
+    rois[2, [2, 4]] = rois[2, [4, 2]]            # mirrored in y
+    rois[3, 1:5] = torch.tensor([-300.0, -200.0, -120.0, -90.0])   # every tap outside the map
+    rois[4, 1:5] = torch.tensor([-40.0, -30.0, 60.0, 50.0])        # straddles the top-left corner
+    rois[5, 1:5] = torch.tensor([W * 16.0 - 50, H * 16.0 - 40, W * 16.0 + 80, H * 16.0 + 90])
+    grid_xy = orc.affine_grid(rois.numpy(), H, W, gs, True)
+    grid_yx = np.ascontiguousarray(np.stack([grid_xy[..., 1], grid_xy[..., 0]], 3)).astype(np.float32)
+    rng = np.random.default_rng(3)
+    grid_yx[6] += rng.normal(0, 0.02, grid_yx[6].shape).astype(np.float32)       # not separable
+    grid_yx[7, 3, 5, 1] = np.nextafter(grid_yx[7, 3, 5, 1], np.float32(2.0))      # one sample off by an ulp
+    g = torch.Generator().manual_seed(6)
+    gout = torch.randn(rois.size(0), C, gs, gs, generator=g)
+    gin = be.roi_crop_backward(cu(gout), cu(grid_yx), tuple(feat.shape)).cpu().numpy()
+    close(gin, orc.roi_crop_bwd(gout.numpy(), grid_yx, tuple(feat.shape)), what="roi_crop bwd general")
+    # accumulate: adds to the caller's gradient
+    base = torch.randn(*feat.shape, generator=g)
+    acc = cu(base).clone()
+    be.roi_crop_backward(cu(gout), cu(grid_yx), tuple(feat.shape), grad_in=acc)
+    close(acc.cpu().numpy(), base.numpy() + gin, what="roi_crop bwd accumulate")
+
+
 def test_roi_crop_module_and_crop_pool(orc):
     from rlobjectdetection_b200.model.roi_crop.modules.roi_crop import _RoICrop
     from rlobjectdetection_b200.model.utils.net_utils import crop_pool
