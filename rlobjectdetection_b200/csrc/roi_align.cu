@@ -563,7 +563,7 @@ __global__ void __launch_bounds__(kWalkThreads, 2)
   // boundary when H*W is even but not a multiple of 4: the copy starts 8 bytes early (skew).
   // Fallback: 4-byte async copies (LDGSTS), interleaved in flight.
   uint64_t *fill_bar = reinterpret_cast<uint64_t *>(stage + kWalkWarps * 2 * 4 * SLOT);
-#if RLOD_ABL != 1
+#if RLOD_ABL != 1 && RLOD_ABL != 4
   if (tma_fill) {
     const uint32_t plane_copy = (uint32_t)((HW * 4 + 8 + 15) & ~15);  // bytes per bulk copy (skew <= 8)
     unsigned char *buf[4];
@@ -672,7 +672,7 @@ __global__ void __launch_bounds__(kWalkThreads, 2)
   {                                                                                         \
     const uint32_t pa = cbase + ((uint32_t)cur.w[T] & 0x1fff0u);                            \
     const uint32_t pa2 = cbase + (((uint32_t)cur.w[T] >> 13) & 0x1fff0u);                   \
-    walk_step(t0, t1, s[T], taps[(T) & 1], pa, pa + da, pa2, pa2 + da, cur.wa, cur.rt[T], RLOD_ABL == 3 ? (cur.w[T] & ~3) : cur.w[T]); \
+    walk_step(t0, t1, s[T], taps[(T) & 1], pa, pa + da, pa2, pa2 + da, cur.wa, cur.rt[T], (RLOD_ABL == 3 || RLOD_ABL == 4) ? (cur.w[T] & ~3) : cur.w[T]); \
   }
     // output of walk position T: NONE stores the sample itself; AVG / MAX pool 2x2 stride 1,
     // along the walk axis in registers and along the lane axis with one shuffle per value

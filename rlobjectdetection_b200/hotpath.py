@@ -13,6 +13,16 @@ from .model.rpn.proposal_layer import _ProposalLayer
 
 
 class DetectRefineStep:
+    """Two streams per device.  Everything that is per-image and latency-bound -- the proposal
+    layer's select / sort / NMS (one CTA per image), the action rewards and the refine -- runs
+    on a private "light" stream; the two RoIAlign calls (a full-GPU kernel each) run on the
+    caller's stream and wait, by event, for the rois they pool.  Within a call that only takes
+    reward + refine off the critical path; across calls, when the caller says its inputs are
+    ready (`inputs_ready`), the light stream runs ahead and step i+1's proposal work fills
+    the SMs' idle slots under step i's RoIAlign kernels -- the per-image kernels use 24 of 148
+    SMs, so they cost next to nothing there.  Results are ordered on the caller's stream as
+    usual (every cross-stream tensor is record_stream'ed)."""
+
     def __init__(self, feat_stride=16, scales=(4, 8, 16, 32), ratios=(0.5, 1, 2), cfg_key="TEST",
                  pool=7, act_delta=(0.5, 0.25), backward=True):
         self.proposal = _ProposalLayer(feat_stride, list(scales), list(ratios))
@@ -22,21 +32,48 @@ class DetectRefineStep:
         self.pool = pool
         self.scale = 1.0 / feat_stride
         self.backward = backward
+        self._light = {}
+
+    def _light_stream(self, device):
+        key = (device.type, device.index)
+        if key not in self._light:
+            self._light[key] = torch.cuda.Stream(device=device)
+        return self._light[key]
 
     @torch.no_grad()
-    def __call__(self, scores, deltas, im_info, feat, gt, grad_pooled=None):
+    def __call__(self, scores, deltas, im_info, feat, gt, grad_pooled=None, inputs_ready=None):
         """scores (B,2A,H,W), deltas (B,4A,H,W), im_info (B,3), feat (B,C,H,W), gt (B,G,4)
         x1y1x2y2; grad_pooled (B*post,C,pool,pool) is the upstream gradient of the re-pooled
-        features (what layer4 would send back) when backward is on."""
-        rois = self.proposal((scores, deltas, im_info, self.cfg_key))         # (B, post, 5)
-        B, N, _ = rois.shape
+        features (what layer4 would send back) when backward is on.
+
+        inputs_ready: None (default) = the inputs are ordered on the current stream, the light
+        stream waits for it (no overlap across calls); a torch.cuda.Event = they are ready once
+        it has fired; True = they are resident and nobody is writing them."""
+        cur = torch.cuda.current_stream(feat.device)
+        light = self._light_stream(feat.device)
+        if inputs_ready is None:
+            light.wait_stream(cur)
+        elif inputs_ready is not True:
+            light.wait_event(inputs_ready)
+        with torch.cuda.stream(light):
+            rois = self.proposal((scores, deltas, im_info, self.cfg_key))     # (B, post, 5)
+            have_rois = torch.cuda.Event()
+            have_rois.record(light)
+            B, N, _ = rois.shape
+            reward, label, weight = action_rewards(self.action, rois[:, :, 1:5], gt, mode=IOU_RCNN)
+            refined = rois.clone()
+            # every box takes its best action if that action's label is +1 (move_from_act with
+            # maxk = N and the rewards as predictions)
+            moved = be.move_from_act(refined, reward, label, self.action.table(rois.device), N,
+                                     corners=True)
+            have_refined = torch.cuda.Event()
+            have_refined.record(light)
+        for t in (rois, reward, label, weight, refined, moved):
+            if torch.is_tensor(t):
+                t.record_stream(cur)
+        cur.wait_event(have_rois)
         pooled = self.align(feat, rois.view(-1, 5))                           # (B*N, C, p, p)
-        reward, label, weight = action_rewards(self.action, rois[:, :, 1:5], gt, mode=IOU_RCNN)
-        refined = rois.clone()
-        # every box takes its best action if that action's label is +1 (move_from_act with
-        # maxk = N and the rewards as predictions)
-        moved = be.move_from_act(refined, reward, label, self.action.table(rois.device), N,
-                                 corners=True)
+        cur.wait_event(have_refined)
         pooled_refined = self.align(feat, refined.view(-1, 5))
         out = dict(rois=rois, pooled=pooled, reward=reward, label=label, weight=weight,
                    refined=refined, moved=moved, pooled_refined=pooled_refined)

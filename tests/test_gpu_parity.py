@@ -520,6 +520,48 @@ def test_hotpath_step_matches_oracle_chain(orc):
           orc.roi_align_bwd(gp.numpy(), feat.numpy(), refined.reshape(-1, 5), 7, 7, 1 / 16.0, pool_mode=orc.POOL_AVG))
 
 
+def test_hotpath_step_run_ahead_streams():
+    """inputs_ready=True / an Event lets the step's light stream run ahead of the caller's stream: many
+    calls back to back on changing inputs, with and without run-ahead, must give identical results
+    (the cross-stream tensors are event-ordered and record_stream'ed), also under allocator churn."""
+    from rlobjectdetection_b200.hotpath import DetectRefineStep
+    B, C, H, W, G = 3, 32, 25, 38, 6
+    step = DetectRefineStep(cfg_key="TEST", backward=False)
+    A = step.proposal._num_anchors
+    g = torch.Generator().manual_seed(12)
+    feat = cu(torch.randn(B, C, H, W, generator=g))
+    ins = []
+    for k in range(6):
+        scores, deltas, im_info = syn.rpn_outputs(20 + k, B, A, H, W, H * 16, W * 16)
+        gt, _ = syn.gt_boxes(40 + k, B, G, H * 16, W * 16)
+        ins.append((cu(scores), cu(deltas), cu(im_info), feat, cu(gt)))
+    torch.cuda.synchronize()
+    keys = ("rois", "reward", "refined", "pooled", "pooled_refined")
+    ref = []
+    for a in ins:
+        o = step(*a)                       # serial: the light stream waits for the caller's stream
+        ref.append({k: o[k].clone() for k in keys})
+    torch.cuda.synchronize()
+    for mode in ("resident", "event"):
+        outs = []
+        for a in ins:
+            if mode == "event":
+                ev = torch.cuda.Event()
+                ev.record()
+                o = step(*a, inputs_ready=ev)
+            else:
+                o = step(*a, inputs_ready=True)
+            outs.append({k: o[k] for k in keys})
+            del o
+            junk = torch.empty(1 << 20, device=DEV).normal_()   # allocator churn on the caller's stream
+            del junk
+        torch.cuda.synchronize()
+        for r, o in zip(ref, outs):
+            for k in keys:
+                assert torch.equal(r[k], o[k]), (mode, k)
+
+
+
 # ------------------------------------------------------------------------------------------
 # test-time post-processing (f1): threshold / decode / clip / sort / per-class NMS / cap
 # ------------------------------------------------------------------------------------------
