@@ -355,6 +355,8 @@ def run_ours(args, rank, local_rank, world):
         "roofline": roofline,
         "cpu_baseline": cpu,
         "kernel_ms_per_step": kernel_ms,
+        "kernel_ms_note": "CUDA events around every launch on its own stream: for the light stream's kernels this is "
+                          "launch-to-finish time, queueing behind the RoIAlign launches for a free SM included",
     }
     print(json.dumps(line), flush=True)
 
