@@ -542,13 +542,17 @@ def test_hotpath_step_run_ahead_streams():
         o = step(*a)                       # serial: the light stream waits for the caller's stream
         ref.append({k: o[k].clone() for k in keys})
     torch.cuda.synchronize()
-    for mode in ("resident", "event"):
+    for mode in ("resident", "event", "prefetch", "prefetch_wrong"):
         outs = []
-        for a in ins:
+        for i, a in enumerate(ins):
             if mode == "event":
                 ev = torch.cuda.Event()
                 ev.record()
                 o = step(*a, inputs_ready=ev)
+            elif mode.startswith("prefetch"):
+                # announce the next step's inputs (or, "wrong", other ones: they must be ignored)
+                n = ins[(i + (1 if mode == "prefetch" else 3)) % len(ins)]
+                o = step(*a, inputs_ready=True, next_inputs=(n[0], n[1], n[2], n[4]), next_ready=True)
             else:
                 o = step(*a, inputs_ready=True)
             outs.append({k: o[k] for k in keys})
