@@ -18,6 +18,7 @@ live with CUDA events on its own stream, cpu_baseline = the CPU port (oracle/) o
 sample.  --impl reference times that CPU port as the reference arm.
 """
 import argparse
+import gc
 import json
 import os
 import statistics
@@ -169,10 +170,18 @@ class ClockSampler:
             self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
             self._ready.set()
             while not self._stop.is_set():
+                # NVML queries share driver state with the launching thread: with a poller running (even one
+                # that had gone quiet a moment before) the first step after a synchronise sometimes found a
+                # kernel launch blocked for 15-70 ms.  So there is NO NVML activity from start-up until
+                # bench.py arms the sampler, which it does once every step of the timed region has been
+                # ENQUEUED: the GPU is still working through them (that is the load the clocks are sampled
+                # under), but no launch is left to be stalled.
                 if self._armed.is_set():
                     self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
                     self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
-                time.sleep(0.001)
+                    time.sleep(0.001)
+                else:
+                    self._stop.wait(0.002)
         except Exception as e:  # noqa: BLE001 -- clocks are reported, never fatal
             self.err = repr(e)
             self._ready.set()
@@ -214,7 +223,8 @@ def run_ours(args, rank, local_rank, world):
     first_image = rank * nb
 
     host = [t.pin_memory() for t in make_inputs(100 + rank, nb)]
-    step = DetectRefineStep(STRIDE, SCALES, RATIOS, "TEST", POOL, ACT_DELTA, backward=False)
+    step = DetectRefineStep(STRIDE, SCALES, RATIOS, "TEST", POOL, ACT_DELTA, backward=False,
+                            outputs=("refined", "reward"))  # what the gathered result is made of
     from rlobjectdetection_b200.model.utils.config import cfg
     cfg.TEST.RPN_PRE_NMS_TOP_N, cfg.TEST.RPN_POST_NMS_TOP_N, cfg.TEST.RPN_NMS_THRESH = PRE, POST, NMS_T
 
@@ -234,17 +244,36 @@ def run_ours(args, rank, local_rank, world):
         packed = pack_results(out["refined"], out["reward"], first_image)
         return out, gather_results(packed, global_batch)
 
-    def timed(fn, steps, warmup):
+    step_marks, host_ms = [], []
+
+    def timed(fn, steps, warmup, marks=None, on_enqueued=None, before_timed=None):
         for _ in range(warmup):
             fn()
+        gc.collect()
+        gc.disable()  # like timeit: a cyclic collection in the launching thread is a multi-millisecond stall
         barrier()
+        if before_timed is not None:
+            before_timed()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(steps):
+        host_t = [time.perf_counter()]
+        for k_ in range(steps):
             fn()
+            if marks is not None:  # one event per step on the caller's stream: the spread of the step time
+                m = torch.cuda.Event(enable_timing=True)
+                m.record()
+                marks.append(m)
+                host_t.append(time.perf_counter())
         e1.record()
+        if on_enqueued is not None:
+            on_enqueued()
         barrier()
+        gc.enable()
         ms = e0.elapsed_time(e1)
+        if marks:
+            ts = [a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks)]
+            marks[:] = ts
+            host_ms[:] = [1e3 * (b - a) for a, b in zip(host_t, host_t[1:])]
         if world > 1:
             t = torch.tensor([ms], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -256,13 +285,23 @@ def run_ours(args, rank, local_rank, world):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    for _ in range(max(args.warmup, 3)):
+    lib.rlod_profile_enable(1)  # before the warm-up: the first event pairs are created outside the timed region
+    n_warm = max(args.warmup, 3)
+    for _ in range(n_warm - 1):
         device_step(dev_in, True, dev_in, True)
-    barrier()
-    launches0 = lib.rlod_launch_count()
-    lib.rlod_profile_enable(1)
-    sampler.arm(True)
-    ms = timed(lambda: device_step(dev_in, True, dev_in, True), args.steps, 0)
+    torch.cuda.synchronize()
+    be.profile_collect()        # drop the warm-up launches (host-side work: milliseconds)
+    # the last warm-up step runs AFTER the host-side housekeeping, so that the GPU (and the link to it) has
+    # been idle for one synchronise only when the timed region starts
+    count0 = [0]
+
+    def before_timed():
+        count0[0] = lib.rlod_launch_count()
+
+    ms = timed(lambda: device_step(dev_in, True, dev_in, True), args.steps, 1, step_marks,
+               on_enqueued=lambda: sampler.arm(True), before_timed=before_timed)
+    launches0 = count0[0]
+    prof_steps = args.steps + 1  # the per-kernel event times also cover that last warm-up step
     sampler.arm(False)
     clocks = sampler.stop() if rank == 0 else None
     lib.rlod_profile_enable(0)
@@ -336,7 +375,7 @@ def run_ours(args, rank, local_rank, world):
         kms, kn = prof["align_fwd"]
         ach = alg_bytes / (kms / kn * 1e-3) / 1e9
         roofline.update(achieved=ach, frac=ach / peak, launches_timed=kn, avg_launch_us=1e3 * kms / kn)
-    kernel_ms = {k: round(v[0] / args.steps, 4) for k, v in prof.items()}
+    kernel_ms = {k: round(v[0] / prof_steps, 4) for k, v in prof.items()}
 
     # ---- CPU baseline (port), bounded sample -----------------------------------------------
     cpu = None
@@ -358,6 +397,12 @@ def run_ours(args, rank, local_rank, world):
         "roofline": roofline,
         "cpu_baseline": cpu,
         "kernel_ms_per_step": kernel_ms,
+        # one event per step on the caller's stream.  The first step after the synchronise has nothing queued
+        # ahead of it, so every host-side hiccup of its ~25 launches is GPU idle time (2-70 ms seen on busy hosts);
+        # from the second step on the host runs ahead and the step time is the GPU's
+        "step_ms_spread": {"min": round(min(step_marks), 4), "median": round(statistics.median(step_marks), 4),
+                           "max": round(max(step_marks), 4), "first5": [round(v, 3) for v in step_marks[:5]],
+                           "host_enqueue_ms_median": round(statistics.median(host_ms), 4)} if step_marks else None,
         "kernel_ms_note": "CUDA events around every launch on its own stream: for the light stream's kernels this is "
                           "launch-to-finish time, queueing behind the RoIAlign launches for a free SM included",
     }

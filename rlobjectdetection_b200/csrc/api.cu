@@ -1,6 +1,7 @@
 // Version / error strings, launch counter and the optional per-kernel CUDA-event profiler of
 // the C ABI (include/rlod.h).
 #include <atomic>
+#include <map>
 #include <mutex>
 #include <vector>
 
@@ -18,11 +19,30 @@ static std::vector<EvPair> g_events[RLOD_KERNEL_COUNT];
 
 void note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// events are recycled: cudaEventCreate can block for milliseconds when the driver grows its pool,
+// and the first launches after a synchronise are the ones nobody can hide behind
+static std::map<int, std::vector<cudaEvent_t>> g_free_events;  // per device
+
+static bool take_event(cudaEvent_t *e) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto &pool = g_free_events[dev];
+    if (!pool.empty()) {
+      *e = pool.back();
+      pool.pop_back();
+      return true;
+    }
+  }
+  return cudaEventCreate(e) == cudaSuccess;
+}
+
 ProfScope::ProfScope(int kernel_id, cudaStream_t st) : id_(kernel_id), st_(st), on_(false) {
   note_launch(1);
   if (!g_profile.load(std::memory_order_relaxed) || id_ < 0 || id_ >= RLOD_KERNEL_COUNT) return;
-  if (cudaEventCreate(&a_) != cudaSuccess) return;
-  if (cudaEventCreate(&b_) != cudaSuccess) {
+  if (!take_event(&a_)) return;
+  if (!take_event(&b_)) {
     cudaEventDestroy(a_);
     return;
   }
@@ -81,8 +101,13 @@ RLOD_API int rlod_profile_collect(int kernel_id, double *total_ms, int *launches
     } else {
       rc = (int)err;
     }
-    cudaEventDestroy(e.a);
-    cudaEventDestroy(e.b);
+  }
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int dev = 0;
+    cudaGetDevice(&dev);  // collected on the device the launches ran on (one device per process in practice)
+    auto &pool = g_free_events[dev];
+    for (auto &e : ev) pool.push_back(e.a), pool.push_back(e.b);
   }
   *total_ms = sum;
   *launches = n;
