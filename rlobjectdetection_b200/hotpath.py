@@ -34,7 +34,8 @@ class DetectRefineStep:
     blocks and keeps growing)."""
 
     def __init__(self, feat_stride=16, scales=(4, 8, 16, 32), ratios=(0.5, 1, 2), cfg_key="TEST",
-                 pool=7, act_delta=(0.5, 0.25), backward=True):
+                 pool=7, act_delta=(0.5, 0.25), backward=True,
+                 outputs=("rois", "reward", "label", "weight", "refined", "moved")):
         self.proposal = _ProposalLayer(feat_stride, list(scales), list(ratios))
         self.align = RoIAlignAvg(pool, pool, 1.0 / feat_stride)
         self.action = Action(list(act_delta))
@@ -42,6 +43,7 @@ class DetectRefineStep:
         self.pool = pool
         self.scale = 1.0 / feat_stride
         self.backward = backward
+        self.outputs = tuple(outputs)  # which of the light stream's small tensors a call hands back (as copies)
         self.max_ahead = 2
         self._light = {}
         self._inflight = collections.deque()  # (event on the caller's stream, the light stream's tensors)
@@ -121,16 +123,16 @@ class DetectRefineStep:
             self._prefetched = (self._key(ns, nd, ni, ng), self._light_work(cur, light, ns, nd, ni, ng, next_ready))
         cur.wait_event(have_refined)
         pooled_refined = self.align(feat, l_refined.view(-1, 5))
-        rois, reward, label, weight, refined, moved = (t.clone() for t in l_tensors)
+        names = ("rois", "reward", "label", "weight", "refined", "moved")
+        out = {n: t.clone() for n, t in zip(names, l_tensors) if n in self.outputs or (n == "refined" and self.backward)}
         consumed = torch.cuda.Event()
         consumed.record(cur)
         self._inflight.append((consumed, l_tensors))
-        out = dict(rois=rois, pooled=pooled, reward=reward, label=label, weight=weight,
-                   refined=refined, moved=moved, pooled_refined=pooled_refined)
+        out.update(pooled=pooled, pooled_refined=pooled_refined)
         if self.backward:
             if grad_pooled is None:
                 raise ValueError("backward=True needs grad_pooled")
-            out["grad_feat"] = be.roi_align_backward(grad_pooled, refined.view(-1, 5), None,
+            out["grad_feat"] = be.roi_align_backward(grad_pooled, out["refined"].view(-1, 5), None,
                                                      tuple(feat.shape), self.pool, self.pool,
                                                      self.scale, be.POOL_AVG)
         return out
