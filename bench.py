@@ -285,6 +285,10 @@ def run_ours(args, rank, local_rank, world):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    # spare small-pool segments for the caller's stream too (see DetectRefineStep._light_stream): no cudaMalloc
+    # may happen inside the timed region
+    spare = [torch.empty(512 << 10, dtype=torch.uint8, device=dev) for _ in range(32)]
+    del spare
     lib.rlod_profile_enable(1)  # before the warm-up: the first event pairs are created outside the timed region
     n_warm = max(args.warmup, 3)
     for _ in range(n_warm - 1):
@@ -295,12 +299,16 @@ def run_ours(args, rank, local_rank, world):
     # been idle for one synchronise only when the timed region starts
     count0 = [0]
 
+    mstat = {}
+
     def before_timed():
         count0[0] = lib.rlod_launch_count()
+        mstat["alloc0"] = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
 
     ms = timed(lambda: device_step(dev_in, True, dev_in, True), args.steps, 1, step_marks,
                on_enqueued=lambda: sampler.arm(True), before_timed=before_timed)
     launches0 = count0[0]
+    mallocs_in_region = torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - mstat["alloc0"]
     prof_steps = args.steps + 1  # the per-kernel event times also cover that last warm-up step
     sampler.arm(False)
     clocks = sampler.stop() if rank == 0 else None
@@ -402,7 +410,8 @@ def run_ours(args, rank, local_rank, world):
         # from the second step on the host runs ahead and the step time is the GPU's
         "step_ms_spread": {"min": round(min(step_marks), 4), "median": round(statistics.median(step_marks), 4),
                            "max": round(max(step_marks), 4), "first5": [round(v, 3) for v in step_marks[:5]],
-                           "host_enqueue_ms_median": round(statistics.median(host_ms), 4)} if step_marks else None,
+                           "host_enqueue_ms_median": round(statistics.median(host_ms), 4),
+                           "cudaMalloc_calls_in_timed_region": int(mallocs_in_region)} if step_marks else None,
         "kernel_ms_note": "CUDA events around every launch on its own stream: for the light stream's kernels this is "
                           "launch-to-finish time, queueing behind the RoIAlign launches for a free SM included",
     }
