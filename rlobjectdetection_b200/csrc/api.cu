@@ -11,6 +11,7 @@ namespace rlod {
 
 static std::atomic<long long> g_launches{0};
 static std::atomic<int> g_profile{0};
+static std::atomic<int> g_profile_only{-1};
 static std::mutex g_mu;
 struct EvPair {
   cudaEvent_t a, b;
@@ -41,6 +42,8 @@ static bool take_event(cudaEvent_t *e) {
 ProfScope::ProfScope(int kernel_id, cudaStream_t st) : id_(kernel_id), st_(st), on_(false) {
   note_launch(1);
   if (!g_profile.load(std::memory_order_relaxed) || id_ < 0 || id_ >= RLOD_KERNEL_COUNT) return;
+  const int only = g_profile_only.load(std::memory_order_relaxed);
+  if (only >= 0 && only != id_) return;
   if (!take_event(&a_)) return;
   if (!take_event(&b_)) {
     cudaEventDestroy(a_);
@@ -81,6 +84,12 @@ RLOD_API const char *rlod_error_string(int code) {
 RLOD_API long long rlod_launch_count(void) { return g_launches.load(); }
 
 RLOD_API int rlod_profile_enable(int on) { return g_profile.exchange(on ? 1 : 0); }
+
+RLOD_API int rlod_profile_only(int kernel_id) {
+  if (kernel_id >= RLOD_KERNEL_COUNT) return RLOD_EINVAL;
+  g_profile_only.store(kernel_id < 0 ? -1 : kernel_id);
+  return RLOD_OK;
+}
 
 RLOD_API int rlod_profile_collect(int kernel_id, double *total_ms, int *launches) {
   if (kernel_id < 0 || kernel_id >= RLOD_KERNEL_COUNT || !total_ms || !launches) return RLOD_EINVAL;

@@ -32,6 +32,7 @@ SIGNATURES = {
     "rlod_error_string": (ctypes.c_char_p, [_I]),
     "rlod_launch_count": (_L, []),
     "rlod_profile_enable": (_I, [_I]),
+    "rlod_profile_only": (_I, [_I]),
     "rlod_profile_collect": (_I, [_I, _P, _P]),
     "rlod_nms_workspace_bytes": (_Z, [_I, _I]),
     "rlod_nms": (_I, [_P, _I, _I, _F, _I, _P, _P, _P, _Z, _P]),
