@@ -194,6 +194,16 @@ class ClockSampler:
         (self._armed.set if on else self._armed.clear)()
 
     def stop(self):
+        late = False
+        if not self.samples and self._thread.is_alive() and not self.err:
+            # the timed region ended before the first NVML query returned: one sample right after it
+            late = True
+            self._armed.set()
+            t0 = time.time()
+            while not self.samples and time.time() - t0 < 0.5:
+                time.sleep(0.002)
+            self._armed.clear()
+        self._late = late
         self._stop.set()
         self._thread.join(timeout=5)
         reasons = sorted(name for bit, name in self.REASONS.items() if self.mask & bit)
@@ -201,6 +211,8 @@ class ClockSampler:
                "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(self.samples)}
         if self.err:
             out["error"] = self.err
+        if getattr(self, "_late", False):
+            out["note"] = "sampled right after the timed region (it ended before the first NVML query returned)"
         return out
 
 
