@@ -118,6 +118,7 @@ static __global__ void k_roi_group_fixup(int R, int B, AlignWs ws) {
 // column (word 16 bits 20-22), so that a narrow roi does not impose its extra scatter rounds
 // on three wide ones.
 constexpr int kOrderThreads = 256;
+constexpr int kOrderMaxKeys = 64;    // nkeys: a power of two <= 64
 constexpr int kOrderMaxRois = 2048;  // per image, held in shared memory; longer lists take the slow path
 static __global__ void __launch_bounds__(kOrderThreads)
     k_roi_order_by_key(const int *__restrict__ ext, const int *__restrict__ order,
@@ -127,7 +128,7 @@ static __global__ void __launch_bounds__(kOrderThreads)
   // list) into shared memory, a per-key count gives the key offsets, then every roi finds its
   // rank among the rois of its key that precede it (stable)
   __shared__ unsigned short s_key[kOrderMaxRois];
-  __shared__ int s_tot[8], s_base[8];
+  __shared__ int s_tot[kOrderMaxKeys], s_base[kOrderMaxKeys];
   const int b = blockIdx.x, t = threadIdx.x, lane = t & 31;
   const int r0 = img_off[b], r1 = img_off[b + 1], n = r1 - r0;
   const unsigned full = 0xffffffffu;
@@ -150,7 +151,7 @@ static __global__ void __launch_bounds__(kOrderThreads)
     }
     return;
   }
-  if (t < 8) s_tot[t] = 0;
+  if (t < kOrderMaxKeys) s_tot[t] = 0;
   __syncthreads();
   for (int i = t; i < n; i += kOrderThreads) {
     const int key = (ext[(size_t)order[r0 + i] * 32 + word] >> shift) & (nkeys - 1);

@@ -24,7 +24,7 @@ namespace rlod {
 // each per (roi, 4 channels).
 // k_pool_plan: one thread per roi, the reference's bin arithmetic (:45-66) once per roi:
 //   record[0..6] hstart, [7..13] hend, [14..20] wstart, [21..27] wend (already clipped),
-//   [28] batch index or -1, [29] max rows of a bin, [30] max columns of a bin, [31] size key.
+//   [28] batch index or -1, [29] max rows of a bin, [30] max columns of a bin, [31] shape key.
 // ----------------------------------------------------------------------------------------
 constexpr int kPoolWarps = 8;
 constexpr int kPoolThreads = kPoolWarps * 32;
@@ -63,9 +63,11 @@ __global__ void k_pool_plan(const float *__restrict__ rois, int R, int B, int H,
   e[28] = bvalid ? bi : -1;
   e[29] = bvalid ? mr : 0;
   e[30] = bvalid ? mc : 0;
-  // size key (8 classes) so that the four rois a warp serves together scan similar windows
-  const int area = bvalid ? mr * mc : 0;
-  e[31] = area <= 1 ? 0 : min(7, 32 - __clz(area - 1));
+  // shape key (8 x 8 classes: bin rows, bin column steps of 4) so that the four rois a warp serves
+  // together scan the same window: the kernel's loops run to the LONGEST bin of the four in each
+  // direction, a tall-thin and a wide-short roi of equal area would cost their product
+  const int kr = bvalid ? min(mr, 8) : 0, kc = bvalid ? min((mc + 3) >> 2, 7) : 0;
+  e[31] = (kr > 0 ? kr - 1 : 0) * 8 + kc;
   roi_list_mark(rois, r, R, B, bvalid ? bi : 0, ws);
 }
 
@@ -288,7 +290,7 @@ RLOD_API int rlod_roi_pool_forward(const float *feat, const float *rois, int B, 
     RLOD_LAUNCH(RLOD_KERNEL_ROI_PLAN, st, k_pool_plan<<<(unsigned)cdiv(R, 128), 128, 0, st>>>(rois, R, B, H, W, spatial_scale, ws));
     RLOD_LAUNCH(RLOD_KERNEL_ROI_PLAN, st, k_roi_group_fixup<<<1, 32, 0, st>>>(R, B, ws));
     RLOD_LAUNCH(RLOD_KERNEL_ROI_PLAN, st,
-                k_roi_order_by_key<<<B, kOrderThreads, 0, st>>>(ws.plan, ws.order, ws.img_off, 31, 0, 8, ws.order2));
+                k_roi_order_by_key<<<B, kOrderThreads, 0, st>>>(ws.plan, ws.order, ws.img_off, 31, 0, 64, ws.order2));
     const int n_chunks = C / 4;
     cudaFuncSetAttribute(k_roi_pool7_fwd_planes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     RLOD_LAUNCH(RLOD_KERNEL_POOL_FWD, st,
