@@ -260,6 +260,64 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// backward, CTA = (roi, chunk of channels): everything that depends only on the roi -- the
+// rounded corners, the bin sizes and, per map row / column, the range of bins the reference's
+// gather would visit from there (roi_pooling_kernel.cu:161-186, same fp32 divisions) -- is
+// computed once per CTA into shared memory; an element then costs a few 32-bit operations, two
+// table lookups and at most one RED (the flat kernel above redoes ~250 instructions of 64-bit
+// index arithmetic and fp32 divisions per element).
+constexpr int kPoolBwdThreads = 256;
+constexpr int kPoolBwdChunk = 64;  // channels per CTA
+
+__global__ void __launch_bounds__(kPoolBwdThreads)
+    k_roi_pool_bwd_roi(const float *__restrict__ gout, const int *__restrict__ argmax,
+                       const float *__restrict__ rois, int C, int H, int W, int PH, int PW, float scale,
+                       long long n_bottom, float *__restrict__ gin) {
+  extern __shared__ int s_tab[];  // [H] rows then [W] columns: lo | hi << 8 | valid << 16
+  const int n = blockIdx.x, c0 = blockIdx.y * kPoolBwdChunk;
+  const int c1 = min(C, c0 + kPoolBwdChunk);
+  const float *roi = rois + (size_t)n * 5;
+  const int roi_start_w = (int)roundf(__fmul_rn(__ldg(roi + 1), scale));
+  const int roi_start_h = (int)roundf(__fmul_rn(__ldg(roi + 2), scale));
+  const int roi_end_w = (int)roundf(__fmul_rn(__ldg(roi + 3), scale));
+  const int roi_end_h = (int)roundf(__fmul_rn(__ldg(roi + 4), scale));
+  const int roi_width = max(roi_end_w - roi_start_w + 1, 1);
+  const int roi_height = max(roi_end_h - roi_start_h + 1, 1);
+  const float bin_h = __fdiv_rn((float)roi_height, (float)PH);
+  const float bin_w = __fdiv_rn((float)roi_width, (float)PW);
+  for (int i = threadIdx.x; i < H + W; i += kPoolBwdThreads) {
+    const bool row = i < H;
+    const int v = row ? i : i - H;
+    const int s0 = row ? roi_start_h : roi_start_w, s1 = row ? roi_end_h : roi_end_w;
+    const float bin = row ? bin_h : bin_w;
+    const int P = row ? PH : PW;
+    int lo = (int)floorf(__fdiv_rn((float)(v - s0), bin));
+    int hi = (int)ceilf(__fdiv_rn((float)(v - s0 + 1), bin));
+    lo = min(max(lo, 0), P), hi = min(max(hi, 0), P);
+    s_tab[i] = lo | (hi << 8) | ((v >= s0 && v <= s1) ? 1 << 16 : 0);
+  }
+  __syncthreads();
+  const int PHW = PH * PW, HW = H * W;
+  const float inv_w = 1.f / (float)W;
+  const size_t base = ((size_t)n * C + c0) * PHW;
+  const int count = (c1 - c0) * PHW;
+  for (int e = threadIdx.x; e < count; e += kPoolBwdThreads) {
+    const int a = __ldcs(argmax + base + e);
+    if (a < 0 || a >= n_bottom) continue;
+    const int p = e % PHW, ph = p / PW, pw = p - ph * PW;
+    // w = a % W, h = (a / W) % H (the reference's decomposition of the flat index, :143-146)
+    const int local = a % HW;
+    int h = (int)((float)local * inv_w);
+    int w = local - h * W;
+    if (w < 0) --h, w += W;
+    if (w >= W) ++h, w -= W;
+    const int th = s_tab[h], tw = s_tab[H + w];
+    if (!((th >> 16) & (tw >> 16) & 1)) continue;
+    if (ph < (th & 255) || ph >= ((th >> 8) & 255) || pw < (tw & 255) || pw >= ((tw >> 8) & 255)) continue;
+    atomicAdd(gin + a, __ldcs(gout + base + e));
+  }
+}
+
 }  // namespace rlod
 
 using namespace rlod;
@@ -322,6 +380,14 @@ RLOD_API int rlod_roi_pool_backward(const float *grad_out, const int *argmax, co
   const long long total = (long long)R * C * ph * pw;
   const long long blocks = cdiv(total, 256);
   const unsigned grid = (unsigned)(blocks < (1LL << 30) ? blocks : (1LL << 30));
+  const size_t tab = (size_t)(H + W) * sizeof(int);
+  if (ph <= 255 && pw <= 255 && tab <= 96 * 1024 && (long long)H * W < (1LL << 24) && (C + kPoolBwdChunk - 1) / kPoolBwdChunk <= 65535) {
+    if (tab > 48 * 1024) cudaFuncSetAttribute(k_roi_pool_bwd_roi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab);
+    RLOD_LAUNCH(RLOD_KERNEL_POOL_BWD, st,
+                k_roi_pool_bwd_roi<<<dim3((unsigned)R, (unsigned)((C + kPoolBwdChunk - 1) / kPoolBwdChunk)), kPoolBwdThreads,
+                                     tab, st>>>(grad_out, argmax, rois, C, H, W, ph, pw, spatial_scale, n_bottom, grad_in));
+    return launch_status();
+  }
   RLOD_LAUNCH(RLOD_KERNEL_POOL_BWD, st,
               k_roi_pool_bwd<<<grid, 256, 0, st>>>(grad_out, argmax, rois, C, H, W, ph, pw,
                                                    spatial_scale, total, n_bottom, grad_in));
