@@ -256,23 +256,36 @@ __global__ void __launch_bounds__(kCropBwdThreads)
     __syncthreads();  // tables ready / the previous tile is consumed
     {
       const float *src = gout + ((size_t)r * C + cb) * ghw;  // nc * ghw contiguous floats
+      // element e of the run lands at e + e / ghw (channel pitch ghw + 1): the quotient advances
+      // incrementally, a division per element was 16 % of the kernel's instructions
+      const int dq = kCropBwdThreads / ghw, dr = kCropBwdThreads - dq * ghw;
+      int c = t / ghw, rem = t - c * ghw;
       for (int e = t; e < nc * ghw; e += kCropBwdThreads) {
-        const int c = e / ghw;
         tile[e + c] = __ldcs(src + e);
+        c += dq, rem += dr;
+        if (rem >= ghw) rem -= ghw, ++c;
       }
     }
     __syncthreads();
     if (lane < nc) {
       float *plane = gfeat + ((size_t)b * C + cb + lane) * HW;
       const float *gl = tile + lane * tp;
+      const float inv_npx = 1.f / (float)nPx;
       for (int q = warp; q < nP; q += kCropBwdThreads / 32) {
-        const int j = q / nPx, i = q - j * nPx;
+        int j = (int)(((float)q + 0.5f) * inv_npx);  // q / nPx for q < 2^16, fixed up below
+        int i = q - j * nPx;
+        if (i < 0) --j, i += nPx;
+        if (i >= nPx) ++j, i -= nPx;
         const int yf = ya[j], ny = ya[H + j], xf = xa[i], nx = xa[W + i];
         const float *g = gl + yf * gw + xf;
         const float *wy = wys + (size_t)j * pitch_y, *wx = wxs + (size_t)i * pitch_x;
         float acc = 0.f;
+        // nx, ny are 1-5 for most pixels: plain loops (the compiler's 8/4/2/1 unrolling spent more
+        // instructions on remainder dispatch than on terms)
+#pragma unroll 1
         for (int u = 0; u < ny; ++u, g += gw) {
           const float wyu = wy[u];
+#pragma unroll 1
           for (int v = 0; v < nx; ++v) acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(wx[v], wyu), g[v]));
         }
         if (ny > 0 && nx > 0) atomicAdd(plane + (size_t)(py0 + j) * W + (px0 + i), acc);
