@@ -320,6 +320,8 @@ def run_ours(args, rank, local_rank, world):
     def before_timed():
         count0[0] = lib.rlod_launch_count()
         mstat["alloc0"] = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
+        if os.environ.get("RLOD_SAMPLER_EARLY"):
+            sampler.arm(True)
 
     ms = timed(lambda: device_step(dev_in, True, dev_in, True), args.steps, 1, step_marks,
                on_enqueued=lambda: sampler.arm(True), before_timed=before_timed)

@@ -1014,10 +1014,11 @@ __global__ void __launch_bounds__(kWalkThreads, 2)
   }
   __syncthreads();
   // planes -> HBM, coalesced per channel plane
-  for (int e = threadIdx.x; e < 4 * HW; e += kWalkThreads) {
-    const int c = e / HW, p = e - c * HW;
-    const int y = p / W, x = p - y * W;
-    dst[(size_t)c * HW + p] = reinterpret_cast<const float *>(planes4 + y * P + x)[c];
+  for (int cy = warp; cy < 4 * H; cy += kWalkWarps) {  // a warp takes (channel, row) runs: no division per element
+    const int c = cy / H, y = cy - c * H;
+    const float *src = reinterpret_cast<const float *>(planes4 + y * P) + c;
+    float *d = dst + (size_t)c * HW + (size_t)y * W;
+    for (int x = lane; x < W; x += 32) d[x] = src[4 * x];
   }
 }
 
