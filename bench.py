@@ -170,12 +170,10 @@ class ClockSampler:
             self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
             self._ready.set()
             while not self._stop.is_set():
-                # NVML queries share driver state with the launching thread: with a poller running (even one
-                # that had gone quiet a moment before) the first step after a synchronise sometimes found a
-                # kernel launch blocked for 15-70 ms.  So there is NO NVML activity from start-up until
-                # bench.py arms the sampler, which it does once every step of the timed region has been
-                # ENQUEUED: the GPU is still working through them (that is the load the clocks are sampled
-                # under), but no launch is left to be stalled.
+                # NVML is queried only while armed (the timed region).  (While a cudaMalloc still fell into
+                # the first timed step, concurrent NVML queries stretched that stall from milliseconds to tens
+                # of milliseconds -- the queries contend for driver locks; without the cudaMalloc 11 runs in a
+                # row were within 0.1 %.)
                 if self._armed.is_set():
                     self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
                     self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
@@ -320,11 +318,10 @@ def run_ours(args, rank, local_rank, world):
     def before_timed():
         count0[0] = lib.rlod_launch_count()
         mstat["alloc0"] = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
-        if os.environ.get("RLOD_SAMPLER_EARLY"):
-            sampler.arm(True)
+        sampler.arm(True)
 
     ms = timed(lambda: device_step(dev_in, True, dev_in, True), args.steps, 1, step_marks,
-               on_enqueued=lambda: sampler.arm(True), before_timed=before_timed)
+               before_timed=before_timed)
     launches0 = count0[0]
     mallocs_in_region = torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - mstat["alloc0"]
     prof_steps = args.steps + 1  # the per-kernel event times also cover that last warm-up step
