@@ -362,11 +362,19 @@ __global__ void __launch_bounds__(128, 6)
   // order (two lanes may not hit one pixel in the same request)
   if (bwd) best = 0u, c0 = c1 = 0;
   const int nat = min(c0, c1);
+#ifdef RLOD_NO_SEARCH  // ablation (profiles/experiments/README.md): natural tap order only
+  if (false) {
+#else
   if (ok0 && lb0 < nat && c0 > lb0) {  // warp-uniform
+#endif
     const unsigned q = span0 < 64 ? tap_order_search<false>(L0, R0, base0, lane) : tap_order_search<true>(L0, R0, base0, lane);
     best = min(best, (((q >> 8) * (unsigned)nl[0]) << 9) | (q & 255u));
   }
+#ifdef RLOD_NO_SEARCH
+  if (false) {
+#else
   if (ok1 && lb1 < nat && c1 > lb1) {
+#endif
     const unsigned q = span1 < 64 ? tap_order_search<false>(L1, R1, base1, lane) : tap_order_search<true>(L1, R1, base1, lane);
     best = min(best, (((q >> 8) * (unsigned)nl[1]) << 9) | 256u | (q & 255u));
   }
