@@ -321,8 +321,37 @@ def bbiou(dt, gt, iscrowd=None):
 MODE_COCO, MODE_RCNN = 0, 1
 
 
+WTRANS_IDENTITY, WTRANS_EXP_ABS = 0, 1
+
+
+def action_reward_f64(boxes, gt, act, crowd=None, iou_thres=0.0, pos_wratio=1.0, neg_wratio=1.0,
+                      wtrans=WTRANS_EXP_ABS):
+    """The reference loop (RL_coco_dataset.py:119-137) over float64 xywh boxes, as the json
+    holds them: pure numpy over bbiou, small cases only."""
+    boxes, gt = np.asarray(boxes, np.float64), np.asarray(gt, np.float64)
+    B, N, _ = boxes.shape
+    A = act.shape[0]
+    reward = np.empty((B, N, A), np.float32)
+    label = np.empty((B, N, A), np.float32)
+    weight = np.empty((B, N, A), np.float32)
+    for b in range(B):
+        cr = np.asarray(crowd[b], np.uint8) if crowd is not None else np.zeros(gt.shape[1], np.uint8)
+        for n in range(N):
+            bbox = boxes[b, n]
+            w, h = bbox[2], bbox[3]
+            o0 = bbiou(bbox[None], gt[b], cr).max()
+            for a in range(A):
+                nb = bbox + act[a] * np.array([w, h, w, h])
+                d = bbiou(nb[None], gt[b], cr).max() - o0
+                pos = d > iou_thres
+                reward[b, n, a] = d
+                label[b, n, a] = 1.0 if pos else -1.0
+                weight[b, n, a] = (np.exp(abs(d)) if wtrans == WTRANS_EXP_ABS else d) * (pos_wratio if pos else neg_wratio)
+    return reward, label, weight
+
+
 def action_reward(boxes, gt, act, crowd=None, ngt=None, mode=MODE_COCO, iou_thres=0.0,
-                  pos_wratio=1.0, neg_wratio=1.0):
+                  pos_wratio=1.0, neg_wratio=1.0, wtrans=WTRANS_EXP_ABS):
     boxes = _f32(boxes)
     gt = _f32(gt)
     act = _f32(act)
@@ -335,21 +364,23 @@ def action_reward(boxes, gt, act, crowd=None, ngt=None, mode=MODE_COCO, iou_thre
     label = np.empty((B, N, A), dtype=np.float32)
     weight = np.empty((B, N, A), dtype=np.float32)
     lib().orc_action_reward(_p(boxes, c_f), _p(gt, c_f), _p(cr, c_u8), _p(ng, c_i), _p(act, c_f), B, N, A, G,
-                            int(mode), ctypes.c_float(iou_thres), ctypes.c_float(pos_wratio),
+                            int(mode), int(wtrans), ctypes.c_float(iou_thres), ctypes.c_float(pos_wratio),
                             ctypes.c_float(neg_wratio), _p(reward, c_f), _p(label, c_f), _p(weight, c_f))
     return reward, label, weight
 
 
 def move_from_act(bboxes, preds, targets, act, maxk):
-    """Action.move_from_act (action.py:25-59) with the documented tie rule: descending by
-    pred, ties -> lower flat index first (numpy's quicksort tie order is unpinned)."""
+    """Action.move_from_act (action.py:25-59).  Visit order = np.flip(np.argsort(pred)) as in
+    the reference (:44) with the sort pinned to a stable one: among equal preds the HIGHER flat
+    index comes first (numpy's default introsort is stable for short / presorted runs and
+    unspecified beyond; tests/golden pins the tied case on the reference's own code)."""
     bboxes = np.array(bboxes, dtype=np.float32, copy=True)
     b, n, _ = bboxes.shape
     A = act.shape[0]
     correct = 0
     for bid in range(b):
         flat = preds[bid].reshape(-1)
-        inds = np.argsort(-flat.astype(np.float64), kind="stable")
+        inds = np.flip(np.argsort(flat, kind="stable"), axis=0)
         cnt = 0
         vis = np.zeros(n, dtype=bool)
         for num in inds:
@@ -569,7 +600,8 @@ def roi_crop_bwd(grad_out, grid_yx, feat_shape):
     return gin
 
 
-def rl_labels(dets, det_cat, ndet, gt, gt_cat, crowd, ngt, act, iou_thres=0.0, pos_wratio=1.0, neg_wratio=1.0):
+def rl_labels(dets, det_cat, ndet, gt, gt_cat, crowd, ngt, act, iou_thres=0.0, pos_wratio=1.0, neg_wratio=1.0,
+              wtrans=WTRANS_EXP_ABS):
     """Label tensor (B,N,A,3) = (act_id, label, weight) of a collated RL batch:
     lib/datasets/RL_coco_dataset.py:107-137 per box (category-specific gt, none -> [[0,0,0,0]],
     bbIou fp64) + the zero padding of lib/datasets/RL_coco_loader.py:66-72."""
@@ -589,7 +621,8 @@ def rl_labels(dets, det_cat, ndet, gt, gt_cat, crowd, ngt, act, iou_thres=0.0, p
                 nb = bbox + act[a].astype(np.float64) * np.array([w, h, w, h])
                 d = bbiou(nb[None], gtb, cr).max() - o0
                 pos = d > iou_thres
-                out[b, n, a] = (a, 1.0 if pos else -1.0, np.exp(abs(d)) * (pos_wratio if pos else neg_wratio))
+                wt = np.exp(abs(d)) if wtrans == WTRANS_EXP_ABS else d
+                out[b, n, a] = (a, 1.0 if pos else -1.0, wt * (pos_wratio if pos else neg_wratio))
     return out
 
 

@@ -610,7 +610,7 @@ ORC_API void orc_bbiou(const double *dt, const double *gt, long m, long n,
  * boxes (B,N,4) f32, gt (B,G,4) f32, crowd (B,G) u8 or NULL, ngt (B) int or NULL (valid gt
  * count per image; 0 -> one all-zero gt, :113-117), act (A,4) f32.
  * reward (B,N,A) f32 = max_g IoU(new) - max_g IoU(orig) (:126).  Optional label (+1/-1 by
- * reward > iou_thres, :128-134) and weight = exp(|reward|) * (pos|neg)_wratio (config.py:48-51).
+ * reward > iou_thres, :128-134) and weight = wtrans(reward) * (pos|neg)_wratio.
  */
 static double orc_max_bbiou(const double *dt, const float *gt, const unsigned char *crowd,
                             int ng) {
@@ -647,8 +647,8 @@ static float orc_max_overlap_f32(const float *box, const float *gt, int ng) {
 
 ORC_API void orc_action_reward(const float *boxes, const float *gt, const unsigned char *crowd,
                                const int *ngt, const float *act, int B, int N, int A, int G,
-                               int mode, float iou_thres, float pos_wratio, float neg_wratio,
-                               float *reward, float *label, float *weight) {
+                               int mode, int wtrans, float iou_thres, float pos_wratio,
+                               float neg_wratio, float *reward, float *label, float *weight) {
 #pragma omp parallel for schedule(static)
   for (int b = 0; b < B; ++b) {
     const float *gtb = gt + (size_t)b * G * 4;
@@ -678,7 +678,10 @@ ORC_API void orc_action_reward(const float *boxes, const float *gt, const unsign
         /* label / weight from the un-rounded reward (fp64 in coco mode, fp32 in rcnn mode) */
         int pos = r > (double)iou_thres;
         if (label) label[oi] = pos ? 1.f : -1.f;
-        if (weight) weight[oi] = (float)(exp(fabs(r)) * (double)(pos ? pos_wratio : neg_wratio));
+        /* weight = wtrans(delta_iou) * ratio (:130-135); wtrans 0 = Identify (action.py:7-10),
+         * 1 = exp(|x|) (config.py:48-51) */
+        if (weight)
+          weight[oi] = (float)((wtrans == 1 ? exp(fabs(r)) : r) * (double)(pos ? pos_wratio : neg_wratio));
       }
     }
   }

@@ -10,7 +10,8 @@
 //     136-166), the action applied to (x1, y1, w, h).
 // k_move_from_act: Action.move_from_act (lib/model/Reinforcement/action.py:25-59) on the
 // device, one CTA per image: per-box best action, bitonic sort of the boxes by
-// (pred descending, flat index ascending), the first maxk boxes move if their target is 1.
+// (pred descending, flat index DESCENDING among equal preds = np.flip(np.argsort(kind='stable'))),
+// the first maxk boxes move if their target is 1.
 #include "rlod_common.cuh"
 
 namespace rlod {
@@ -26,7 +27,8 @@ __device__ __forceinline__ double bbiou_f64(const double *D, const double *G, bo
   return __ddiv_rn(i, u);
 }
 
-__device__ __forceinline__ double max_bbiou(const double *D, const float *__restrict__ gt,
+template <typename T>
+__device__ __forceinline__ double max_bbiou(const double *D, const T *__restrict__ gt,
                                             const unsigned char *__restrict__ crowd, int ng) {
   if (ng <= 0) {
     const double z[4] = {0., 0., 0., 0.};
@@ -40,6 +42,15 @@ __device__ __forceinline__ double max_bbiou(const double *D, const float *__rest
     if (o > best) best = o;
   }
   return best;
+}
+
+// Action.wtrans (action.py:7-10 default Identify; config.py:48-51 exp(|x|)) applied to delta_iou,
+// times the positive / negative ratio (RL_coco_dataset.py:128-135).  RLOD_WTRANS_RAW hands
+// delta_iou itself back so that the caller can apply any other callable.
+__device__ __forceinline__ float label_weight(double r, int wtrans, double ratio) {
+  if (wtrans == RLOD_WTRANS_EXP_ABS) return (float)(exp(fabs(r)) * ratio);
+  if (wtrans == RLOD_WTRANS_IDENTITY) return (float)(r * ratio);
+  return (float)r;
 }
 
 __device__ __forceinline__ float overlap_f32(const float *a, const float *g) {
@@ -68,10 +79,11 @@ __device__ __forceinline__ float max_overlap_f32(const float *a, const float *__
   return best;
 }
 
+template <typename T>
 __global__ void __launch_bounds__(256)
-    k_action_reward(const float *__restrict__ boxes, const float *__restrict__ gt,
+    k_action_reward(const T *__restrict__ boxes, const T *__restrict__ gt,
                     const unsigned char *__restrict__ crowd, const int *__restrict__ ngt,
-                    const float *__restrict__ act, int B, int N, int A, int G, int mode,
+                    const float *__restrict__ act, int B, int N, int A, int G, int mode, int wtrans,
                     float iou_thres, float pos_wratio, float neg_wratio, float *__restrict__ reward,
                     float *__restrict__ label, float *__restrict__ weight) {
   const long long total = (long long)B * N * A;
@@ -80,12 +92,12 @@ __global__ void __launch_bounds__(256)
     const int a = (int)(idx % A);
     const long long bn = idx / A;
     const int b = (int)(bn / N);
-    const float *bx = boxes + bn * 4;
-    const float *gtb = gt + (size_t)b * G * 4;
+    const T *bx = boxes + bn * 4;
+    const T *gtb = gt + (size_t)b * G * 4;
     const unsigned char *crb = crowd ? crowd + (size_t)b * G : nullptr;
     int ng = ngt ? __ldg(ngt + b) : G;
     if (ng > G) ng = G;
-    const float x0 = __ldg(bx), x1 = __ldg(bx + 1), x2 = __ldg(bx + 2), x3 = __ldg(bx + 3);
+    const T x0 = __ldg(bx), x1 = __ldg(bx + 1), x2 = __ldg(bx + 2), x3 = __ldg(bx + 3);
     const float a0 = __ldg(act + a * 4), a1 = __ldg(act + a * 4 + 1);
     const float a2 = __ldg(act + a * 4 + 2), a3 = __ldg(act + a * 4 + 3);
     double r;
@@ -100,7 +112,7 @@ __global__ void __launch_bounds__(256)
                             __dadd_rn(dt[3], __dmul_rn((double)a3, h))};
       r = __dsub_rn(max_bbiou(nb, gtb, crb, ng), max_bbiou(dt, gtb, crb, ng));
       rf = (float)r;
-    } else {
+    } else if constexpr (sizeof(T) == 4) {
       const float w = __fadd_rn(__fsub_rn(x2, x0), 1.f), h = __fadd_rn(__fsub_rn(x3, x1), 1.f);
       const float nx = __fadd_rn(x0, __fmul_rn(a0, w)), ny = __fadd_rn(x1, __fmul_rn(a1, h));
       const float nw = __fadd_rn(w, __fmul_rn(a2, w)), nh = __fadd_rn(h, __fmul_rn(a3, h));
@@ -108,11 +120,13 @@ __global__ void __launch_bounds__(256)
       const float ob[4] = {x0, x1, x2, x3};
       rf = __fsub_rn(max_overlap_f32(nb, gtb, ng), max_overlap_f32(ob, gtb, ng));
       r = rf;
+    } else {
+      r = 0., rf = 0.f;  // fp64 boxes exist in COCO mode only (host-checked)
     }
     reward[idx] = rf;
     const bool pos = r > (double)iou_thres;
     if (label) label[idx] = pos ? 1.f : -1.f;
-    if (weight) weight[idx] = (float)(exp(fabs(r)) * (double)(pos ? pos_wratio : neg_wratio));
+    if (weight) weight[idx] = label_weight(r, wtrans, (double)(pos ? pos_wratio : neg_wratio));
   }
 }
 
@@ -121,11 +135,12 @@ __global__ void __launch_bounds__(256)
 // labels (B, N, A, 3) = (act_id, label, weight), zero rows for padded boxes.  Per box only the
 // ground truth of ITS category counts (RL_coco_dataset.py:108-117: gt_boxes[img_id, cat_id]);
 // none -> the single all-zero gt.  IoU = pycocotools bbIou, fp64 (xywh boxes).
+template <typename T>
 __global__ void __launch_bounds__(256)
-    k_rl_labels(const float *__restrict__ dets, int det_stride, const int *__restrict__ det_cat,
-                const int *__restrict__ ndet, const float *__restrict__ gt, const int *__restrict__ gt_cat,
+    k_rl_labels(const T *__restrict__ dets, int det_stride, const int *__restrict__ det_cat,
+                const int *__restrict__ ndet, const T *__restrict__ gt, const int *__restrict__ gt_cat,
                 const unsigned char *__restrict__ crowd, const int *__restrict__ ngt,
-                const float *__restrict__ act, int B, int N, int A, int G, float iou_thres,
+                const float *__restrict__ act, int B, int N, int A, int G, int wtrans, float iou_thres,
                 float pos_wratio, float neg_wratio, float *__restrict__ labels) {
   const long long total = (long long)B * N * A;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -138,7 +153,7 @@ __global__ void __launch_bounds__(256)
       o[0] = 0.f, o[1] = 0.f, o[2] = 0.f;  // collate pads with zeros (:70-72)
       continue;
     }
-    const float *bx = dets + bn * det_stride;
+    const T *bx = dets + bn * det_stride;
     const int cat = det_cat ? __ldg(det_cat + bn) : 0;
     int ng = ngt ? __ldg(ngt + b) : G;
     if (ng > G) ng = G;
@@ -152,7 +167,7 @@ __global__ void __launch_bounds__(256)
     bool any = false;
     for (int g = 0; g < ng; ++g) {
       if (gt_cat && __ldg(gt_cat + (size_t)b * G + g) != cat) continue;
-      const float *gp = gt + ((size_t)b * G + g) * 4;
+      const T *gp = gt + ((size_t)b * G + g) * 4;
       const double Gb[4] = {(double)__ldg(gp), (double)__ldg(gp + 1), (double)__ldg(gp + 2), (double)__ldg(gp + 3)};
       const bool cr = crowd ? (crowd[(size_t)b * G + g] != 0) : false;
       const double o0 = bbiou_f64(dt, Gb, cr), o1 = bbiou_f64(nb, Gb, cr);
@@ -168,7 +183,7 @@ __global__ void __launch_bounds__(256)
     const bool pos = r > (double)iou_thres;
     o[0] = (float)a;
     o[1] = pos ? 1.f : -1.f;
-    o[2] = (float)(exp(fabs(r)) * (double)(pos ? pos_wratio : neg_wratio));
+    o[2] = label_weight(r, wtrans, (double)(pos ? pos_wratio : neg_wratio));
   }
 }
 
@@ -194,17 +209,19 @@ __global__ void __launch_bounds__(kMoveThreads)
   for (int n = t; n < np2; n += kMoveThreads) {
     unsigned long long key = ~0ull;
     if (n < N) {
-      // best action of the box: max pred, ties -> lowest action id (= lowest flat index)
+      // best action of the box: max pred; among equal preds the reference's
+      // np.flip(np.argsort(...)) visits the HIGHER flat index first wherever the sort is stable
+      // (action.py:44), so ties go to the highest action id, then to the highest box
       int best = 0;
       float bv = __ldg(pr + (size_t)n * A);
       for (int a = 1; a < A; ++a) {
         const float v = __ldg(pr + (size_t)n * A + a);
-        if (v > bv) {
+        if (v >= bv) {
           bv = v;
           best = a;
         }
       }
-      key = ((unsigned long long)desc_key32(bv) << 32) | (unsigned)(n * A + best);
+      key = ((unsigned long long)desc_key32(bv) << 32) | (0xffffffffu - (unsigned)(n * A + best));
     }
     mkeys[n] = key;
   }
@@ -224,7 +241,7 @@ __global__ void __launch_bounds__(kMoveThreads)
   const int take = min(maxk, N);
   int local = 0;
   for (int i = t; i < take; i += kMoveThreads) {
-    const unsigned flat = (unsigned)(mkeys[i] & 0xffffffffull);
+    const unsigned flat = 0xffffffffu - (unsigned)(mkeys[i] & 0xffffffffull);
     const int n = (int)(flat / (unsigned)A), a = (int)(flat % (unsigned)A);
     if (__ldg(targets + ((size_t)b * N + n) * A + a) == 1.f) {
       ++local;
@@ -261,21 +278,30 @@ __global__ void __launch_bounds__(kMoveThreads)
 
 using namespace rlod;
 
-RLOD_API int rlod_action_reward(const float *boxes, const float *gt, const unsigned char *crowd,
-                                const int *ngt, const float *act, int B, int N, int A, int G,
-                                int mode, float iou_thres, float pos_wratio, float neg_wratio,
-                                float *reward, float *label, float *weight, rlod_stream_t stream) {
+RLOD_API int rlod_action_reward(const void *boxes, const void *gt, int f64_boxes,
+                                const unsigned char *crowd, const int *ngt, const float *act, int B,
+                                int N, int A, int G, int mode, int wtrans, float iou_thres,
+                                float pos_wratio, float neg_wratio, float *reward, float *label,
+                                float *weight, rlod_stream_t stream) {
   if (B < 0 || N < 0 || A < 0 || G < 0) return RLOD_EINVAL;
   if (mode != RLOD_IOU_COCO && mode != RLOD_IOU_RCNN) return RLOD_EINVAL;
+  if (wtrans < RLOD_WTRANS_IDENTITY || wtrans > RLOD_WTRANS_RAW) return RLOD_EINVAL;
+  if (f64_boxes && mode != RLOD_IOU_COCO) return RLOD_EINVAL;
   if (B == 0 || N == 0 || A == 0) return RLOD_OK;
   if (!boxes || !act || !reward) return RLOD_EINVAL;
   if (G > 0 && !gt) return RLOD_EINVAL;
   const long long total = (long long)B * N * A;
   const long long blocks = cdiv(total, 256);
   const unsigned grid = (unsigned)(blocks < (1LL << 30) ? blocks : (1LL << 30));
-  RLOD_LAUNCH(RLOD_KERNEL_REWARD, (cudaStream_t)stream, k_action_reward<<<grid, 256, 0, (cudaStream_t)stream>>>(boxes, gt, crowd, ngt, act, B, N, A, G,
-                                                          mode, iou_thres, pos_wratio, neg_wratio,
-                                                          reward, label, weight));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (f64_boxes)
+    RLOD_LAUNCH(RLOD_KERNEL_REWARD, st, k_action_reward<double><<<grid, 256, 0, st>>>(
+        (const double *)boxes, (const double *)gt, crowd, ngt, act, B, N, A, G, mode, wtrans, iou_thres,
+        pos_wratio, neg_wratio, reward, label, weight));
+  else
+    RLOD_LAUNCH(RLOD_KERNEL_REWARD, st, k_action_reward<float><<<grid, 256, 0, st>>>(
+        (const float *)boxes, (const float *)gt, crowd, ngt, act, B, N, A, G, mode, wtrans, iou_thres,
+        pos_wratio, neg_wratio, reward, label, weight));
   return launch_status();
 }
 
@@ -288,26 +314,33 @@ RLOD_API int rlod_move_from_act(float *boxes, int box_stride, int corners, const
   if (N > kMoveMaxN || (long long)N * A >= (1LL << 31)) return RLOD_EUNSUPPORTED;
   int np2 = 2;
   while (np2 < N) np2 <<= 1;
-  k_move_from_act<<<B, kMoveThreads, (size_t)np2 * sizeof(unsigned long long),
-                    (cudaStream_t)stream>>>(boxes, box_stride, corners, preds, targets, act, N, A,
-                                            maxk, np2, correct);
+  RLOD_LAUNCH(RLOD_KERNEL_MOVE, (cudaStream_t)stream,
+              k_move_from_act<<<B, kMoveThreads, (size_t)np2 * sizeof(unsigned long long),
+                                (cudaStream_t)stream>>>(boxes, box_stride, corners, preds, targets, act, N, A,
+                                                        maxk, np2, correct));
   return launch_status();
 }
 
-RLOD_API int rlod_rl_labels(const float *dets, int det_stride, const int *det_cat, const int *ndet,
-                            const float *gt, const int *gt_cat, const unsigned char *crowd,
-                            const int *ngt, const float *act, int B, int N, int A, int G,
-                            float iou_thres, float pos_wratio, float neg_wratio, float *labels,
-                            rlod_stream_t stream) {
+RLOD_API int rlod_rl_labels(const void *dets, int det_stride, int f64_boxes, const int *det_cat,
+                            const int *ndet, const void *gt, const int *gt_cat,
+                            const unsigned char *crowd, const int *ngt, const float *act, int B, int N,
+                            int A, int G, int wtrans, float iou_thres, float pos_wratio,
+                            float neg_wratio, float *labels, rlod_stream_t stream) {
   if (B < 0 || N < 0 || A < 0 || G < 0 || det_stride < 4) return RLOD_EINVAL;
+  if (wtrans < RLOD_WTRANS_IDENTITY || wtrans > RLOD_WTRANS_RAW) return RLOD_EINVAL;
   if (B == 0 || N == 0 || A == 0) return RLOD_OK;
   if (!dets || !act || !labels || (G > 0 && !gt)) return RLOD_EINVAL;
   const long long total = (long long)B * N * A;
   const long long blocks = (total + 255) / 256;
   const unsigned grid = (unsigned)(blocks < (1LL << 20) ? blocks : (1LL << 20));
-  RLOD_LAUNCH(RLOD_KERNEL_REWARD, (cudaStream_t)stream,
-              k_rl_labels<<<grid, 256, 0, (cudaStream_t)stream>>>(dets, det_stride, det_cat, ndet, gt, gt_cat, crowd,
-                                                                 ngt, act, B, N, A, G, iou_thres, pos_wratio,
-                                                                 neg_wratio, labels));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (f64_boxes)
+    RLOD_LAUNCH(RLOD_KERNEL_REWARD, st, k_rl_labels<double><<<grid, 256, 0, st>>>(
+        (const double *)dets, det_stride, det_cat, ndet, (const double *)gt, gt_cat, crowd, ngt, act, B, N, A, G,
+        wtrans, iou_thres, pos_wratio, neg_wratio, labels));
+  else
+    RLOD_LAUNCH(RLOD_KERNEL_REWARD, st, k_rl_labels<float><<<grid, 256, 0, st>>>(
+        (const float *)dets, det_stride, det_cat, ndet, (const float *)gt, gt_cat, crowd, ngt, act, B, N, A, G,
+        wtrans, iou_thres, pos_wratio, neg_wratio, labels));
   return launch_status();
 }

@@ -850,24 +850,26 @@ __device__ __noinline__ void row_flush(float4 v, int need, uint32_t p0, uint32_t
   while (__any_sync(full, need)) {
     int got = 0;
     if (need && k == 0) {
-      asm volatile("atom.shared.cas.b32 %0, [%1], 0, 1;" : "=r"(got) : "r"(lock_addr) : "memory");
+      asm volatile("atom.acquire.cta.shared.cas.b32 %0, [%1], 0, 1;" : "=r"(got) : "r"(lock_addr) : "memory");
       got = got == 0;
     }
     got = __shfl_sync(full, got, 0, 8);
     const bool go = need && got;
+    __syncwarp();  // the leader's acquire is ordered before every lane's plane accesses
     if (maxrank_warp == 0) {
       smem_axpy4_if(p0, w0, v, go);
+      __syncwarp();  // a lane's second tap may be its neighbour's first
       smem_axpy4_if(p1, w1, v, go);
     } else {
       for (int rnd = 0; rnd <= maxrank_warp; ++rnd) {
         smem_axpy4_if(p0, w0, v, go && rank == rnd);
+        __syncwarp();
         smem_axpy4_if(p1, w1, v, go && rank == rnd);
+        __syncwarp();
       }
     }
-    __syncwarp();
-    // shared-memory accesses of one warp are performed in program order: a plain store after
-    // the updates releases the lock
-    if (go && k == 0) asm volatile("st.volatile.shared.b32 [%0], %1;" ::"r"(lock_addr), "r"(0) : "memory");
+    __syncwarp();  // every lane's updates happen before the leader's release
+    if (go && k == 0) asm volatile("st.release.cta.shared.b32 [%0], %1;" ::"r"(lock_addr), "r"(0) : "memory");
     need = need && !got;
   }
 }

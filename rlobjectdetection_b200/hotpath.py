@@ -8,7 +8,7 @@ import collections
 import torch
 
 from .model import _backend as be
-from .model.Reinforcement.action import Action
+from .model.Reinforcement.action import Action, exp_abs
 from .model.Reinforcement.reward import IOU_RCNN, action_rewards
 from .model.roi_align.modules.roi_align import RoIAlignAvg
 from .model.rpn.proposal_layer import _ProposalLayer
@@ -38,7 +38,7 @@ class DetectRefineStep:
                  outputs=("rois", "reward", "label", "weight", "refined", "moved")):
         self.proposal = _ProposalLayer(feat_stride, list(scales), list(ratios))
         self.align = RoIAlignAvg(pool, pool, 1.0 / feat_stride)
-        self.action = Action(list(act_delta))
+        self.action = Action(list(act_delta), wtrans=exp_abs)  # Config.act_wtrans (config.py:48-51)
         self.cfg_key = cfg_key
         self.pool = pool
         self.scale = 1.0 / feat_stride

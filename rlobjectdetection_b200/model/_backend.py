@@ -20,6 +20,7 @@ KERNELS = ["align_fwd", "align_bwd", "align_fwd_generic", "align_bwd_generic", "
            "nms_scan", "nms_small", "proposal_sort", "pool_fwd", "pool_bwd", "boxes", "reward", "move",
            "nms_lazy", "detect", "crop", "targets"]
 IOU_COCO, IOU_RCNN = 0, 1
+WTRANS_IDENTITY, WTRANS_EXP_ABS, WTRANS_RAW = 0, 1, 2
 SORT_MAX = 16384  # rlod_proposal_forward: min(pre_nms_topN, H*W*A) limit
 
 _c_void_p, _c_int, _c_float, _c_size_t, _c_ll = (ctypes.c_void_p, ctypes.c_int, ctypes.c_float,
@@ -52,7 +53,7 @@ SIGNATURES = {
     "rlod_clip_boxes": (_I, [_P, _P, _I, _L, _I, _P]),
     "rlod_bbox_overlaps": (_I, [_P, _P, _I, _I, _P, _P]),
     "rlod_bbox_overlaps_batch": (_I, [_P, _L, _I, _P, _I, _I, _I, _I, _P, _P]),
-    "rlod_action_reward": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _F, _P, _P, _P,
+    "rlod_action_reward": (_I, [_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _F, _F, _P, _P, _P,
                                 _P]),
     "rlod_move_from_act": (_I, [_P, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "rlod_proposal_target": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
@@ -62,7 +63,7 @@ SIGNATURES = {
     "rlod_affine_grid": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
     "rlod_roi_crop_forward": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "rlod_roi_crop_backward": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
-    "rlod_rl_labels": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _F, _P, _P]),
+    "rlod_rl_labels": (_I, [_P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _F, _P, _P]),
     "rlod_detect_postprocess": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _F, _F, _I, _P, _P, _P]),
 }
 
@@ -296,12 +297,22 @@ def proposal_forward(scores, deltas, im_info, anchors, feat_stride, pre_nms_topN
     return rois
 
 
+def _boxes_pair(boxes, gt, mode):
+    """fp64 rows stay fp64 in COCO mode (the reference's json boxes are float64); anything
+    else is computed from fp32 rows."""
+    f64 = mode == IOU_COCO and (boxes.dtype == torch.float64 or gt.dtype == torch.float64)
+    if f64:
+        return boxes.double().contiguous(), gt.double().contiguous(), 1
+    return f32c(boxes), f32c(gt), 0
+
+
 def action_reward(boxes, gt, act, crowd=None, ngt=None, mode=IOU_COCO, iou_thres=0.0,
-                  pos_wratio=1.0, neg_wratio=1.0, want_labels=True):
+                  pos_wratio=1.0, neg_wratio=1.0, want_labels=True, wtrans=WTRANS_EXP_ABS):
     """rlod_action_reward.  boxes (B,N,4), gt (B,G,4), act (A,4) -> reward[, label, weight]
-    each (B,N,A)."""
+    each (B,N,A).  float64 boxes / gt are kept in fp64 (COCO mode)."""
     require_cuda("action_reward", boxes, gt, act, crowd, ngt)
-    boxes, gt, act = f32c(boxes), f32c(gt), f32c(act)
+    boxes, gt, f64 = _boxes_pair(boxes, gt, mode)
+    act = f32c(act)
     B, N, _ = boxes.shape
     G = gt.size(1)
     A = act.size(0)
@@ -314,8 +325,8 @@ def action_reward(boxes, gt, act, crowd=None, ngt=None, mode=IOU_COCO, iou_thres
     label = torch.empty_like(reward) if want_labels else None
     weight = torch.empty_like(reward) if want_labels else None
     with torch.cuda.device(dev):
-        check(lib().rlod_action_reward(ptr(boxes), ptr(gt), ptr(crowd), ptr(ngt), ptr(act), B, N, A,
-                                       G, int(mode), float(iou_thres), float(pos_wratio),
+        check(lib().rlod_action_reward(ptr(boxes), ptr(gt), f64, ptr(crowd), ptr(ngt), ptr(act), B, N, A,
+                                       G, int(mode), int(wtrans), float(iou_thres), float(pos_wratio),
                                        float(neg_wratio), ptr(reward), ptr(label), ptr(weight),
                                        stream_of(boxes)), "rlod_action_reward")
     if want_labels:
@@ -374,11 +385,13 @@ def detect_postprocess(rois, cls_prob, bbox_pred, im_info, thresh=0.0, nms_thres
 
 
 def rl_labels(dets, gt, act, det_cat=None, ndet=None, gt_cat=None, crowd=None, ngt=None, iou_thres=0.0,
-              pos_wratio=1.0, neg_wratio=1.0):
+              pos_wratio=1.0, neg_wratio=1.0, wtrans=WTRANS_EXP_ABS):
     """rlod_rl_labels: labels (B,N,A,3) = (act_id, label, weight) of a collated RL batch.
-    dets (B,N,>=4) xywh rows, gt (B,G,4) xywh; categories int32; crowd uint8."""
+    dets (B,N,>=4) xywh rows, gt (B,G,4) xywh (float64 rows are kept in fp64); categories int32;
+    crowd uint8."""
     require_cuda("rl_labels", dets, gt, act)
-    dets, gt, act = f32c(dets), f32c(gt), f32c(act)
+    dets, gt, f64 = _boxes_pair(dets, gt, IOU_COCO)
+    act = f32c(act)
     B, N, S = dets.shape
     G, A = gt.size(1), act.size(0)
     i32 = lambda t: None if t is None else t.to(device=dets.device, dtype=torch.int32).contiguous()  # noqa: E731
@@ -386,8 +399,8 @@ def rl_labels(dets, gt, act, det_cat=None, ndet=None, gt_cat=None, crowd=None, n
     crowd = None if crowd is None else crowd.to(device=dets.device, dtype=torch.uint8).contiguous()
     labels = torch.empty(B, N, A, 3, dtype=torch.float32, device=dets.device)
     with torch.cuda.device(dets.device):
-        check(lib().rlod_rl_labels(ptr(dets), S, ptr(det_cat), ptr(ndet), ptr(gt), ptr(gt_cat), ptr(crowd), ptr(ngt),
-                                   ptr(act), B, N, A, G, float(iou_thres), float(pos_wratio), float(neg_wratio),
+        check(lib().rlod_rl_labels(ptr(dets), S, f64, ptr(det_cat), ptr(ndet), ptr(gt), ptr(gt_cat), ptr(crowd), ptr(ngt),
+                                   ptr(act), B, N, A, G, int(wtrans), float(iou_thres), float(pos_wratio), float(neg_wratio),
                                    ptr(labels), stream_of(dets)), "rlod_rl_labels")
     return labels
 

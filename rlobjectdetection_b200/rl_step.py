@@ -11,6 +11,7 @@
 import torch
 
 from .model import _backend as be
+from .model.Reinforcement.action import apply_custom_wtrans, wtrans_code
 
 
 def generate_labels(action, dets_xywh, det_score, det_cat, det_img, ndet, gt_xywh, gt_cat, iscrowd=None, ngt=None,
@@ -19,9 +20,13 @@ def generate_labels(action, dets_xywh, det_score, det_cat, det_img, ndet, gt_xyw
     image; gt_xywh (B,G,4), gt_cat (B,G), iscrowd (B,G), ngt (B).  Returns (bboxes [B,N,8],
     labels [B,N,A,3]) with the collate's zero padding."""
     B, N, _ = dets_xywh.shape
+    code = wtrans_code(action)
     labels = be.rl_labels(dets_xywh, gt_xywh, action.table(dets_xywh.device), det_cat=det_cat, ndet=ndet,
                           gt_cat=gt_cat, crowd=iscrowd, ngt=ngt, iou_thres=float(action.iou_thres),
-                          pos_wratio=pos_wratio, neg_wratio=neg_wratio)
+                          pos_wratio=pos_wratio, neg_wratio=neg_wratio, wtrans=code)
+    if code == be.WTRANS_RAW:  # a callable the kernel does not know: applied to the raw delta_iou
+        w = apply_custom_wtrans(action, labels[..., 2], labels[..., 1], pos_wratio, neg_wratio)
+        labels[..., 2] = torch.where(labels[..., 1] != 0, w, torch.zeros_like(w))  # padded rows stay zero
     d = dets_xywh.float()
     x2, y2 = d[..., 0] + d[..., 2], d[..., 1] + d[..., 3]  # bbox[2] += bbox[0]; bbox[3] += bbox[1] (:142-143)
     rows = torch.stack([d[..., 0], d[..., 1], x2, y2, det_score.float(), det_cat.float(), det_img.float()], 2)

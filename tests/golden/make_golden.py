@@ -9,7 +9,7 @@ The fixtures are committed; tests never read /root/reference.
 Stubs: `easydict` (pip package missing here) and `model.nms._ext.nms`
 (the cffi extension cannot be built: torch.utils.ffi is gone).  The nms stub is backed by the
 oracle's greedy NMS; the NMS arithmetic itself is pinned separately against the reference's
-legacy CUDA kernel on the GPU (tests/test_gpu_legacy.py, tests/golden/legacy_cuda.npz).
+legacy CUDA kernel on the GPU (tests/test_gpu_legacy.py, oracle/_ref/libref_legacy.so).
 """
 import os
 import sys
@@ -145,6 +145,40 @@ def main():
         out[f"move_k{maxk}_boxes"] = moved
         out[f"move_k{maxk}_prec"] = np.array(prec)
     out.update(move_in_boxes=bb, move_preds=preds, move_targets=targets)
+    # tied / saturated predictions: the visit order is np.flip(np.argsort(pred)) (action.py:44).  numpy's
+    # default sort is stable only for short or presorted runs (and SIMD-dispatched beyond), so the fixture is
+    # the reference's own move_from_act with np.argsort pinned to kind='stable' -- among equal preds the
+    # HIGHER flat index is visited first.  Where the unpinned run agrees on this machine it is said so.
+    import model.Reinforcement.action as ref_action
+    real_argsort = np.argsort
+
+    class _StableNp:
+        def __getattr__(self, k):
+            return getattr(np, k)
+
+        @staticmethod
+        def argsort(a, *args, **kw):
+            return real_argsort(a, kind="stable")
+
+    for tag, (tb, tn, levels) in {"tie_small": (2, 1, 3), "tie_large": (2, 40, 2), "tie_all": (2, 40, 1)}.items():
+        tbx = np.concatenate([torch.rand(tb, tn, 2, generator=g).numpy() * 400,
+                              torch.rand(tb, tn, 2, generator=g).numpy() * 200 + 4], 2).astype(np.float32)
+        tpr = (torch.randint(0, levels, (tb, tn, 16), generator=g).float() / max(levels - 1, 1)).numpy()
+        ttg = np.where(torch.rand(tb, tn, 16, generator=g).numpy() > 0.4, 1.0, -1.0).astype(np.float32)
+        out.update({f"{tag}_boxes": tbx, f"{tag}_preds": tpr, f"{tag}_targets": ttg})
+        for maxk in (1, 3):
+            ref_action.np = _StableNp()
+            try:
+                moved, prec = act.move_from_act(tbx.copy(), tpr, ttg, maxk)
+            finally:
+                ref_action.np = np
+            plain, plain_prec = act.move_from_act(tbx.copy(), tpr, ttg, maxk)
+            print(f"{tag} maxk={maxk}: unpinned numpy sort agrees with the stable one here:",
+                  bool(np.array_equal(plain, moved) and plain_prec == prec))
+            if tag == "tie_all":  # all preds equal (an untrained head): the UNPINNED reference run is the fixture
+                assert np.array_equal(plain, moved) and plain_prec == prec
+            out[f"{tag}_k{maxk}_out"] = moved
+            out[f"{tag}_k{maxk}_prec"] = np.array(prec)
 
     # ---- bbIou + reward loop (maskApi.c:98-109 compiled unchanged; RL_coco_dataset.py:119-137)
     g = torch.Generator().manual_seed(40)

@@ -455,6 +455,83 @@ def test_reward_c3_size(orc, mode, nact):
     np.testing.assert_allclose(w.cpu().numpy(), rw, rtol=1e-6)
 
 
+@pytest.mark.parametrize("kind", ["identity", "exp_abs", "custom_tensor", "custom_scalar"])
+def test_action_wtrans_is_honoured(orc, kind):
+    # weight = action.wtrans(delta_iou) * ratio (RL_coco_dataset.py:128-135): Action's default is the
+    # identity (action.py:7-10), Config.act_wtrans is exp(|x|) (config.py:48-51), anything else is custom
+    import math
+    from rlobjectdetection_b200.model.Reinforcement.action import Action, exp_abs
+    from rlobjectdetection_b200.model.Reinforcement.reward import action_rewards
+    from rlobjectdetection_b200.rl_step import generate_labels
+    B, N, G = 2, 40, 5
+    g = torch.Generator().manual_seed(77)
+    boxes = syn.to_xywh(torch.stack([syn.random_boxes(g, N, 300, 400, 16, 200) for _ in range(B)], 0))
+    gt, crowd = syn.gt_boxes(78, B, G, 300, 400)
+    gt = syn.to_xywh(gt)
+    wt = {"identity": None, "exp_abs": exp_abs, "custom_tensor": lambda x: x * x + 0.5,
+          "custom_scalar": lambda x: math.sqrt(math.fabs(x)) + 1.0}[kind]
+    action = Action([0.5, 0.25]) if wt is None else Action([0.5, 0.25], wtrans=wt)
+    r, l, w = action_rewards(action, cu(boxes), cu(gt), iscrowd=cu(crowd), pos_wratio=1.5, neg_wratio=0.75)
+    code = {"identity": orc.WTRANS_IDENTITY, "exp_abs": orc.WTRANS_EXP_ABS}.get(kind)
+    rr, rl, rw = orc.action_reward(boxes.numpy(), gt.numpy(), action.actDeltas, crowd=crowd.numpy(), pos_wratio=1.5,
+                                   neg_wratio=0.75, wtrans=orc.WTRANS_IDENTITY if code is None else code)
+    assert np.array_equal(r.cpu().numpy(), rr) and np.array_equal(l.cpu().numpy(), rl)
+    if code is None:  # custom: the callable on the fp32 reward, times the ratio
+        f = (lambda x: x * x + 0.5) if kind == "custom_tensor" else np.vectorize(wt)
+        rw = (f(rr.astype(np.float64)) * np.where(rl > 0, 1.5, 0.75)).astype(np.float32)
+    np.testing.assert_allclose(w.cpu().numpy(), rw, rtol=1e-6, atol=1e-7)
+    if kind == "identity":
+        assert (w.cpu().numpy() < 0).any()  # identity weights follow the sign of delta_iou
+    # the collated label tensor takes the same transform
+    det_cat = torch.zeros(B, N, dtype=torch.int32)
+    _, labels = generate_labels(action, cu(boxes), cu(torch.zeros(B, N)), cu(det_cat), cu(torch.zeros(B, N)),
+                                cu(torch.full((B,), N, dtype=torch.int32)), cu(gt), cu(torch.zeros(B, G, dtype=torch.int32)),
+                                iscrowd=cu(crowd), pos_wratio=1.5, neg_wratio=0.75)
+    np.testing.assert_allclose(labels[..., 2].cpu().numpy(), rw, rtol=1e-6, atol=1e-7)
+
+
+def test_reward_float64_boxes_bit_exact(orc):
+    # COCO json boxes are float64 (e.g. 123.45 is not an fp32 number): double rows go through in fp64 and match
+    # the reference loop bit for bit, labels included, where the fp32-rounded boxes would not
+    rng = np.random.default_rng(3)
+    B, N, G = 2, 30, 4
+    boxes = np.round(np.concatenate([rng.uniform(0, 300, (B, N, 2)), rng.uniform(5, 150, (B, N, 2))], 2), 2)
+    gt = np.round(np.concatenate([rng.uniform(0, 300, (B, G, 2)), rng.uniform(5, 150, (B, G, 2))], 2), 2)
+    crowd = (rng.uniform(size=(B, G)) < 0.25).astype(np.uint8)
+    act = orc.action_table([0.5, 0.25])
+    rr, rl, rw = orc.action_reward_f64(boxes, gt, act, crowd=crowd, pos_wratio=2.0, neg_wratio=0.5)
+    r, l, w = be.action_reward(cu(boxes), cu(gt), cu(act), crowd=cu(crowd), mode=be.IOU_COCO, pos_wratio=2.0,
+                               neg_wratio=0.5)
+    assert np.array_equal(r.cpu().numpy(), rr) and np.array_equal(l.cpu().numpy(), rl)
+    np.testing.assert_allclose(w.cpu().numpy(), rw, rtol=2e-7)
+    lab = be.rl_labels(cu(boxes), cu(gt), cu(act), crowd=cu(crowd), pos_wratio=2.0, neg_wratio=0.5).cpu().numpy()
+    assert np.array_equal(lab[..., 1], rl)
+    np.testing.assert_allclose(lab[..., 2], rw, rtol=2e-7)
+    with pytest.raises(RuntimeError):  # fp64 rows exist in COCO mode only
+        be.lib()  # keep the library loaded
+        from rlobjectdetection_b200.model._backend import check, ptr, stream_of
+        t = cu(boxes)
+        check(be.lib().rlod_action_reward(ptr(t), ptr(cu(gt)), 1, None, None, ptr(cu(act)), B, N, 16, G, be.IOU_RCNN,
+                                          1, 0.0, 1.0, 1.0, ptr(torch.empty(B, N, 16, device=DEV)), None, None,
+                                          stream_of(t)), "rlod_action_reward")
+
+
+def test_move_from_act_tied_preds(orc, golden):
+    # saturated / equal predictions: the visit order is np.flip(np.argsort(pred)) = higher flat index first
+    # among equals; pinned on the reference's own move_from_act (tests/golden/make_golden.py, tied cases)
+    from rlobjectdetection_b200.model.Reinforcement.action import Action
+    act = Action([0.5, 0.25])
+    for tag in ("tie_small", "tie_large", "tie_all"):  # tie_all: the reference's unpinned run (all preds equal)
+        for k in (1, 3):
+            bb = golden[f"{tag}_boxes"].copy()
+            moved, prec = act.move_from_act(bb, golden[f"{tag}_preds"], golden[f"{tag}_targets"], k, device=DEV)
+            assert np.array_equal(moved, golden[f"{tag}_k{k}_out"]), (tag, k)
+            assert prec == float(golden[f"{tag}_k{k}_prec"])
+            rb, rp = orc.move_from_act(golden[f"{tag}_boxes"], golden[f"{tag}_preds"], golden[f"{tag}_targets"],
+                                       golden["act16"], k)
+            assert np.array_equal(rb, moved) and rp == prec
+
+
 def test_move_from_act_vs_golden(orc, golden):
     from rlobjectdetection_b200.model.Reinforcement.action import Action
     act = Action([0.5, 0.25])
@@ -619,8 +696,11 @@ def test_rl_generate_labels_vs_reference_collate(orc):
     import os
     from rlobjectdetection_b200.model.Reinforcement.action import Action
     from rlobjectdetection_b200.rl_step import generate_labels
+    from math import exp, fabs
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_rl.npz"))
-    action = Action([0.5, 0.25])
+    # the golden was made with the reference's Config.act_wtrans, passed the way a user of the
+    # reference passes it: as a plain callable (recognised by probing, action.wtrans_code)
+    action = Action([0.5, 0.25], wtrans=lambda x: exp(fabs(x)))
     bboxes, labels = generate_labels(action, cu(g["dets"]), cu(g["det_score"]), cu(g["det_cat"]), cu(g["det_img"]),
                                      cu(g["ndet"]), cu(g["gt"]), cu(g["gt_cat"]), iscrowd=cu(g["crowd"]), ngt=cu(g["ngt"]),
                                      pos_wratio=float(g["wratio"][0]), neg_wratio=float(g["wratio"][1]))

@@ -61,6 +61,32 @@ def test_action_table_and_move(orc, golden):
         assert prec == float(golden[f"move_k{k}_prec"])
 
 
+def test_move_from_act_tied_preds_vs_reference(orc, golden):
+    # equal predictions: np.flip(np.argsort) visits the higher flat index first (reference run with the sort
+    # pinned stable; "tie_all" = all preds equal, where the reference's unpinned run is the fixture)
+    for tag in ("tie_small", "tie_large", "tie_all"):
+        for k in (1, 3):
+            moved, prec = orc.move_from_act(golden[f"{tag}_boxes"], golden[f"{tag}_preds"], golden[f"{tag}_targets"],
+                                            golden["act16"], k)
+            np.testing.assert_array_equal(moved, golden[f"{tag}_k{k}_out"])
+            assert prec == float(golden[f"{tag}_k{k}_prec"])
+
+
+def test_reward_weight_transforms_and_f64_rows(orc, golden):
+    # weight = wtrans(delta_iou) * ratio: identity (Action's default) vs exp(|x|) (Config.act_wtrans); and the
+    # fp64-row loop equals the C port on fp32-representable boxes
+    a = (golden["iou_dt"][None], golden["iou_gt"][None], golden["act16"])
+    r1, l1, w1 = orc.action_reward(*a, crowd=golden["iou_crowd"][None], pos_wratio=2.0, neg_wratio=0.5,
+                                   wtrans=orc.WTRANS_EXP_ABS)
+    r0, l0, w0 = orc.action_reward(*a, crowd=golden["iou_crowd"][None], pos_wratio=2.0, neg_wratio=0.5,
+                                   wtrans=orc.WTRANS_IDENTITY)
+    assert np.array_equal(r0, r1) and np.array_equal(l0, l1)
+    np.testing.assert_allclose(w0[0], golden["reward_out"] * np.where(golden["reward_label"] > 0, 2.0, 0.5), rtol=1e-6)
+    rf, lf, wf = orc.action_reward_f64(*a, crowd=golden["iou_crowd"][None], pos_wratio=2.0, neg_wratio=0.5)
+    assert np.array_equal(rf, r1) and np.array_equal(lf, l1)
+    np.testing.assert_allclose(wf, w1, rtol=1e-6)
+
+
 def test_bbiou_and_reward(orc, golden):
     o = orc.bbiou(golden["iou_dt"], golden["iou_gt"], golden["iou_crowd"])
     np.testing.assert_array_equal(o, golden["iou_out"])  # bit-exact fp64 vs maskApi.c
