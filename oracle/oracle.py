@@ -397,6 +397,30 @@ def move_from_act(bboxes, preds, targets, act, maxk):
     return bboxes, correct * 100.0 / (b * maxk)
 
 
+def refine_best_action(rois, reward, label, act):
+    """The hot path's refine: Action.move_from_act (action.py:25-59) with maxk = N, the rewards
+    as predictions and the labels as targets, on x1y1x2y2 rois (B,N,5) with the +1 convention:
+    every box takes its best action (ties -> the HIGHEST action id, the visit order of
+    np.flip(np.argsort)) if that action's label is +1.  Returns (refined rois, boxes moved)."""
+    rois = _f32(rois)
+    B, N, _ = rois.shape
+    A = reward.shape[2]
+    best = A - 1 - np.argmax(reward[:, :, ::-1], axis=2)
+    bi, ni = np.meshgrid(np.arange(B), np.arange(N), indexing="ij")
+    take = label[bi, ni, best] == 1
+    d = _f32(act)[best]
+    b = rois[:, :, 1:5]
+    f1 = np.float32(1)
+    w = b[..., 2] - b[..., 0] + f1
+    h = b[..., 3] - b[..., 1] + f1
+    nx, ny = b[..., 0] + d[..., 0] * w, b[..., 1] + d[..., 1] * h
+    nw, nh = w + d[..., 2] * w, h + d[..., 3] * h
+    moved = np.stack([nx, ny, nx + nw - f1, ny + nh - f1], -1).astype(np.float32)
+    refined = rois.copy()
+    refined[:, :, 1:5] = np.where(take[..., None], moved, b)
+    return refined, int(take.sum())
+
+
 # ----------------------------------------------------------------------------------------
 # the compiled reference itself (oracle/_ref, built from /root/reference in place)
 # ----------------------------------------------------------------------------------------

@@ -274,6 +274,109 @@ __global__ void __launch_bounds__(kMoveThreads)
   if ((t & 31) == 0 && local && correct) atomicAdd(correct, local);
 }
 
+
+// ----------------------------------------------------------------------------------------
+// k_reward_refine: the hot path's whole RL-refine in ONE launch -- what the step used to do
+// as rlod_action_reward (RCNN mode) + a copy of the rois + rlod_move_from_act(maxk = N, the
+// rewards as predictions, the labels as targets) + concatenation + global image index:
+//   reward[b,n,a] = max_g IoU(box moved by action a, gt_g) - max_g IoU(box, gt_g)
+//   every box takes its best action (highest reward, ties -> highest action id, the visit
+//   order of move_from_act) if that action's label is +1 (reward > iou_thres)
+//   refined (B,N,5) = [b, moved box];  packed (B,N,5+A) = [b + first_image, moved box, rewards]
+// One warp per box, lanes over the actions, the image's ground truth in shared memory; the
+// unmoved box's max IoU is computed once per box (lanes over gt).  Arithmetic is the
+// reward / move kernels' own, operation for operation, so the results are bit-identical to
+// the unfused sequence (tests/test_gpu_parity.py::test_reward_refine_equals_unfused).
+// ----------------------------------------------------------------------------------------
+constexpr int kRefineWarps = 8;
+
+__global__ void __launch_bounds__(kRefineWarps * 32)
+    k_reward_refine(const float *__restrict__ rois, const float *__restrict__ gt,
+                    const int *__restrict__ ngt, const float *__restrict__ act, int N, int A, int G,
+                    int wtrans, float iou_thres, float pos_wratio, float neg_wratio,
+                    float first_image, float *__restrict__ reward, float *__restrict__ label,
+                    float *__restrict__ weight, float *__restrict__ refined,
+                    float *__restrict__ packed, int *__restrict__ moved) {
+  extern __shared__ float s_gt[];  // [G * 4]
+  const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned full = 0xffffffffu;
+  for (int i = threadIdx.x; i < G * 4; i += blockDim.x) s_gt[i] = __ldg(gt + (size_t)b * G * 4 + i);
+  __syncthreads();
+  const int n = blockIdx.x * kRefineWarps + warp;
+  if (n >= N) return;
+  int ng = ngt ? __ldg(ngt + b) : G;
+  if (ng > G) ng = G;
+  const size_t bn = (size_t)b * N + n;
+  const float *roi = rois + bn * 5;
+  const float x0 = __ldg(roi + 1), x1 = __ldg(roi + 2), x2 = __ldg(roi + 3), x3 = __ldg(roi + 4);
+  const float ob[4] = {x0, x1, x2, x3};
+  // max IoU of the unmoved box: lanes over gt, warp max (max is exact, any order)
+  float orig;
+  if (ng <= 0) {
+    const float z[4] = {0.f, 0.f, 0.f, 0.f};
+    orig = overlap_f32(ob, z);
+  } else {
+    float best = -INFINITY;
+    for (int g = lane; g < ng; g += 32) {
+      const float o = overlap_f32(ob, s_gt + g * 4);
+      if (o > best) best = o;
+    }
+    for (int d = 16; d > 0; d >>= 1) best = fmaxf(best, __shfl_xor_sync(full, best, d));
+    orig = best;
+  }
+  const float w = __fadd_rn(__fsub_rn(x2, x0), 1.f), h = __fadd_rn(__fsub_rn(x3, x1), 1.f);
+  // lanes over actions; per lane the best (reward, action) seen, later actions win ties
+  float bv = 0.f;
+  int ba = -1;
+  bool first_nan = false;
+  for (int a = lane; a < A; a += 32) {
+    const float a0 = __ldg(act + a * 4), a1 = __ldg(act + a * 4 + 1);
+    const float a2 = __ldg(act + a * 4 + 2), a3 = __ldg(act + a * 4 + 3);
+    const float nx = __fadd_rn(x0, __fmul_rn(a0, w)), ny = __fadd_rn(x1, __fmul_rn(a1, h));
+    const float nw = __fadd_rn(w, __fmul_rn(a2, w)), nh = __fadd_rn(h, __fmul_rn(a3, h));
+    const float nb[4] = {nx, ny, __fsub_rn(__fadd_rn(nx, nw), 1.f), __fsub_rn(__fadd_rn(ny, nh), 1.f)};
+    const float rf = __fsub_rn(max_overlap_f32(nb, s_gt, ng), orig);
+    const bool pos = (double)rf > (double)iou_thres;
+    const size_t oi = bn * A + a;
+    if (reward) reward[oi] = rf;
+    if (label) label[oi] = pos ? 1.f : -1.f;
+    if (weight) weight[oi] = label_weight((double)rf, wtrans, (double)(pos ? pos_wratio : neg_wratio));
+    if (packed) packed[bn * (size_t)(5 + A) + 5 + a] = rf;
+    if (a == 0 && rf != rf) first_nan = true;
+    if (rf == rf && (ba < 0 || rf >= bv)) bv = rf, ba = a;  // a NaN never replaces the running best
+  }
+  // warp argmax with move_from_act's rule: the sequential scan "if (v >= best) take" over
+  // a = 0..A-1 (a NaN in slot 0 is never replaced)
+  for (int d = 16; d > 0; d >>= 1) {
+    const float ov = __shfl_xor_sync(full, bv, d);
+    const int oa = __shfl_xor_sync(full, ba, d);
+    const bool take = oa >= 0 && (ba < 0 || (oa > ba ? ov >= bv : ov > bv));
+    if (take) bv = ov, ba = oa;
+  }
+  first_nan = __any_sync(full, first_nan);
+  if (lane != 0) return;
+  if (first_nan || ba < 0) ba = 0, bv = __int_as_float(0x7fc00000);
+  const bool go = (double)bv > (double)iou_thres;  // label of the best action is +1
+  float o0 = x0, o1 = x1, o2 = x2, o3 = x3;
+  if (go) {
+    const float a0 = __ldg(act + ba * 4 + 0), a1 = __ldg(act + ba * 4 + 1);
+    const float a2 = __ldg(act + ba * 4 + 2), a3 = __ldg(act + ba * 4 + 3);
+    const float nx = __fadd_rn(x0, __fmul_rn(a0, w)), ny = __fadd_rn(x1, __fmul_rn(a1, h));
+    const float nw = __fadd_rn(w, __fmul_rn(a2, w)), nh = __fadd_rn(h, __fmul_rn(a3, h));
+    o0 = nx, o1 = ny, o2 = __fsub_rn(__fadd_rn(nx, nw), 1.f), o3 = __fsub_rn(__fadd_rn(ny, nh), 1.f);
+    if (moved) atomicAdd(moved, 1);
+  }
+  const float bidx = __ldg(roi);
+  if (refined) {
+    float *q = refined + bn * 5;
+    q[0] = bidx, q[1] = o0, q[2] = o1, q[3] = o2, q[4] = o3;
+  }
+  if (packed) {
+    float *q = packed + bn * (size_t)(5 + A);
+    q[0] = __fadd_rn(bidx, first_image), q[1] = o0, q[2] = o1, q[3] = o2, q[4] = o3;
+  }
+}
+
 }  // namespace rlod
 
 using namespace rlod;
@@ -342,5 +445,24 @@ RLOD_API int rlod_rl_labels(const void *dets, int det_stride, int f64_boxes, con
     RLOD_LAUNCH(RLOD_KERNEL_REWARD, st, k_rl_labels<float><<<grid, 256, 0, st>>>(
         (const float *)dets, det_stride, det_cat, ndet, (const float *)gt, gt_cat, crowd, ngt, act, B, N, A, G,
         wtrans, iou_thres, pos_wratio, neg_wratio, labels));
+  return launch_status();
+}
+
+RLOD_API int rlod_reward_refine(const float *rois, const float *gt, const int *ngt, const float *act,
+                                int B, int N, int A, int G, int wtrans, float iou_thres,
+                                float pos_wratio, float neg_wratio, int first_image, float *reward,
+                                float *label, float *weight, float *refined, float *packed,
+                                int *moved, rlod_stream_t stream) {
+  if (B < 0 || N < 0 || A < 1 || G < 0) return RLOD_EINVAL;
+  if (wtrans < RLOD_WTRANS_IDENTITY || wtrans > RLOD_WTRANS_RAW) return RLOD_EINVAL;
+  if (B == 0 || N == 0) return RLOD_OK;
+  if (!rois || !act || (G > 0 && !gt)) return RLOD_EINVAL;
+  if (B > 65535 || (size_t)G * 16 > 40000) return RLOD_EUNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  const dim3 grid((unsigned)cdiv(N, kRefineWarps), (unsigned)B);
+  RLOD_LAUNCH(RLOD_KERNEL_REWARD, st,
+              k_reward_refine<<<grid, kRefineWarps * 32, (size_t)G * 16, st>>>(
+                  rois, gt, ngt, act, N, A, G, wtrans, iou_thres, pos_wratio, neg_wratio,
+                  (float)first_image, reward, label, weight, refined, packed, moved));
   return launch_status();
 }

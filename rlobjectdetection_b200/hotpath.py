@@ -2,40 +2,52 @@
 RL-refine (action rewards, apply the best positive action per box) -> RoIAlignAvg re-pool
 [-> RoIAlign backward].  This is what bench.py times; it strings together the same modules a
 user of the reference would call (_ProposalLayer, RoIAlignAvg, Action) -- nothing here computes
-on the host and nothing synchronises until the caller reads a result."""
+on the host and nothing synchronises until the caller reads a result.
+
+Two forms:
+  * DetectRefineStep(...)(scores, deltas, im_info, feat, gt): eager launches on two streams;
+  * DetectRefineStep.capture(...) -> GraphedStep: the same launches recorded once into a CUDA
+    graph over fixed input buffers and replayed with one host call per step -- for shards so
+    small (3 images per GPU when BASELINE config 4's batch of 24 is split over 8 GPUs) that
+    the ~25 launches of a step cost more host time than the GPU needs to run them."""
 import collections
 
 import torch
 
 from .model import _backend as be
-from .model.Reinforcement.action import Action, exp_abs
-from .model.Reinforcement.reward import IOU_RCNN, action_rewards
+from .model.Reinforcement.action import Action, exp_abs, wtrans_code
 from .model.roi_align.modules.roi_align import RoIAlignAvg
 from .model.rpn.proposal_layer import _ProposalLayer
+
+LIGHT_NAMES = ("rois", "reward", "label", "weight", "refined", "moved", "packed")
 
 
 class DetectRefineStep:
     """Two streams per device.  Everything that is per-image and latency-bound -- the proposal
-    layer's select / sort / NMS (one CTA per image), the action rewards and the refine -- runs
-    on a private "light" stream; the two RoIAlign calls (a full-GPU kernel each) run on the
-    caller's stream and wait, by event, for the rois they pool.  Within a call that only takes
-    reward + refine off the critical path.  Across calls the caller can hand over the NEXT
-    step's inputs (`next_inputs`): their light work is enqueued between this step's two
-    RoIAlign launches, so it is dispatched in the tail of the first one and runs under the
-    second -- the per-image kernels use 24 of 148 SMs, so they cost next to nothing there --
-    and the next call finds its rois ready.  (Enqueue order matters: a proposal CTA needs
-    180 KB of shared memory and two resident RoIAlign CTAs leave an SM none, so it is only
-    dispatched once every CTA of the RoIAlign launch enqueued before it has been dispatched.)
-    Results are ordered on the caller's stream as usual: what the caller gets back are
-    copies made on ITS stream; the light stream's own tensors are kept alive by the step until
-    the caller's stream has read them, and at most `max_ahead` steps of them exist
+    layer's select / sort / NMS and the fused reward + refine + pack kernel -- runs on a private
+    "light" stream; the two RoIAlign calls (a full-GPU kernel each) run on the caller's stream
+    and wait, by event, for the rois they pool.  Within a call that only takes reward + refine
+    off the critical path.  Across calls the caller can hand over the NEXT step's inputs
+    (`next_inputs`): their light work is enqueued between this step's two RoIAlign launches, so
+    it is dispatched in the tail of the first one and runs under the second, and the next call
+    finds its rois ready.  (Enqueue order matters: nothing with more than ~0.9 KB of shared
+    memory can co-reside with two RoIAlign CTAs, so a light kernel is only dispatched once every
+    CTA of the RoIAlign launch enqueued before it has been dispatched.)
+    Results are ordered on the caller's stream as usual: what the caller gets back are copies
+    made on ITS stream; the light stream's own tensors are kept alive by the step until the
+    caller's stream has read them, and at most `max_ahead` steps of them exist
     (Tensor.record_stream would do the same bookkeeping inside the caching allocator, but with
     a run-ahead producer it costs ~0.5 ms of host time per step: the light pool cannot recycle
-    blocks and keeps growing)."""
+    blocks and keeps growing).
+
+    outputs: which of the light stream's small tensors a call hands back -- "rois" (B,N,5),
+    "reward" / "label" / "weight" (B,N,A), "refined" (B,N,5), "moved" (1,) and "packed"
+    (B,N,5+A) = [image index + first_image, refined box, rewards], the row layout of the
+    multi-GPU gather (shard.py)."""
 
     def __init__(self, feat_stride=16, scales=(4, 8, 16, 32), ratios=(0.5, 1, 2), cfg_key="TEST",
                  pool=7, act_delta=(0.5, 0.25), backward=True,
-                 outputs=("rois", "reward", "label", "weight", "refined", "moved")):
+                 outputs=("rois", "reward", "label", "weight", "refined", "moved"), first_image=0):
         self.proposal = _ProposalLayer(feat_stride, list(scales), list(ratios))
         self.align = RoIAlignAvg(pool, pool, 1.0 / feat_stride)
         self.action = Action(list(act_delta), wtrans=exp_abs)  # Config.act_wtrans (config.py:48-51)
@@ -43,7 +55,11 @@ class DetectRefineStep:
         self.pool = pool
         self.scale = 1.0 / feat_stride
         self.backward = backward
-        self.outputs = tuple(outputs)  # which of the light stream's small tensors a call hands back (as copies)
+        unknown = set(outputs) - set(LIGHT_NAMES)
+        if unknown:
+            raise ValueError(f"unknown outputs {sorted(unknown)}")
+        self.outputs = tuple(outputs)
+        self.first_image = int(first_image)  # global index of this shard's image 0 (packed rows)
         self.max_ahead = 2
         self._light = {}
         self._inflight = collections.deque()  # (event on the caller's stream, the light stream's tensors)
@@ -67,9 +83,21 @@ class DetectRefineStep:
     def _key(scores, deltas, im_info, gt):
         return tuple((t.data_ptr(), tuple(t.shape), t._version) for t in (scores, deltas, im_info, gt))
 
+    def _light_kernels(self, scores, deltas, im_info, gt, after_rois=None):
+        """proposal -> NMS -> fused reward / refine / pack on the CURRENT stream: three launches.
+        Returns {name: tensor} with rois, refined and the requested outputs."""
+        rois = self.proposal((scores, deltas, im_info, self.cfg_key))          # (B, post, 5)
+        if after_rois is not None:
+            after_rois()
+        want = tuple(n for n in LIGHT_NAMES[1:] if n in self.outputs or n == "refined")
+        t = be.reward_refine(rois, gt, self.action.table(rois.device), iou_thres=float(self.action.iou_thres),
+                             first_image=self.first_image, wtrans=_kernel_wtrans(self.action), want=want)
+        t["rois"] = rois
+        return t
+
     def _light_work(self, cur, light, scores, deltas, im_info, gt, ready):
-        """proposal -> NMS -> rewards -> refine on the light stream; returns the events the
-        caller's stream has to wait for and the (light-stream-owned) tensors."""
+        """The light kernels on the light stream; returns the events the caller's stream has to
+        wait for and the (light-stream-owned) tensors."""
         if ready is None:
             light.wait_stream(cur)
         elif ready is not True:
@@ -80,18 +108,11 @@ class DetectRefineStep:
             consumed, _ = self._inflight.popleft()
             light.wait_event(consumed)
         with torch.cuda.stream(light):
-            rois = self.proposal((scores, deltas, im_info, self.cfg_key))     # (B, post, 5)
             have_rois = torch.cuda.Event()
-            have_rois.record(light)
-            N = rois.size(1)
-            reward, label, weight = action_rewards(self.action, rois[:, :, 1:5], gt, mode=IOU_RCNN)
-            refined = rois.clone()
-            # every box takes its best action if that action's label is +1 (move_from_act with
-            # maxk = N and the rewards as predictions)
-            moved = be.move_from_act(refined, reward, label, self.action.table(rois.device), N, corners=True)
+            t = self._light_kernels(scores, deltas, im_info, gt, after_rois=lambda: have_rois.record(light))
             have_refined = torch.cuda.Event()
             have_refined.record(light)
-        return have_rois, have_refined, (rois, reward, label, weight, refined, moved)
+        return have_rois, have_refined, t
 
     @torch.no_grad()
     def __call__(self, scores, deltas, im_info, feat, gt, grad_pooled=None, inputs_ready=None,
@@ -120,22 +141,20 @@ class DetectRefineStep:
                 self._inflight.append((consumed, cand[2]))
         if rec is None:
             rec = self._light_work(cur, light, scores, deltas, im_info, gt, inputs_ready)
-        have_rois, have_refined, l_tensors = rec
-        l_rois, l_refined = l_tensors[0], l_tensors[4]
+        have_rois, have_refined, lt = rec
         cur.wait_event(have_rois)
-        pooled = self.align(feat, l_rois.view(-1, 5))                         # (B*N, C, p, p)
+        pooled = self.align(feat, lt["rois"].view(-1, 5))                      # (B*N, C, p, p)
         if next_inputs is not None:
             if next_ready is None:
                 raise ValueError("next_inputs need next_ready = True or an event")
             ns, nd, ni, ng = next_inputs
             self._prefetched = (self._key(ns, nd, ni, ng), self._light_work(cur, light, ns, nd, ni, ng, next_ready))
         cur.wait_event(have_refined)
-        pooled_refined = self.align(feat, l_refined.view(-1, 5))
-        names = ("rois", "reward", "label", "weight", "refined", "moved")
-        out = {n: t.clone() for n, t in zip(names, l_tensors) if n in self.outputs or (n == "refined" and self.backward)}
+        pooled_refined = self.align(feat, lt["refined"].view(-1, 5))
+        out = {n: lt[n].clone() for n in LIGHT_NAMES if n in lt and (n in self.outputs or (n == "refined" and self.backward))}
         consumed = torch.cuda.Event()
         consumed.record(cur)
-        self._inflight.append((consumed, l_tensors))
+        self._inflight.append((consumed, lt))
         out.update(pooled=pooled, pooled_refined=pooled_refined)
         if self.backward:
             if grad_pooled is None:
@@ -144,3 +163,114 @@ class DetectRefineStep:
                                                      tuple(feat.shape), self.pool, self.pool,
                                                      self.scale, be.POOL_AVG)
         return out
+
+    def capture(self, scores, deltas, im_info, feat, gt, next_inputs=None):
+        """Record the step over these (fixed) input buffers into a CUDA graph -> GraphedStep."""
+        return GraphedStep(self, (scores, deltas, im_info, feat, gt), next_inputs)
+
+
+def _kernel_wtrans(action):
+    code = wtrans_code(action)
+    if code == be.WTRANS_RAW:
+        raise ValueError("DetectRefineStep: Action.wtrans must be the identity or exp(|x|) (the fused refine kernel "
+                         "applies it on the device); use model.Reinforcement.reward.action_rewards for other callables")
+    return code
+
+
+class GraphedStep:
+    """One CUDA graph = one whole step over fixed input buffers; `replay()` is a single host
+    call (cudaGraphLaunch) instead of ~25 launches, and returns the step's outputs in STATIC
+    buffers (valid until the next replay, like any captured output).
+
+    next_inputs = None: the light kernels of these inputs, then the two RoIAlign launches
+    (the fused reward / refine kernel runs on a forked branch under the first RoIAlign).
+    next_inputs = (scores, deltas, im_info, gt) of the step that follows (the same buffers in a
+    steady loop): the graph pools the rois that the PREVIOUS replay's light branch left in the
+    step's hand-over buffers while its own light branch prepares the next step's -- the
+    software pipeline of DetectRefineStep's `next_inputs`, frozen into the graph.  `prime()`
+    fills the hand-over buffers for the first replay (and after the inputs changed by more
+    than one step)."""
+
+    def __init__(self, step, inputs, next_inputs=None):
+        if step.backward:
+            raise ValueError("GraphedStep covers the forward step (backward=False)")
+        self.step = step
+        self.inputs = inputs
+        self.next_inputs = next_inputs
+        scores, deltas, im_info, feat, gt = inputs
+        dev = feat.device
+        self.device = dev
+        self._cap = torch.cuda.Stream(device=dev)
+        self._side = torch.cuda.Stream(device=dev)
+        self.graph = torch.cuda.CUDAGraph()
+        self.out = None
+        self._hand = None  # hand-over buffers (pipelined form): rois / refined / outputs of the step to pool next
+        profiling = be.lib().rlod_profile_enable(0)  # event records cannot be timed from inside a graph
+        try:
+            with torch.no_grad():
+                self._warm_and_capture()
+        finally:
+            be.lib().rlod_profile_enable(profiling)
+
+    def _heavy(self, feat, lt):
+        pooled = self.step.align(feat, lt["rois"].view(-1, 5))
+        pooled_refined = self.step.align(feat, lt["refined"].view(-1, 5))
+        return pooled, pooled_refined
+
+    def _warm_and_capture(self):
+        step, cap, side = self.step, self._cap, self._side
+        scores, deltas, im_info, feat, gt = self.inputs
+        cap.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(cap):
+            # eager warm-up: function attributes, cached tables, allocator pools
+            lt = step._light_kernels(scores, deltas, im_info, gt)
+            self._heavy(feat, lt)
+            if self.next_inputs is not None:
+                self._hand = {k: v.clone() for k, v in lt.items()}
+            del lt
+        cap.synchronize()
+        with torch.cuda.graph(self.graph, stream=cap):
+            if self.next_inputs is None:
+                rois = step.proposal((scores, deltas, im_info, step.cfg_key))
+                side.wait_stream(cap)                                    # fork: refine under the first RoIAlign
+                with torch.cuda.stream(side):
+                    want = tuple(n for n in LIGHT_NAMES[1:] if n in step.outputs or n == "refined")
+                    lt = be.reward_refine(rois, gt, step.action.table(self.device),
+                                          iou_thres=float(step.action.iou_thres), first_image=step.first_image,
+                                          wtrans=_kernel_wtrans(step.action), want=want)
+                    lt["rois"] = rois
+                pooled = step.align(feat, rois.view(-1, 5))
+                cap.wait_stream(side)                                    # join
+                pooled_refined = step.align(feat, lt["refined"].view(-1, 5))
+                out = {n: lt[n] for n in LIGHT_NAMES if n in lt and n in step.outputs}
+            else:
+                ns, nd, ni, ng = self.next_inputs
+                hand = self._hand
+                side.wait_stream(cap)                                    # fork: the NEXT step's light kernels
+                with torch.cuda.stream(side):
+                    nxt = step._light_kernels(ns, nd, ni, ng)
+                pooled, pooled_refined = self._heavy(feat, hand)
+                out = {n: hand[n].clone() for n in LIGHT_NAMES if n in hand and n in step.outputs}
+                cap.wait_stream(side)                                    # join, then hand over
+                for k in hand:
+                    hand[k].copy_(nxt[k])
+            out.update(pooled=pooled, pooled_refined=pooled_refined)
+            self.out = out
+        cap.synchronize()
+
+    @torch.no_grad()
+    def prime(self):
+        """Pipelined form: run the light kernels of `inputs` now so that the next replay pools them."""
+        if self._hand is None:
+            return
+        scores, deltas, im_info, feat, gt = self.inputs
+        cur = torch.cuda.current_stream(self.device)
+        lt = self.step._light_kernels(scores, deltas, im_info, gt)
+        for k in self._hand:
+            self._hand[k].copy_(lt[k])
+        cur.synchronize()
+
+    def replay(self):
+        """Enqueue the whole step on the current stream; returns the static output dict."""
+        self.graph.replay()
+        return self.out

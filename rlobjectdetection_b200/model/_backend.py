@@ -56,6 +56,7 @@ SIGNATURES = {
     "rlod_action_reward": (_I, [_P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _F, _F, _P, _P, _P,
                                 _P]),
     "rlod_move_from_act": (_I, [_P, _I, _I, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "rlod_reward_refine": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _F, _I, _P, _P, _P, _P, _P, _P, _P]),
     "rlod_proposal_target": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "rlod_anchor_target_workspace_bytes": (_Z, [_I, _I, _I, _I]),
     "rlod_anchor_target": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _F, _I, _F, _I, _F, _F, _P, _P, _P, _P, _P,
@@ -353,6 +354,33 @@ def move_from_act(boxes, preds, targets, act, maxk, corners=False):
                                        ptr(act), B, N, A, int(maxk), ptr(correct),
                                        stream_of(boxes)), "rlod_move_from_act")
     return correct
+
+
+def reward_refine(rois, gt, act, ngt=None, iou_thres=0.0, pos_wratio=1.0, neg_wratio=1.0, first_image=0,
+                  wtrans=WTRANS_EXP_ABS, want=("reward", "label", "weight", "refined", "packed", "moved")):
+    """rlod_reward_refine: rewards of every (box, action), the best positive action applied to every
+    box, and the packed rows of the gather, in one launch.  rois (B,N,5), gt (B,G,4) x1y1x2y2.
+    Returns a dict with the requested tensors (B,N,A) / (B,N,5) / (B,N,5+A) / (1,) int32."""
+    require_cuda("reward_refine", rois, gt, act, ngt)
+    rois, gt, act = f32c(rois), f32c(gt), f32c(act)
+    B, N, five = rois.shape
+    if five != 5:
+        raise ValueError("reward_refine: rois must be (B, N, 5)")
+    G, A = gt.size(1), act.size(0)
+    dev = rois.device
+    if ngt is not None:
+        ngt = ngt.to(torch.int32).contiguous()
+    out = {}
+    for name, shape in (("reward", (B, N, A)), ("label", (B, N, A)), ("weight", (B, N, A)), ("refined", (B, N, 5)),
+                        ("packed", (B, N, 5 + A))):
+        out[name] = torch.empty(shape, dtype=torch.float32, device=dev) if name in want else None
+    out["moved"] = torch.zeros(1, dtype=torch.int32, device=dev) if "moved" in want else None
+    with torch.cuda.device(dev):
+        check(lib().rlod_reward_refine(ptr(rois), ptr(gt), ptr(ngt), ptr(act), B, N, A, G, int(wtrans),
+                                       float(iou_thres), float(pos_wratio), float(neg_wratio), int(first_image),
+                                       ptr(out["reward"]), ptr(out["label"]), ptr(out["weight"]), ptr(out["refined"]),
+                                       ptr(out["packed"]), ptr(out["moved"]), stream_of(rois)), "rlod_reward_refine")
+    return {k: v for k, v in out.items() if v is not None}
 
 
 def detect_postprocess(rois, cls_prob, bbox_pred, im_info, thresh=0.0, nms_thresh=0.3, max_per_image=100,

@@ -571,9 +571,113 @@ def test_move_from_act_corners_matches_reward():
     assert torch.equal(refined[:, :, 0], cu(rois)[:, :, 0])
 
 
+@pytest.mark.parametrize("nact,ties", [(16, False), (56, False), (16, True)])
+def test_reward_refine_equals_unfused(orc, nact, ties):
+    # rlod_reward_refine == rlod_action_reward(RCNN) -> copy -> rlod_move_from_act(maxk=N, rewards as preds) -> pack,
+    # bit for bit (also with heavily tied rewards: coarse integer boxes), and == the oracle's restatement
+    B, N, G = 3, 300, 20
+    g = torch.Generator().manual_seed(51)
+    boxes = torch.stack([syn.random_boxes(g, N, 800, 1200) for _ in range(B)], 0)
+    gt, _ = syn.gt_boxes(52, B, G, 800, 1200)
+    if ties:
+        boxes, gt = (boxes / 64).round() * 64, (gt / 64).round() * 64
+    ngt = torch.tensor([20, 0, 7], dtype=torch.int32)
+    rois = torch.cat([torch.arange(B).float()[:, None, None].expand(B, N, 1), boxes], 2).contiguous()
+    delta = [.5, .25] if nact == 16 else [.5, .25, .125, .0625, .03125, .015625, .008]
+    act = cu(orc.action_table(delta))
+    r, l, w = be.action_reward(cu(boxes), cu(gt), act, ngt=cu(ngt), mode=be.IOU_RCNN, pos_wratio=1.5, neg_wratio=0.75)
+    refined = cu(rois).clone()
+    moved = be.move_from_act(refined, r, l, act, N, corners=True)
+    f = be.reward_refine(cu(rois), cu(gt), act, ngt=cu(ngt), pos_wratio=1.5, neg_wratio=0.75, first_image=7)
+    for name, ref in (("reward", r), ("label", l), ("weight", w), ("refined", refined)):
+        assert torch.equal(f[name], ref), name
+    assert int(f["moved"].item()) == int(moved.item())
+    packed = torch.cat([refined, r], 2)
+    packed[:, :, 0] += 7
+    assert torch.equal(f["packed"], packed)
+    o_ref, o_moved = orc.refine_best_action(rois.numpy(), r.cpu().numpy(), l.cpu().numpy(), act.cpu().numpy())
+    assert np.array_equal(f["refined"].cpu().numpy(), o_ref) and o_moved == int(moved.item())
+    if ties:
+        rr = r.cpu().numpy()
+        assert ((rr == rr.max(axis=2, keepdims=True)).sum(axis=2) > 1).any()  # the tie rule is exercised
+    only = be.reward_refine(cu(rois), cu(gt), act, ngt=cu(ngt), want=("packed",))
+    assert list(only) == ["packed"] and torch.equal(only["packed"][:, :, 1:], packed[:, :, 1:])
+
+
 # ------------------------------------------------------------------------------------------
 # whole step
 # ------------------------------------------------------------------------------------------
+def test_c4_bench_workload_matches_oracle(orc):
+    """The EXACT workload bench.py's headline number is quoted on -- bench.make_inputs(100, 24): 24 images,
+    50x75x1024 features, 45 000 anchors each, TEST cfg 6000 -> 300, 7 200 rois, 16 actions x 20 gt -- through
+    DetectRefineStep and against the CPU oracle: sort order / keep decisions / rewards / labels / refined boxes
+    bit-exact (the oracle's NMS and rewards run on the GPU's decoded boxes: device expf vs libm differ in the last
+    ulp, bounded separately at 3e-6), pooled features of both RoIAlign passes within 1e-5."""
+    import bench
+    from rlobjectdetection_b200.hotpath import DetectRefineStep
+    from rlobjectdetection_b200.model.utils.config import cfg
+    inputs = bench.make_inputs(100, bench.IMAGES)
+    scores, deltas, im_info, feat, gt = inputs
+    step = DetectRefineStep(bench.STRIDE, bench.SCALES, bench.RATIOS, "TEST", bench.POOL, bench.ACT_DELTA, backward=False,
+                            outputs=("rois", "reward", "label", "refined", "moved", "packed"), first_image=0)
+    old = (cfg.TEST.RPN_PRE_NMS_TOP_N, cfg.TEST.RPN_POST_NMS_TOP_N, cfg.TEST.RPN_NMS_THRESH)
+    cfg.TEST.RPN_PRE_NMS_TOP_N, cfg.TEST.RPN_POST_NMS_TOP_N, cfg.TEST.RPN_NMS_THRESH = bench.PRE, bench.POST, bench.NMS_T
+    try:
+        out = step(*(cu(t) for t in inputs))
+        torch.cuda.synchronize()
+    finally:
+        cfg.TEST.RPN_PRE_NMS_TOP_N, cfg.TEST.RPN_POST_NMS_TOP_N, cfg.TEST.RPN_NMS_THRESH = old
+    anchors = step.proposal._anchors.cpu()
+    rois = _proposal_parity(orc, scores, deltas, im_info, anchors, bench.STRIDE, bench.PRE, bench.POST, bench.NMS_T)
+    assert np.array_equal(out["rois"].cpu().numpy(), rois)           # the step's rois are the layer's
+    assert rois.shape == (24, 300, 5) and (rois[:, :, 1:].any(axis=2)).all()  # 300 kept per image, none padded
+    act = step.action.actDeltas
+    rr, rl, _ = orc.action_reward(rois[:, :, 1:5], gt.numpy(), act, mode=orc.MODE_RCNN)
+    assert np.array_equal(out["reward"].cpu().numpy(), rr) and np.array_equal(out["label"].cpu().numpy(), rl)
+    refined, moved = orc.refine_best_action(rois, rr, rl, act)
+    assert np.array_equal(out["refined"].cpu().numpy(), refined) and int(out["moved"].item()) == moved
+    assert np.array_equal(out["packed"].cpu().numpy(), np.concatenate([refined, rr], 2))
+    for name, boxes in (("pooled", rois), ("pooled_refined", refined)):
+        got = out[name].cpu().numpy()
+        del out[name]
+        ref = orc.roi_align(feat.numpy(), boxes.reshape(-1, 5), 7, 7, 1 / 16.0, pool_mode=orc.POOL_AVG)
+        close(got, ref, what=name)
+        del got, ref
+
+
+@pytest.mark.parametrize("pipelined", [False, True])
+def test_graphed_step_equals_eager(pipelined):
+    # the CUDA-graph form of the step (serial, and pipelined over the next step's inputs) against eager launches
+    from rlobjectdetection_b200.hotpath import DetectRefineStep
+    B, C, H, W, G = 3, 32, 25, 38, 6
+    step = DetectRefineStep(cfg_key="TEST", backward=False, outputs=("rois", "reward", "refined", "packed", "moved"),
+                            first_image=5)
+    A = step.proposal._num_anchors
+    g = torch.Generator().manual_seed(12)
+    feat = cu(torch.randn(B, C, H, W, generator=g))
+    scores, deltas, im_info = (cu(t) for t in syn.rpn_outputs(20, B, A, H, W, H * 16, W * 16))
+    gt = cu(syn.gt_boxes(40, B, G, H * 16, W * 16)[0])
+    keys = ("rois", "reward", "refined", "packed", "moved", "pooled", "pooled_refined")
+    ref = {k: v.clone() for k, v in step(scores, deltas, im_info, feat, gt).items()}
+    gs = step.capture(scores, deltas, im_info, feat, gt, next_inputs=(scores, deltas, im_info, gt) if pipelined else None)
+    gs.prime()
+    for it in range(3):
+        out = gs.replay()
+        torch.cuda.synchronize()
+        for k in keys:
+            assert torch.equal(out[k], ref[k]), (k, it)
+    # new contents in the same buffers: the replay follows them (pipelined: one step later, or after prime())
+    s2, d2, _ = syn.rpn_outputs(21, B, A, H, W, H * 16, W * 16)
+    scores.copy_(cu(s2)), deltas.copy_(cu(d2))
+    ref2 = {k: v.clone() for k, v in step(scores, deltas, im_info, feat, gt).items()}
+    assert not torch.equal(ref2["rois"], ref["rois"])
+    if pipelined:
+        gs.replay()   # pools the old rois, prepares the new ones
+    out = gs.replay()
+    torch.cuda.synchronize()
+    for k in keys:
+        assert torch.equal(out[k], ref2[k]), k
+
 def test_hotpath_step_matches_oracle_chain(orc):
     from rlobjectdetection_b200.hotpath import DetectRefineStep
     B, C, H, W, G = 2, 16, 25, 38, 6
