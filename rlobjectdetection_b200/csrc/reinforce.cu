@@ -79,6 +79,20 @@ __device__ __forceinline__ float max_overlap_f32(const float *a, const float *__
   return best;
 }
 
+// the same scan over ground truth held in shared memory (plain loads: __ldg is global-only)
+__device__ __forceinline__ float max_overlap_f32_smem(const float *a, const float *gt, int ng) {
+  if (ng <= 0) {
+    const float z[4] = {0.f, 0.f, 0.f, 0.f};
+    return overlap_f32(a, z);
+  }
+  float best = -INFINITY;
+  for (int g = 0; g < ng; ++g) {
+    const float o = overlap_f32(a, gt + g * 4);
+    if (o > best) best = o;
+  }
+  return best;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
     k_action_reward(const T *__restrict__ boxes, const T *__restrict__ gt,
@@ -335,7 +349,7 @@ __global__ void __launch_bounds__(kRefineWarps * 32)
     const float nx = __fadd_rn(x0, __fmul_rn(a0, w)), ny = __fadd_rn(x1, __fmul_rn(a1, h));
     const float nw = __fadd_rn(w, __fmul_rn(a2, w)), nh = __fadd_rn(h, __fmul_rn(a3, h));
     const float nb[4] = {nx, ny, __fsub_rn(__fadd_rn(nx, nw), 1.f), __fsub_rn(__fadd_rn(ny, nh), 1.f)};
-    const float rf = __fsub_rn(max_overlap_f32(nb, s_gt, ng), orig);
+    const float rf = __fsub_rn(max_overlap_f32_smem(nb, s_gt, ng), orig);
     const bool pos = (double)rf > (double)iou_thres;
     const size_t oi = bn * A + a;
     if (reward) reward[oi] = rf;

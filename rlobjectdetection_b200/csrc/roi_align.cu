@@ -22,6 +22,9 @@
 //      once, coalesced; no global atomics, no memset.
 //   Generic kernels (any grid size / channel count / plane size, and RoIAlignMax backward)
 //   cover everything the fast paths do not.
+#include <cstdlib>
+#include <type_traits>
+
 #include "roi_lists.cuh"
 
 #ifndef RLOD_ABL
@@ -730,6 +733,296 @@ __global__ void __launch_bounds__(kWalkThreads, 2)
 }
 
 // ----------------------------------------------------------------------------------------
+// k_align8_fwd_walk2: the same walk with packed fp32 arithmetic.  sm_100 has two-wide fp32
+// instructions (FADD2 / FMUL2 / FFMA2 on 64-bit register pairs), and LDS.128 delivers the four
+// channels of a tap as exactly two such pairs: every lerp of the walk is one FADD2 + one FFMA2
+// per PAIR of channels -- half the fp32 issue slots of the scalar walk (276 of its 646
+// instructions per group of four rois were fp32; the kernel is bound by issue slots and the
+// shared-memory pipe, not by HBM, profiles/r01_align_fwd.md).  Further differences:
+//   * RoIAlignAvg: the 1/4 of the 2x2 average is applied to the planes once at fill time
+//     (exact: a power of two), not to every pooled value;
+//   * the staging stores are plain C++ under the loop-invariant predicate k < 7 (the asm
+//     volatile block made ptxas wrap them in BSSY / BRA / BSYNC: 65 control instructions per
+//     group);
+//   * the loop is unrolled by two over two record register sets (no 18-register move per
+//     iteration) and the staging buffer parity is a compile-time constant;
+//   * the interleave of the fill walks (y, x) incrementally instead of dividing per pixel;
+//   * rois are taken from a list partitioned by walk mode (k_roi_order_by_key), so the four
+//     rois of a warp stage with the same strides and their stores stay bank-disjoint.
+// ----------------------------------------------------------------------------------------
+typedef unsigned long long u64;
+struct F4 {
+  u64 a, b;  // channels (0, 1) and (2, 3) as packed f32x2
+};
+__device__ __forceinline__ u64 pack2(float lo, float hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ float2 unpack2(u64 v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+__device__ __forceinline__ u64 add2(u64 x, u64 y) {
+  u64 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(x), "l"(y));
+  return r;
+}
+__device__ __forceinline__ u64 max2(u64 x, u64 y) {
+  const float2 a = unpack2(x), b = unpack2(y);
+  return pack2(fmaxf(a.x, b.x), fmaxf(a.y, b.y));
+}
+__device__ __forceinline__ u64 shfl_down8(u64 v) { return __shfl_down_sync(0xffffffffu, v, 1, 8); }
+
+struct WalkTaps2 {
+  u64 x0, x1, y0, y1, z0, z1, w0, w1;  // line slot a: taps x, y; line slot b: taps z, w
+};
+__device__ __forceinline__ u64 lerp2(u64 p, u64 q, u64 w) {  // p + w * (q - p), two channels
+  u64 d, r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(q), "l"(p));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(w), "l"(d), "l"(p));
+  return r;
+}
+
+// The loads of one walk position: bit 0 of `flags` fetches the two taps of line slot a, bit 1 those
+// of slot b; a slot that is not fetched keeps the taps it holds (predicated LDS.128 into read-write
+// operands).  Only the loads are predicated: the lerps that follow are recomputed from the slot's
+// taps whether or not they were just fetched (same inputs, same result), because a predicated
+// packed fp32 instruction costs ptxas a pair of SELs on top.
+__device__ __forceinline__ void walk_load2(WalkTaps2 &q, uint32_t pa, uint32_t pb, uint32_t pa2,
+                                           uint32_t pb2, int flags) {
+  asm volatile(
+      "{\n"
+      ".reg .pred pr, pd;\n"
+      ".reg .b32 tt;\n"
+      "and.b32 tt, %12, 1;\n"
+      "setp.ne.b32 pr, tt, 0;\n"
+      "and.b32 tt, %12, 2;\n"
+      "setp.ne.b32 pd, tt, 0;\n"
+      "@pr ld.shared.v2.b64 {%0, %1}, [%8];\n"
+      "@pr ld.shared.v2.b64 {%2, %3}, [%9];\n"
+      "@pd ld.shared.v2.b64 {%4, %5}, [%10];\n"
+      "@pd ld.shared.v2.b64 {%6, %7}, [%11];\n"
+      "}\n"
+      : "+l"(q.x0), "+l"(q.x1), "+l"(q.y0), "+l"(q.y1), "+l"(q.z0), "+l"(q.z1), "+l"(q.w0), "+l"(q.w1)
+      : "r"(pa), "r"(pb), "r"(pa2), "r"(pb2), "r"(flags));
+}
+
+template <int POOL>
+__global__ void __launch_bounds__(kWalkThreads, 2)
+    k_align8_fwd_walk2(const float *__restrict__ feat, const int *__restrict__ ext,
+                       const int *__restrict__ order, const int *__restrict__ img_off, int C,
+                       int H, int W, int P, int n_chunks, int tma_fill, float *__restrict__ out) {
+  constexpr int OW = POOL == RLOD_POOL_NONE ? 8 : 7;
+  constexpr int OHW = OW * OW;                            // 64 | 49
+  constexpr int STG = 4 * OHW;                            // floats per (roi, 4 channels)
+  constexpr int SLOT = POOL == RLOD_POOL_NONE ? 264 : 200;  // = 8 (mod 32): slots bank-disjoint
+  constexpr float kPre = POOL == RLOD_POOL_AVG ? 0.25f : 1.f;  // plane prescale (exact)
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float4 *planes4 = reinterpret_cast<float4 *>(smem_raw);
+  const int HW = H * W;
+  float *stage = reinterpret_cast<float *>(planes4 + (H + 2) * P);
+
+  const int b = blockIdx.x / n_chunks, chunk = blockIdx.x - b * n_chunks;
+  const int r0 = img_off[b], r1 = img_off[b + 1];
+  if (r0 >= r1) return;
+  const float *src = feat + ((size_t)b * C + (size_t)chunk * 4) * HW;
+  uint64_t *fill_bar = reinterpret_cast<uint64_t *>(stage + kWalkWarps * 2 * 4 * SLOT);
+  // ---- fill (see k_align8_fwd_walk): bulk copies land the planes planar, threads interleave ----
+  if (tma_fill) {
+    const uint32_t plane_copy = (uint32_t)((HW * 4 + 8 + 15) & ~15);
+    unsigned char *buf[4];
+    buf[0] = smem_raw + (size_t)(H + 2) * P * 16 - plane_copy;
+    for (int c = 1; c < 4; ++c) buf[c] = reinterpret_cast<unsigned char *>(stage) + (size_t)(c - 1) * plane_copy;
+    if (threadIdx.x == 0) {
+      mbar_init(fill_bar, 1);
+      uint32_t total = 0;
+      for (int c = 0; c < 4; ++c) {
+        const uint32_t skew = (uint32_t)((size_t)c * HW * 4) & 15u;
+        total += (skew + (uint32_t)HW * 4 + 15u) & ~15u;
+      }
+      mbar_expect_tx(fill_bar, total);
+      for (int c = 0; c < 4; ++c) {
+        const uint32_t skew = (uint32_t)((size_t)c * HW * 4) & 15u;
+        bulk_g2s(buf[c], reinterpret_cast<const char *>(src + (size_t)c * HW) - skew,
+                 (skew + (uint32_t)HW * 4 + 15u) & ~15u, fill_bar);
+      }
+    }
+    __syncthreads();  // barrier initialised before anyone polls it
+    // next planes of this SM slot into L2 while the copies are in flight
+    {
+      const unsigned nb2 = blockIdx.x + 2u * (unsigned)kSmCount;
+      if (nb2 < gridDim.x) {
+        const unsigned b2 = nb2 / (unsigned)n_chunks, c2 = nb2 - b2 * (unsigned)n_chunks;
+        const char *nx = reinterpret_cast<const char *>(feat + ((size_t)b2 * C + (size_t)c2 * 4) * HW);
+        for (int i = threadIdx.x * 128; i < 4 * HW * 4; i += kWalkThreads * 128)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + i));
+      }
+    }
+    mbar_wait(fill_bar, 0);
+    const float *pl[4];
+    for (int c = 0; c < 4; ++c)
+      pl[c] = reinterpret_cast<const float *>(buf[c] + ((uint32_t)((size_t)c * HW * 4) & 15u));
+    constexpr int kPer = 4;  // pixels per thread and batch
+    // pixel p = base + q * kWalkThreads + tid walks (y, x) by constant steps: no division per pixel
+    const int dy = kWalkThreads / W, dx = kWalkThreads - dy * W;
+    int y = (int)threadIdx.x / W, x = (int)threadIdx.x - y * W;
+    for (int base = 0; base < HW; base += kWalkThreads * kPer) {
+      float4 v[kPer];
+#pragma unroll
+      for (int q = 0; q < kPer; ++q) {
+        const int p = base + q * kWalkThreads + threadIdx.x;
+        if (p < HW) v[q] = make_float4(kPre * pl[0][p], kPre * pl[1][p], kPre * pl[2][p], kPre * pl[3][p]);
+      }
+      __syncthreads();  // plane-0 pixels of this batch are in registers before the region is written
+#pragma unroll
+      for (int q = 0; q < kPer; ++q) {
+        const int p = base + q * kWalkThreads + threadIdx.x;
+        if (p < HW) planes4[y * P + x] = v[q];
+        x += dx, y += dy;
+        if (x >= W) x -= W, ++y;
+      }
+    }
+    __syncthreads();  // staging and the plane tail are free again
+  } else {
+    fill_planes4_async<kWalkThreads>(planes4, src, H, W, P, HW);
+    const unsigned nb2 = blockIdx.x + 2u * (unsigned)kSmCount;
+    if (nb2 < gridDim.x) {
+      const unsigned b2 = nb2 / (unsigned)n_chunks, c2 = nb2 - b2 * (unsigned)n_chunks;
+      const char *nx = reinterpret_cast<const char *>(feat + ((size_t)b2 * C + (size_t)c2 * 4) * HW);
+      for (int i = threadIdx.x * 128; i < 4 * HW * 4; i += kWalkThreads * 128)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + i));
+    }
+    if (POOL == RLOD_POOL_AVG) {  // prescale in place once the async copies have landed
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();
+      for (int p = threadIdx.x; p < H * P; p += kWalkThreads) {
+        float4 v = planes4[p];
+        planes4[p] = make_float4(kPre * v.x, kPre * v.y, kPre * v.z, kPre * v.w);
+      }
+    }
+  }
+  {
+    const int padw = P - W;  // zero columns W .. P-1 of the data rows, then the two zero rows
+    for (int p = threadIdx.x; p < H * padw; p += kWalkThreads) {
+      const int yy = p / padw, xx = W + (p - yy * padw);
+      planes4[yy * P + xx] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int p = threadIdx.x; p < 2 * P; p += kWalkThreads) planes4[H * P + p] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k = lane & 7, slot = lane >> 3;
+  const uint32_t pbase = smem_u32(planes4);
+  float *stg = stage + (warp * 2) * (4 * SLOT) + slot * SLOT;  // + parity * 4 * SLOT
+  const int n_groups = (r1 - r0 + 3) >> 2;
+  const bool kst = POOL == RLOD_POOL_NONE || k < 7;  // this lane stores (lane 7 only pools for lane 6)
+
+  auto roi_of = [&](int gg) {
+    const int kk = r0 + 4 * gg + slot;
+    return (gg < n_groups && kk < r1) ? __ldg(order + kk) : -1;
+  };
+  // two record register sets: one is computed while the other is loaded
+  WalkRec recA, recB;
+  walk_rec_clear(recA);
+  int ra = roi_of(warp);
+  if (ra >= 0) walk_rec_load(ext, ra, k, recA);
+  int rb = roi_of(warp + kWalkWarps);
+  WalkTaps2 taps;
+  taps.x0 = taps.x1 = taps.y0 = taps.y1 = taps.z0 = taps.z1 = taps.w0 = taps.w1 = 0ull;
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  // one group of four rois; PAR = parity of the staging buffer (compile-time)
+  auto body = [&](const WalkRec &cur, int r, WalkRec &nxt, int rn, int it, auto par) {
+    constexpr int PAR = decltype(par)::value;
+    walk_rec_clear(nxt);
+    if (rn >= 0) walk_rec_load(ext, rn, k, nxt);
+    float *sbuf = stg + PAR * (4 * SLOT);
+    const bool mode1 = (cur.w[0] >> 30) & 1;
+    const int st_t = mode1 ? 1 : OW, st_k = mode1 ? OW : 1;
+    float *sp = sbuf + k * st_k;
+    const uint32_t cbase = pbase + (((uint32_t)cur.la & 0xffffu) << 4);
+    const uint32_t cbase2 = cbase + (uint32_t)((cur.la >> 16) << 4);
+    const u64 wa2 = pack2(cur.wa, cur.wa);
+    F4 s[8];
+    // LOAD(T): the predicated tap fetches of walk position T; MATH(T): its three lerps per channel pair
+#define RLOD_LOAD2(T)                                                                        \
+  {                                                                                          \
+    const uint32_t oa = (uint32_t)cur.w[T] & 0x1fff0u, ob = ((uint32_t)cur.w[T] >> 13) & 0x1fff0u; \
+    walk_load2(taps, cbase + oa, cbase2 + oa, cbase + ob, cbase2 + ob, cur.w[T]);            \
+  }
+#define RLOD_MATH2(T)                                                                        \
+  {                                                                                          \
+    const u64 r2 = pack2(cur.rt[T], cur.rt[T]);                                              \
+    s[T].a = lerp2(lerp2(taps.x0, taps.y0, wa2), lerp2(taps.z0, taps.w0, wa2), r2);          \
+    s[T].b = lerp2(lerp2(taps.x1, taps.y1, wa2), lerp2(taps.z1, taps.w1, wa2), r2);          \
+  }
+#define RLOD_EMIT2(T)                                                                        \
+  if (POOL == RLOD_POOL_NONE) {                                                              \
+    float *q = sp + (T) * st_t;                                                              \
+    const float2 lo = unpack2(s[T].a), hi = unpack2(s[T].b);                                 \
+    q[0] = lo.x, q[OHW] = lo.y, q[2 * OHW] = hi.x, q[3 * OHW] = hi.y;                        \
+  } else if ((T) < 7) {                                                                      \
+    u64 va, vb;                                                                              \
+    if (POOL == RLOD_POOL_AVG) {                                                             \
+      va = add2(s[T].a, s[(T) < 7 ? (T) + 1 : 7].a), vb = add2(s[T].b, s[(T) < 7 ? (T) + 1 : 7].b); \
+    } else {                                                                                 \
+      va = max2(s[T].a, s[(T) < 7 ? (T) + 1 : 7].a), vb = max2(s[T].b, s[(T) < 7 ? (T) + 1 : 7].b); \
+    }                                                                                        \
+    const u64 na = shfl_down8(va), nb = shfl_down8(vb);                                      \
+    const u64 oa = POOL == RLOD_POOL_AVG ? add2(va, na) : max2(va, na);                      \
+    const u64 ob = POOL == RLOD_POOL_AVG ? add2(vb, nb) : max2(vb, nb);                      \
+    if (kst) {                                                                               \
+      float *q = sp + (T) * st_t;                                                            \
+      const float2 lo = unpack2(oa), hi = unpack2(ob);                                       \
+      q[0] = lo.x, q[OHW] = lo.y, q[2 * OHW] = hi.x, q[3 * OHW] = hi.y;                      \
+    }                                                                                        \
+  }
+    // software pipeline: the loads of position T+1 are issued right after the math of T has read the taps, and
+    // the pooling / stores of position T-1 sit in their shadow
+    RLOD_LOAD2(0)
+    RLOD_MATH2(0) RLOD_LOAD2(1)
+    // the buffer about to be written was handed to the bulk-copy engine two iterations ago
+    if (it >= 2) {
+      if (k == 0) bulk_wait_read<1>();
+      __syncwarp();
+    }
+    RLOD_MATH2(1) RLOD_LOAD2(2) RLOD_EMIT2(0)
+    RLOD_MATH2(2) RLOD_LOAD2(3) RLOD_EMIT2(1)
+    RLOD_MATH2(3) RLOD_LOAD2(4) RLOD_EMIT2(2)
+    RLOD_MATH2(4) RLOD_LOAD2(5) RLOD_EMIT2(3)
+    RLOD_MATH2(5) RLOD_LOAD2(6) RLOD_EMIT2(4)
+    RLOD_MATH2(6) RLOD_LOAD2(7) RLOD_EMIT2(5)
+    RLOD_MATH2(7) RLOD_EMIT2(6) RLOD_EMIT2(7)
+#undef RLOD_LOAD2
+#undef RLOD_MATH2
+#undef RLOD_EMIT2
+    fence_async_smem();
+    __syncwarp();
+    if (k == 0) {
+      if (r >= 0)
+        bulk_s2g_nocommit(out + ((size_t)r * C + (size_t)chunk * 4) * OHW, sbuf, (uint32_t)(STG * sizeof(float)));
+      bulk_commit();
+    }
+  };
+  using P0 = std::integral_constant<int, 0>;
+  using P1 = std::integral_constant<int, 1>;
+  for (int g = warp, it = 0; g < n_groups;) {
+    const int rc = roi_of(g + 2 * kWalkWarps);
+    body(recA, ra, recB, rb, it, P0{});
+    g += kWalkWarps, ++it;
+    if (g >= n_groups) break;
+    const int rd = roi_of(g + 2 * kWalkWarps);
+    body(recB, rb, recA, rc, it, P1{});
+    g += kWalkWarps, ++it;
+    ra = rc, rb = rd;
+  }
+  if (k == 0) bulk_wait_read<0>();  // shared memory must outlive the engine's reads
+}
+
+// ----------------------------------------------------------------------------------------
 // generic backward (atomics): NONE / AVG one thread per sample point, MAX one thread per
 // pooled output (argmax recomputed from feat: first maximum in row-major window order, the
 // rule of ATen's max_pool2d backward).
@@ -1119,14 +1412,29 @@ RLOD_API int rlod_roi_align_forward(const float *feat, const float *rois, int B,
     RLOD_LAUNCH(RLOD_KERNEL_ROI_PLAN, st,
                 k_roi_plan8_walk<<<(unsigned)cdiv(R, 4), 128, 0, st>>>(rois, R, B, H, W, P, spatial_scale, 0, ws));
     RLOD_LAUNCH(RLOD_KERNEL_ROI_PLAN, st, k_roi_group_fixup<<<1, 32, 0, st>>>(R, B, ws));
+    static const bool v1 = getenv("RLOD_FWD_V1") != nullptr;  // A/B switch: the scalar walk of round 1
+    if (!v1)  // every image's list partitioned by walk mode: the four rois of a warp stage alike
+      RLOD_LAUNCH(RLOD_KERNEL_ROI_PLAN, st,
+                  k_roi_order_by_key<<<B, kOrderThreads, 0, st>>>(ws.ext, ws.order, ws.img_off, 0, 30, 2, ws.order2));
 #define RLOD_LAUNCH_FWD(POOL)                                                                  \
   do {                                                                                         \
-    cudaFuncSetAttribute(k_align8_fwd_walk<POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                         (int)smem);                                                           \
+    static bool attr_set = false;                                                              \
+    if (!attr_set) {                                                                           \
+      cudaFuncSetAttribute(k_align8_fwd_walk<POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                           kMaxSmemPerCta);                                                    \
+      cudaFuncSetAttribute(k_align8_fwd_walk2<POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                           kMaxSmemPerCta);                                                    \
+      attr_set = true;                                                                         \
+    }                                                                                          \
     ProfScope _ps(RLOD_KERNEL_ALIGN_FWD, st);                                                  \
-    k_align8_fwd_walk<POOL><<<grid, kWalkThreads, smem, st>>>(feat, ws.ext, ws.order,          \
-                                                              ws.img_off, C, H, W, P,          \
-                                                              n_chunks, tma_fill, out);        \
+    if (v1)                                                                                    \
+      k_align8_fwd_walk<POOL><<<grid, kWalkThreads, smem, st>>>(feat, ws.ext, ws.order,        \
+                                                                ws.img_off, C, H, W, P,        \
+                                                                n_chunks, tma_fill, out);      \
+    else                                                                                       \
+      k_align8_fwd_walk2<POOL><<<grid, kWalkThreads, smem, st>>>(feat, ws.ext, ws.order2,      \
+                                                                 ws.img_off, C, H, W, P,       \
+                                                                 n_chunks, tma_fill, out);     \
   } while (0)
     if (pool_mode == RLOD_POOL_NONE)
       RLOD_LAUNCH_FWD(RLOD_POOL_NONE);
