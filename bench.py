@@ -20,7 +20,7 @@ One JSON line on rank 0 (see the task contract): value = device-resident through
 through the public API from pinned HOST buffers (H2D of all inputs + D2H of detections and
 rewards inside the timed region), e2e_features_resident = the same with the feature map already
 on the device (where the reference's backbone leaves it, faster_rcnn.py:47), roofline = the
-dominant kernel (k_align8_fwd_walk) timed live with CUDA events on its own stream, cpu_baseline /
+dominant kernel (k_align8_fwd_walk2) timed live with CUDA events on its own stream, cpu_baseline /
 --impl reference = the reference's own Python for the stages it has on the CPU + the CPU port
 (oracle/) for its CUDA-only stages (baseline/ref_arm.py), ops = every other BASELINE config next
 to the reference's legacy CUDA kernels, verified = the timed step's outputs against the oracle.
@@ -544,7 +544,7 @@ def run_ours(args, rank, local_rank, world):
         except (OSError, ValueError):
             pass
     roofline = {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None,
-                "traffic": traffic, "kernel": "k_align8_fwd_walk<AVG>", "peak_source": peak_src,
+                "traffic": traffic, "kernel": "k_align8_fwd_walk2<AVG>", "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "timed": "CUDA events around every launch of the kernel inside the timed region" if not graphed else
                          f"CUDA events around the kernel's launches in {extra_steps} untimed eager steps after the "

@@ -86,6 +86,32 @@ __device__ __forceinline__ void bulk_s2g_nocommit(void *dst_gmem, const void *sr
                "r"(smem_u32(src_smem)), "r"(bytes)
                : "memory");
 }
+// the same with an L2 eviction policy (createpolicy): streamed outputs are marked evict-first so
+// that they do not push the prefetched feature planes out of L2
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void bulk_s2g_hint_nocommit(void *dst_gmem, uint32_t src_smem, uint32_t bytes,
+                                                       uint64_t policy) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst_gmem),
+               "r"(src_smem), "r"(bytes), "l"(policy)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_hint(void *dst_smem, const void *src_gmem, uint32_t bytes,
+                                              uint64_t *bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
 __device__ __forceinline__ void bulk_commit() {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }

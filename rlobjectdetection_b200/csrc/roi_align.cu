@@ -845,8 +845,8 @@ __global__ void __launch_bounds__(kWalkThreads, 2)
       mbar_expect_tx(fill_bar, total);
       for (int c = 0; c < 4; ++c) {
         const uint32_t skew = (uint32_t)((size_t)c * HW * 4) & 15u;
-        bulk_g2s(buf[c], reinterpret_cast<const char *>(src + (size_t)c * HW) - skew,
-                 (skew + (uint32_t)HW * 4 + 15u) & ~15u, fill_bar);
+        bulk_g2s_hint(buf[c], reinterpret_cast<const char *>(src + (size_t)c * HW) - skew,
+                      (skew + (uint32_t)HW * 4 + 15u) & ~15u, fill_bar, l2_policy_evict_first());
       }
     }
     __syncthreads();  // barrier initialised before anyone polls it
@@ -857,7 +857,7 @@ __global__ void __launch_bounds__(kWalkThreads, 2)
         const unsigned b2 = nb2 / (unsigned)n_chunks, c2 = nb2 - b2 * (unsigned)n_chunks;
         const char *nx = reinterpret_cast<const char *>(feat + ((size_t)b2 * C + (size_t)c2 * 4) * HW);
         for (int i = threadIdx.x * 128; i < 4 * HW * 4; i += kWalkThreads * 128)
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + i));
+          asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(nx + i));
       }
     }
     mbar_wait(fill_bar, 0);
@@ -892,7 +892,7 @@ __global__ void __launch_bounds__(kWalkThreads, 2)
       const unsigned b2 = nb2 / (unsigned)n_chunks, c2 = nb2 - b2 * (unsigned)n_chunks;
       const char *nx = reinterpret_cast<const char *>(feat + ((size_t)b2 * C + (size_t)c2 * 4) * HW);
       for (int i = threadIdx.x * 128; i < 4 * HW * 4; i += kWalkThreads * 128)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + i));
+        asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(nx + i));
     }
     if (POOL == RLOD_POOL_AVG) {  // prescale in place once the async copies have landed
       asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -918,6 +918,9 @@ __global__ void __launch_bounds__(kWalkThreads, 2)
   float *stg = stage + (warp * 2) * (4 * SLOT) + slot * SLOT;  // + parity * 4 * SLOT
   const int n_groups = (r1 - r0 + 3) >> 2;
   const bool kst = POOL == RLOD_POOL_NONE || k < 7;  // this lane stores (lane 7 only pools for lane 6)
+  float *out_chunk = out + (size_t)chunk * 4 * OHW;
+  const size_t roi_pitch = (size_t)C * OHW;
+  const uint64_t pol_out = l2_policy_evict_first();
 
   auto roi_of = [&](int gg) {
     const int kk = r0 + 4 * gg + slot;
@@ -986,7 +989,7 @@ __global__ void __launch_bounds__(kWalkThreads, 2)
     RLOD_MATH2(0) RLOD_LOAD2(1)
     // the buffer about to be written was handed to the bulk-copy engine two iterations ago
     if (it >= 2) {
-      if (k == 0) bulk_wait_read<1>();
+      if (lane == 0) bulk_wait_read<1>();
       __syncwarp();
     }
     RLOD_MATH2(1) RLOD_LOAD2(2) RLOD_EMIT2(0)
@@ -1001,10 +1004,19 @@ __global__ void __launch_bounds__(kWalkThreads, 2)
 #undef RLOD_EMIT2
     fence_async_smem();
     __syncwarp();
-    if (k == 0) {
-      if (r >= 0)
-        bulk_s2g_nocommit(out + ((size_t)r * C + (size_t)chunk * 4) * OHW, sbuf, (uint32_t)(STG * sizeof(float)));
-      bulk_commit();
+    // lane 0 hands the four staged blocks to the bulk-copy engine (one issuing lane: the compiler serialises
+    // divergent UBLKCP issuers through a vote loop, ~12 instructions per issuer), marked evict-first in L2
+    {
+      const int r1_ = __shfl_sync(0xffffffffu, r, 8), r2_ = __shfl_sync(0xffffffffu, r, 16), r3_ = __shfl_sync(0xffffffffu, r, 24);
+      if (lane == 0) {
+        const uint32_t sb = smem_u32(sbuf);
+        const int rr[4] = {r, r1_, r2_, r3_};
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (rr[q] >= 0)
+            bulk_s2g_hint_nocommit(out_chunk + (size_t)rr[q] * roi_pitch, sb + q * (SLOT * 4), (uint32_t)(STG * sizeof(float)), pol_out);
+        bulk_commit();
+      }
     }
   };
   using P0 = std::integral_constant<int, 0>;
@@ -1019,7 +1031,7 @@ __global__ void __launch_bounds__(kWalkThreads, 2)
     g += kWalkWarps, ++it;
     ra = rc, rb = rd;
   }
-  if (k == 0) bulk_wait_read<0>();  // shared memory must outlive the engine's reads
+  if (lane == 0) bulk_wait_read<0>();  // shared memory must outlive the engine's reads
 }
 
 // ----------------------------------------------------------------------------------------
