@@ -17,6 +17,8 @@
 //          separately like the eager torch expression it replaces.
 //   k_nms_mask + k_nms_scan (nms.cu): batched NMS; the scan stops at post_nms_topN keeps
 //       and writes the zero-padded (B, post_nms_topN, 5) output itself (:151-159).
+#include <cstdlib>
+
 #include "nms_device.cuh"
 
 namespace rlod {
@@ -225,6 +227,327 @@ __global__ void __launch_bounds__(kSortThreads) k_proposal_sort_decode(PropArgs 
   for (int i = t; i < M; i += kSortThreads) sel[i] = keys[sidx(i)];
 }
 
+// ----------------------------------------------------------------------------------------
+// k_proposal_cluster: select + sort spread over a thread-block CLUSTER of 8 CTAs per image
+// (distributed shared memory), instead of one 1024-thread CTA with 180 KB of shared memory
+// per image (24 of 148 SMs at C4).  CTA c of the cluster owns the pixels [c * HWc, (c+1) * HWc)
+// -- a contiguous range of anchor indices, since idx = pix * A + a -- and holds their 32-bit
+// score keys in its own shared memory (22.5 KB at C4).
+//   1. SELECT: the M-th smallest key by radix select, 8 bits per pass, 4 passes: local
+//      256-bin histogram of the keys that match the digits fixed so far, summed into CTA 0's
+//      shared memory by remote atomics (red.shared::cluster), read back by every CTA after a
+//      cluster barrier.  Ties at the threshold are cut by anchor index (lower index first),
+//      which is a prefix over the CTAs because they own index ranges in order.
+//   2. BALANCE: every CTA writes its selected composite keys (key << 32 | idx) into a sort
+//      buffer that is distributed over the cluster by global position (st.shared::cluster),
+//      so each CTA sorts exactly ceil(M / 8) keys whatever the spatial distribution of scores.
+//   3. SORT: bitonic sort of the local buffer.
+//   4. MERGE: the final rank of a key = its local rank + the number of smaller keys in each of
+//      the 7 other sorted lists (binary search through ld.shared::cluster); the key goes
+//      straight to its place in the global `sel` row.
+// Same result as k_proposal_sort_decode bit for bit (all composite keys are distinct).
+// ----------------------------------------------------------------------------------------
+constexpr int kClusterSize = 8;
+constexpr int kClThreads = 512;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local_smem_addr` in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t dsmem_addr(uint32_t local_smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void dsmem_red_add(uint32_t addr, uint32_t v) {
+  asm volatile("red.relaxed.cluster.shared::cluster.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t dsmem_ld32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long dsmem_ld64(uint32_t addr) {
+  unsigned long long v;
+  asm volatile("ld.shared::cluster.u64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void dsmem_st64(uint32_t addr, unsigned long long v) {
+  asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
+}
+__device__ __forceinline__ void dsmem_st32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+// bitonic_pass for a CTA of NT threads (same network as above)
+template <int NL, int NT>
+__device__ __forceinline__ void bitonic_pass_nt(unsigned long long *keys, int mp, int k, int jl, int t) {
+  constexpr int Q = 1 << NL;
+  const int sh = 31 - __clz(jl);
+  for (int p = t; p < (mp >> NL); p += NT) {
+    const int base = ((p >> sh) << (sh + NL)) | (p & (jl - 1));
+    const bool up = (base & k) == 0;
+    unsigned long long x[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) x[q] = keys[sidx(base + q * jl)];
+#pragma unroll
+    for (int s = Q >> 1; s >= 1; s >>= 1)
+#pragma unroll
+      for (int q = 0; q < Q; ++q)
+        if ((q & s) == 0) cmpex(x[q], x[q | s], up);
+#pragma unroll
+    for (int q = 0; q < Q; ++q) keys[sidx(base + q * jl)] = x[q];
+  }
+}
+
+// shared-memory layout of one CTA of the cluster (byte offsets from the dynamic base)
+struct ClLayout {
+  int hwc;      // pixels per CTA
+  int kac;      // keys per CTA = hwc * A
+  int cap;      // sort-buffer keys per CTA (power of two >= ceil(M / 8))
+  size_t off_sort, off_hist, off_whist, off_cnt, bytes;
+};
+static __host__ __device__ inline ClLayout cl_layout(int A, int HW, int M) {
+  ClLayout l;
+  l.hwc = (HW + kClusterSize - 1) / kClusterSize;
+  l.kac = l.hwc * A;
+  int per = (M + kClusterSize - 1) / kClusterSize, cap = 64;
+  while (cap < per) cap <<= 1;
+  l.cap = cap;
+  size_t off = ((size_t)l.kac * 4 + 15) & ~(size_t)15;
+  l.off_sort = off;
+  off += (size_t)(cap + (cap >> 3)) * 8;
+  l.off_hist = off;          // [4 passes][256] cluster histograms (CTA 0's copy is the sum) + [256] local
+  off += 5 * 256 * 4;        //   + [warps][256] private histograms
+  l.off_whist = off;
+  off += (size_t)(kClThreads / 32) * 256 * 4;
+  l.off_cnt = off;           // [8] lt counts, [8] eq counts (CTA 0's copy is authoritative), scratch
+  off += 32 * 4;
+  l.bytes = off;
+  return l;
+}
+
+__global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kClThreads)
+    k_proposal_cluster(PropArgs a, int mp) {
+  extern __shared__ __align__(16) unsigned char cl_raw[];
+  const int HW = a.H * a.W, KA = HW * a.A, M = a.pre;
+  const ClLayout L = cl_layout(a.A, HW, M);
+  uint32_t *skeys = reinterpret_cast<uint32_t *>(cl_raw);
+  unsigned long long *sortb = reinterpret_cast<unsigned long long *>(cl_raw + L.off_sort);
+  uint32_t *ghist = reinterpret_cast<uint32_t *>(cl_raw + L.off_hist);   // [4][256]
+  uint32_t *lhist = ghist + 4 * 256;                                      // [256]
+  uint32_t *whist = reinterpret_cast<uint32_t *>(cl_raw + L.off_whist);   // [warps][256]
+  uint32_t *cnts = reinterpret_cast<uint32_t *>(cl_raw + L.off_cnt);     // [0..7] lt, [8..15] eq, [16] local sel count
+  __shared__ uint32_t s_digit, s_remaining, s_tie_index;
+  const int t = threadIdx.x, lane = t & 31;
+  const uint32_t c = cluster_ctarank();
+  const int b = blockIdx.x / kClusterSize;
+  const float *fg = a.scores + ((size_t)b * 2 * a.A + a.A) * HW;
+  const int pix0 = (int)c * L.hwc, npix = max(0, min(L.hwc, HW - pix0));
+  const int n_loc = npix * a.A, idx0 = pix0 * a.A;  // this CTA's anchor indices [idx0, idx0 + n_loc)
+
+  // ---- keys of my pixels: one coalesced run per anchor plane --------------------------------
+  for (int an = 0; an < a.A; ++an) {
+    const float *src = fg + (size_t)an * HW + pix0;
+    for (int p = t; p < npix; p += kClThreads) skeys[p * a.A + an] = desc_key(__ldg(src + p));
+  }
+  for (int i = t; i < 5 * 256; i += kClThreads) ghist[i] = 0u;
+  if (t < 32) cnts[t] = 0u;
+  for (int i = t; i < L.cap; i += kClThreads) sortb[sidx(i)] = ~0ull;
+  __syncthreads();
+  cluster_sync_all();  // every CTA's shared memory is initialised before anyone writes into it
+
+  const uint32_t ghist0 = dsmem_addr(smem_u32(ghist), 0);
+  const uint32_t cnts0 = dsmem_addr(smem_u32(cnts), 0);
+  uint32_t T = 0xffffffffu, r_T = 0u;  // threshold key, number of keys == T to take (cluster-wide)
+  const bool all = M >= KA;
+  if (!all) {
+    // ---- radix select of the M-th smallest key ----------------------------------------------
+    uint32_t prefix = 0u, remaining = (uint32_t)M;
+    for (int pass = 0; pass < 4; ++pass) {
+      const int shift = 24 - 8 * pass;
+      for (int i = t; i < (kClThreads / 32) * 256; i += kClThreads) whist[i] = 0u;
+      __syncthreads();
+      // per-warp private histograms: the leading byte of a probability's key takes a handful of values, and
+      // 5 600 same-address atomics on ONE shared histogram serialise across the whole CTA
+      for (int i = t; i < n_loc; i += kClThreads) {
+        const uint32_t kv = skeys[i];
+        if (pass == 0 || (kv >> (shift + 8)) == prefix) atomicAdd(&whist[(t >> 5) * 256 + ((kv >> shift) & 255u)], 1u);
+      }
+      __syncthreads();
+      if (t < 256) {
+        uint32_t v = 0u;
+#pragma unroll
+        for (int w = 0; w < kClThreads / 32; ++w) v += whist[w * 256 + t];
+        if (v) dsmem_red_add(ghist0 + (uint32_t)(pass * 256 + t) * 4u, v);
+      }
+      cluster_sync_all();
+      // every CTA finds the digit itself from CTA 0's summed histogram
+      if (t < 256) lhist[t] = dsmem_ld32(ghist0 + (uint32_t)(pass * 256 + t) * 4u);
+      __syncthreads();
+      if (t < 32) {
+        // 8 bins per lane, warp scan of the lane sums, then the crossing bin
+        uint32_t v[8], sum = 0u;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = lhist[lane * 8 + q], sum += v[q];
+        uint32_t inc = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+          if (lane >= d) inc += o;
+        }
+        uint32_t before = inc - sum;  // keys in bins below this lane's
+        const bool mine = before < remaining && remaining <= inc;
+        if (mine) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            if (remaining > before && remaining <= before + v[q]) {
+              s_digit = (uint32_t)(lane * 8 + q);
+              s_remaining = remaining - before;
+            }
+            before += v[q];
+          }
+        }
+      }
+      __syncthreads();
+      prefix = (prefix << 8) | s_digit;
+      remaining = s_remaining;
+      __syncthreads();
+    }
+    T = prefix;
+    r_T = remaining;
+  }
+  // ---- counts: keys < T and == T per CTA, published in CTA 0 --------------------------------
+  {
+    uint32_t lt = 0u, eq = 0u;
+    for (int i = t; i < n_loc; i += kClThreads) {
+      const uint32_t kv = skeys[i];
+      lt += (all || kv < T) ? 1u : 0u;
+      eq += (!all && kv == T) ? 1u : 0u;
+    }
+    lt = __reduce_add_sync(0xffffffffu, lt);
+    eq = __reduce_add_sync(0xffffffffu, eq);
+    if (lane == 0) {
+      if (lt) dsmem_red_add(cnts0 + c * 4u, lt);
+      if (eq) dsmem_red_add(cnts0 + (8u + c) * 4u, eq);
+    }
+  }
+  cluster_sync_all();
+  uint32_t lt_c[kClusterSize], eq_c[kClusterSize];
+#pragma unroll
+  for (int q = 0; q < kClusterSize; ++q) lt_c[q] = dsmem_ld32(cnts0 + q * 4u), eq_c[q] = dsmem_ld32(cnts0 + (8u + q) * 4u);
+  // ties at T go to the lowest anchor indices: CTA q takes take_q = clamp(r_T - sum_{q' < q} eq_q', 0, eq_q)
+  uint32_t base = 0u, my_take = 0u, eq_before = 0u;
+#pragma unroll
+  for (int q = 0; q < kClusterSize; ++q) {
+    const uint32_t left = r_T > eq_before ? r_T - eq_before : 0u;
+    const uint32_t take_q = min(left, eq_c[q]);
+    if (q < (int)c) base += lt_c[q] + take_q;
+    if (q == (int)c) my_take = take_q;
+    eq_before += eq_c[q];
+  }
+  // partial ties inside this CTA: the index of its my_take-th tie (ordered walk by one warp; rare)
+  uint32_t tie_hi = 0xffffffffu;  // take ties with local index <= tie_hi
+  if (!all && my_take < eq_c[c]) {
+    if (t < 32) {
+      uint32_t seen = 0u, found = 0xffffffffu;
+      if (my_take == 0u) found = 0u;  // none: "index <= found" must fail -> handled below by my_take == 0
+      for (int i0 = 0; i0 < n_loc && found == 0xffffffffu; i0 += 32) {
+        const int i = i0 + lane;
+        const bool hit = i < n_loc && skeys[i] == T;
+        const unsigned bal = __ballot_sync(0xffffffffu, hit);
+        const uint32_t cntb = (uint32_t)__popc(bal);
+        if (seen + cntb >= my_take) {
+          // the (my_take - seen)-th set bit of bal
+          unsigned m = bal;
+          for (uint32_t q = 1; q < my_take - seen; ++q) m &= m - 1u;
+          found = (uint32_t)(i0 + __ffs(m) - 1);
+        }
+        seen += cntb;
+      }
+      if (lane == 0) s_tie_index = found;
+    }
+    __syncthreads();
+    tie_hi = s_tie_index;
+  }
+  // ---- compaction into the cluster-distributed sort buffer ------------------------------------
+  const uint32_t sort_local = smem_u32(sortb);
+  for (int i0 = 0; i0 < n_loc; i0 += kClThreads) {
+    const int i = i0 + t;
+    bool take = false;
+    uint32_t kv = 0u;
+    if (i < n_loc) {
+      kv = skeys[i];
+      take = all || kv < T || (kv == T && my_take > 0u && (uint32_t)i <= tie_hi);
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, take);
+    unsigned wbase = 0;
+    if (lane == 0 && bal) wbase = atomicAdd(&cnts[16], (unsigned)__popc(bal));
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+    if (take) {
+      const uint32_t pos = base + wbase + (uint32_t)__popc(bal & ((1u << lane) - 1u));
+      const uint32_t owner = pos / (uint32_t)L.cap, slot = pos - owner * (uint32_t)L.cap;
+      if (owner < (uint32_t)kClusterSize)
+        dsmem_st64(dsmem_addr(sort_local + (uint32_t)sidx((int)slot) * 8u, owner),
+                   ((unsigned long long)kv << 32) | (unsigned)(idx0 + i));
+    }
+  }
+  cluster_sync_all();
+  // ---- local bitonic sort (cap keys, padded with ~0) ------------------------------------------
+  for (int k = 2; k <= L.cap; k <<= 1) {
+    int j = k >> 1;
+    while (j >= 1) {
+      if (j >= 4) {
+        bitonic_pass_nt<3, kClThreads>(sortb, L.cap, k, j >> 2, t);
+        j >>= 3;
+      } else if (j == 2) {
+        bitonic_pass_nt<2, kClThreads>(sortb, L.cap, k, 1, t);
+        j = 0;
+      } else {
+        bitonic_pass_nt<1, kClThreads>(sortb, L.cap, k, 1, t);
+        j = 0;
+      }
+      __syncthreads();
+    }
+  }
+  cluster_sync_all();
+  // ---- merge by rank: local rank + smaller keys in the other seven sorted lists ---------------
+  unsigned long long *sel = a.sel + (size_t)b * mp;
+  uint32_t rbase[kClusterSize];
+#pragma unroll
+  for (int q = 0; q < kClusterSize; ++q) rbase[q] = dsmem_addr(sort_local, (uint32_t)q);
+  for (int i = t; i < L.cap; i += kClThreads) {
+    const unsigned long long key = sortb[sidx(i)];
+    if (key == ~0ull) continue;
+    // lower bound in all eight lists at once (independent probes: their latencies overlap); in the key's own
+    // list that is its local rank, because all composite keys are distinct
+    int lo[kClusterSize];
+#pragma unroll
+    for (int q = 0; q < kClusterSize; ++q) lo[q] = 0;
+    for (int half = L.cap >> 1; half >= 1; half >>= 1) {
+#pragma unroll
+      for (int q = 0; q < kClusterSize; ++q) {
+        const unsigned long long v = dsmem_ld64(rbase[q] + (uint32_t)sidx(lo[q] + half - 1) * 8u);
+        if (v < key) lo[q] += half;
+      }
+    }
+    uint32_t rank = 0u;
+#pragma unroll
+    for (int q = 0; q < kClusterSize; ++q) {
+      // lo[q] is in [0, cap - 1]: one more probe decides the last element
+      const unsigned long long v = dsmem_ld64(rbase[q] + (uint32_t)sidx(lo[q]) * 8u);
+      rank += (uint32_t)lo[q] + (v < key ? 1u : 0u);
+    }
+    if (rank < (uint32_t)M) sel[rank] = key;
+  }
+  cluster_sync_all();  // nobody leaves while its shared memory may still be read
+}
+
 // decode + clip the selected anchors in sorted order: one thread per (image, rank)
 __global__ void __launch_bounds__(256) k_proposal_decode(PropArgs a, int mp) {
   const int M = a.pre, HW = a.H * a.W;
@@ -336,11 +659,24 @@ RLOD_API int rlod_proposal_forward(const float *scores, const float *deltas, con
   pa.props = ws.props, pa.order_out = order_out, pa.props_out = props_out;
   pa.sel = ws.sel;
   pa.keys_in_smem = key_bytes <= (size_t)(kMaxSmemPerCta - 1024) ? 1 : 0;
-  size_t smem = (size_t)(mp + (mp >> 3)) * sizeof(unsigned long long);
-  if (pa.keys_in_smem && key_bytes > smem) smem = align_up(key_bytes, 16);
-  cudaFuncSetAttribute(k_proposal_sort_decode, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       (int)smem);
-  RLOD_LAUNCH(RLOD_KERNEL_PROPOSAL_SORT, st, k_proposal_sort_decode<<<B, kSortThreads, smem, st>>>(pa, mp));
+  // select + sort: a cluster of 8 CTAs per image when a slice of the keys and of the sort buffer fits one
+  // CTA's shared memory (always at the reference's shapes), else one big CTA per image
+  static const bool no_cluster = getenv("RLOD_PROPOSAL_V1") != nullptr;  // A/B switch: round 1's kernel
+  const ClLayout cl = cl_layout(A, H * W, pre);
+  if (!no_cluster && cl.bytes <= (size_t)(kMaxSmemPerCta - 1024)) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(k_proposal_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemPerCta - 1024);
+      attr_set = true;
+    }
+    RLOD_LAUNCH(RLOD_KERNEL_PROPOSAL_SORT, st,
+                k_proposal_cluster<<<B * kClusterSize, kClThreads, cl.bytes, st>>>(pa, mp));
+  } else {
+    size_t smem = (size_t)(mp + (mp >> 3)) * sizeof(unsigned long long);
+    if (pa.keys_in_smem && key_bytes > smem) smem = align_up(key_bytes, 16);
+    cudaFuncSetAttribute(k_proposal_sort_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    RLOD_LAUNCH(RLOD_KERNEL_PROPOSAL_SORT, st, k_proposal_sort_decode<<<B, kSortThreads, smem, st>>>(pa, mp));
+  }
   RLOD_LAUNCH(RLOD_KERNEL_PROPOSAL_SORT, st,
               k_proposal_decode<<<(unsigned)cdiv((long long)B * pre, 256), 256, 0, st>>>(pa, mp));
   int rc = launch_status();
