@@ -81,8 +81,10 @@ __device__ __forceinline__ void tri_decode(int idx, int nb, int &rb, int &cb) {
 __device__ __forceinline__ bool iou_gt(const float4 &a, float Sa, const float4 &b,
                                        const float2 &bwh, float thresh, bool zero_false) {
   const float left = fmaxf(a.x, b.x), right = fminf(a.z, b.z);
-  const float top = fmaxf(a.y, b.y), bottom = fminf(a.w, b.w);
   const float w = fmaxf(__fadd_rn(__fsub_rn(right, left), 1.f), 0.f);
+  // most pairs do not even overlap in x: w == 0 makes inter == +-0 or NaN (0 * inf), never > thresh >= 0
+  if (zero_false && w == 0.f) return false;
+  const float top = fmaxf(a.y, b.y), bottom = fminf(a.w, b.w);
   const float h = fmaxf(__fadd_rn(__fsub_rn(bottom, top), 1.f), 0.f);
   const float inter = __fmul_rn(w, h);
   if (zero_false && inter == 0.f) return false;

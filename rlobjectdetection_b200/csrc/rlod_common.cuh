@@ -156,6 +156,24 @@ __device__ __forceinline__ void fill_planes4_async(float4 *planes4, const float 
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
+// The same fill from a channels-last (NHWC) feature map: the 4 channels of a pixel are already one
+// contiguous, 16-byte aligned float4 (C % 4 == 0), C floats from the next pixel -- one 16-byte async
+// copy per pixel, no interleave at all.  A 32-byte DRAM sector holds two chunks' worth, so the CTAs
+// of neighbouring chunks (they run side by side) share every sector through L2.
+template <int THREADS>
+__device__ __forceinline__ void fill_planes4_nhwc_async(float4 *planes4, const float *__restrict__ src, int H,
+                                                        int W, int P, int C) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int y = warp; y < H; y += THREADS / 32) {
+    const float *s = src + (size_t)y * W * C;
+    const uint32_t d = smem_u32(planes4 + y * P);
+    for (int x = lane; x < W; x += 32)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 16u * (uint32_t)x), "l"(s + (size_t)x * C)
+                   : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
 // streaming (evict-first) 128-bit store / load: outputs and one-shot inputs must not push
 // the feature planes out of L2
 __device__ __forceinline__ void st_stream4(float *p, float4 v) {

@@ -830,7 +830,18 @@ __global__ void __launch_bounds__(kWalkThreads, 2)
   const float *src = feat + ((size_t)b * C + (size_t)chunk * 4) * HW;
   uint64_t *fill_bar = reinterpret_cast<uint64_t *>(stage + kWalkWarps * 2 * 4 * SLOT);
   // ---- fill (see k_align8_fwd_walk): bulk copies land the planes planar, threads interleave ----
-  if (tma_fill) {
+  // tma_fill: 1 = NCHW by bulk copies, 0 = NCHW by 4-byte async copies, 2 = channels-last input
+  if (tma_fill == 2) {
+    fill_planes4_nhwc_async<kWalkThreads>(planes4, feat + (size_t)b * HW * C + (size_t)chunk * 4, H, W, P, C);
+    if (POOL == RLOD_POOL_AVG) {  // prescale in place once the async copies have landed
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();
+      for (int p = threadIdx.x; p < H * P; p += kWalkThreads) {
+        float4 v = planes4[p];
+        planes4[p] = make_float4(kPre * v.x, kPre * v.y, kPre * v.z, kPre * v.w);
+      }
+    }
+  } else if (tma_fill) {
     const uint32_t plane_copy = (uint32_t)((HW * 4 + 8 + 15) & ~15);
     unsigned char *buf[4];
     buf[0] = smem_raw + (size_t)(H + 2) * P * 16 - plane_copy;
@@ -1399,7 +1410,7 @@ RLOD_API size_t rlod_roi_align_workspace_bytes(int B, int R, int ah, int aw, int
 
 RLOD_API int rlod_roi_align_forward(const float *feat, const float *rois, int B, int C, int H,
                                     int W, int R, int ah, int aw, float spatial_scale,
-                                    int pool_mode, float *out, void *workspace,
+                                    int pool_mode, int channels_last, float *out, void *workspace,
                                     size_t workspace_bytes, rlod_stream_t stream) {
   int rc = check_align_args(rois, B, C, H, W, R, ah, aw, pool_mode);
   if (rc != RLOD_OK) return rc;
@@ -1414,8 +1425,13 @@ RLOD_API int rlod_roi_align_forward(const float *feat, const float *rois, int B,
   const size_t smem = fwd_walk_smem(H, W, pool_mode) + 16;  // + the fill mbarrier
   const bool fast = GH == 8 && GW == 8 && (C % 4) == 0 && smem <= (size_t)kMaxSmemPerCta &&
                     (H + 2) * walk_pitch(W) <= 8192 && ((uintptr_t)out % 16) == 0 && R >= 2 * B;
+  // a channels-last map is only read by the plane kernel (its taps are contiguous float4s there); the
+  // generic kernels index NCHW planes
+  if (channels_last && (!fast || ((uintptr_t)feat % 16) != 0)) return RLOD_EUNSUPPORTED;
   if (fast) {
-    const int tma_fill = fwd_tma_fill_ok(feat, H, W, pool_mode) ? 1 : 0;
+    static const bool v1_ = getenv("RLOD_FWD_V1") != nullptr;
+    if (channels_last && v1_) return RLOD_EUNSUPPORTED;
+    const int tma_fill = channels_last ? 2 : (fwd_tma_fill_ok(feat, H, W, pool_mode) ? 1 : 0);
     const int n_chunks = C / 4;
     const unsigned grid = (unsigned)(B * n_chunks);
     const int P = walk_pitch(W);

@@ -74,8 +74,8 @@ __global__ void k_pool_plan(const float *__restrict__ rois, int R, int B, int H,
 __global__ void __launch_bounds__(kPoolThreads, 2)
     k_roi_pool7_fwd_planes(const float *__restrict__ feat, const int *__restrict__ rec,
                            const int *__restrict__ order, const int *__restrict__ img_off, int C,
-                           int H, int W, int P, int n_chunks, float *__restrict__ out,
-                           int *__restrict__ argmax) {
+                           int H, int W, int P, int n_chunks, int channels_last,
+                           float *__restrict__ out, int *__restrict__ argmax) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float4 *planes4 = reinterpret_cast<float4 *>(smem_raw);
   const int HW = H * W;
@@ -83,8 +83,12 @@ __global__ void __launch_bounds__(kPoolThreads, 2)
   const int b = blockIdx.x / n_chunks, chunk = blockIdx.x - b * n_chunks;
   const int r0 = img_off[b], r1 = img_off[b + 1];
   if (r0 >= r1) return;
-  const float *src = feat + ((size_t)b * C + (size_t)chunk * 4) * HW;
-  fill_planes4_async<kPoolThreads>(planes4, src, H, W, P, HW);
+  if (channels_last) {
+    fill_planes4_nhwc_async<kPoolThreads>(planes4, feat + (size_t)b * HW * C + (size_t)chunk * 4, H, W, P, C);
+  } else {
+    const float *src = feat + ((size_t)b * C + (size_t)chunk * 4) * HW;
+    fill_planes4_async<kPoolThreads>(planes4, src, H, W, P, HW);
+  }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k = lane & 7, slot = lane >> 3;
   const uint32_t pbase = smem_u32(planes4);
@@ -328,9 +332,9 @@ RLOD_API size_t rlod_roi_pool_workspace_bytes(int B, int R) {
 }
 
 RLOD_API int rlod_roi_pool_forward(const float *feat, const float *rois, int B, int C, int H,
-                                   int W, int R, int ph, int pw, float spatial_scale, float *out,
-                                   int *argmax, void *workspace, size_t workspace_bytes,
-                                   rlod_stream_t stream) {
+                                   int W, int R, int ph, int pw, float spatial_scale,
+                                   int channels_last, float *out, int *argmax, void *workspace,
+                                   size_t workspace_bytes, rlod_stream_t stream) {
   if (B < 0 || C < 0 || H < 1 || W < 1 || R < 0 || ph < 1 || pw < 1) return RLOD_EINVAL;
   if ((long long)B * C * H * W >= (1LL << 31)) return RLOD_EUNSUPPORTED;  // int argmax
   if (R == 0 || C == 0) return RLOD_OK;
@@ -343,6 +347,7 @@ RLOD_API int rlod_roi_pool_forward(const float *feat, const float *rois, int B, 
   const bool fast = ph == 7 && pw == 7 && (C % 4) == 0 && B >= 1 && smem <= (size_t)kMaxSmemPerCta &&
                     workspace && workspace_bytes >= ws.bytes && ((uintptr_t)out % 16) == 0 &&
                     (!argmax || ((uintptr_t)argmax % 16) == 0) && R >= 2 * B;
+  if (channels_last && (!fast || ((uintptr_t)feat % 16) != 0)) return RLOD_EUNSUPPORTED;  // plane kernel only
   if (fast) {
     cudaMemsetAsync(ws.flag, 0, 4 * sizeof(int), st);
     RLOD_LAUNCH(RLOD_KERNEL_ROI_PLAN, st, k_pool_plan<<<(unsigned)cdiv(R, 128), 128, 0, st>>>(rois, R, B, H, W, spatial_scale, ws));
@@ -353,7 +358,7 @@ RLOD_API int rlod_roi_pool_forward(const float *feat, const float *rois, int B, 
     cudaFuncSetAttribute(k_roi_pool7_fwd_planes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     RLOD_LAUNCH(RLOD_KERNEL_POOL_FWD, st,
                 k_roi_pool7_fwd_planes<<<(unsigned)(B * n_chunks), kPoolThreads, smem, st>>>(
-                    feat, ws.plan, ws.order2, ws.img_off, C, H, W, P, n_chunks, out, argmax));
+                    feat, ws.plan, ws.order2, ws.img_off, C, H, W, P, n_chunks, channels_last, out, argmax));
     return launch_status();
   }
   const long long total = (long long)R * C * ph * pw;

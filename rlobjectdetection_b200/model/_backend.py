@@ -40,11 +40,11 @@ SIGNATURES = {
     "rlod_debug_nms_force_large": (_I, [_I]),
     "rlod_nms_batched": (_I, [_P, _I, _P, _I, _I, _F, _I, _P, _P, _P, _Z, _P]),
     "rlod_roi_align_workspace_bytes": (_Z, [_I, _I, _I, _I, _I]),
-    "rlod_roi_align_forward": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P, _P, _Z, _P]),
+    "rlod_roi_align_forward": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _I, _I, _P, _P, _Z, _P]),
     "rlod_roi_align_backward": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _I, _I, _P, _P,
                                      _Z, _P]),
     "rlod_roi_pool_workspace_bytes": (_Z, [_I, _I]),
-    "rlod_roi_pool_forward": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P, _Z, _P]),
+    "rlod_roi_pool_forward": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P, _P, _P, _Z, _P]),
     "rlod_roi_pool_backward": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P, _P]),
     "rlod_proposal_workspace_bytes": (_Z, [_I, _I, _I, _I, _I, _I]),
     "rlod_proposal_forward": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P,
@@ -194,10 +194,24 @@ def _check_rois(features, rois):
         raise ValueError("features and rois must be on the same device")
 
 
+def feature_layout(features, what):
+    """(tensor to pass, channels_last flag) of a (B,C,H,W) feature map.  NCHW-dense and
+    channels-last (NHWC-dense) maps are read in place; anything else is refused rather than
+    silently copied (a C4 map is 369 MB)."""
+    if features.dtype != torch.float32:
+        raise TypeError(f"{what}: features must be float32")
+    if features.is_contiguous():
+        return features, 0
+    if features.is_contiguous(memory_format=torch.channels_last):
+        return features, 1
+    raise ValueError(f"{what}: features must be dense NCHW or channels-last; call .contiguous() explicitly")
+
+
 def roi_align_forward(features, rois, ah, aw, scale, pool_mode):
     require_cuda("roi_align", features, rois)
     _check_rois(features, rois)
-    features, rois = f32c(features), f32c(rois)
+    features, nhwc = feature_layout(features, "roi_align")
+    rois = f32c(rois)
     B, C, H, W = features.shape
     R = rois.size(0)
     out = torch.empty(R, C, ah, aw, dtype=torch.float32, device=features.device)
@@ -205,7 +219,7 @@ def roi_align_forward(features, rois, ah, aw, scale, pool_mode):
     with torch.cuda.device(features.device):
         ws = workspace(l.rlod_roi_align_workspace_bytes(B, R, ah, aw, pool_mode), features.device)
         check(l.rlod_roi_align_forward(ptr(features), ptr(rois), B, C, H, W, R, ah, aw,
-                                       float(scale), pool_mode, ptr(out), ptr(ws), ws.numel(),
+                                       float(scale), pool_mode, nhwc, ptr(out), ptr(ws), ws.numel(),
                                        stream_of(features)), "rlod_roi_align_forward")
     return out
 
@@ -221,6 +235,8 @@ def roi_align_backward(grad_out, rois, features, feature_size, ah, aw, scale, po
     accumulate = grad_in is not None
     if grad_in is None:
         grad_in = torch.empty(B, C, H, W, dtype=torch.float32, device=grad_out.device)
+    # RoIAlignMax recomputes its argmax from the features with the generic (NCHW) kernel: the one place a
+    # channels-last map is copied
     feat = f32c(features) if (features is not None and pool_mode == POOL_MAX) else None
     l = lib()
     with torch.cuda.device(grad_out.device):
@@ -235,7 +251,8 @@ def roi_align_backward(grad_out, rois, features, feature_size, ah, aw, scale, po
 def roi_pool_forward(features, rois, ph, pw, scale):
     require_cuda("roi_pool", features, rois)
     _check_rois(features, rois)
-    features, rois = f32c(features), f32c(rois)
+    features, nhwc = feature_layout(features, "roi_pool")
+    rois = f32c(rois)
     B, C, H, W = features.shape
     R = rois.size(0)
     out = torch.empty(R, C, ph, pw, dtype=torch.float32, device=features.device)
@@ -244,7 +261,7 @@ def roi_pool_forward(features, rois, ph, pw, scale):
     with torch.cuda.device(features.device):
         ws = workspace(l.rlod_roi_pool_workspace_bytes(B, R), features.device)
         check(l.rlod_roi_pool_forward(ptr(features), ptr(rois), B, C, H, W, R, ph, pw,
-                                      float(scale), ptr(out), ptr(argmax), ptr(ws), ws.numel(),
+                                      float(scale), nhwc, ptr(out), ptr(argmax), ptr(ws), ws.numel(),
                                       stream_of(features)), "rlod_roi_pool_forward")
     return out, argmax
 

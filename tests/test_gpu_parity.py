@@ -571,6 +571,63 @@ def test_move_from_act_corners_matches_reward():
     assert torch.equal(refined[:, :, 0], cu(rois)[:, :, 0])
 
 
+@pytest.mark.parametrize("pool", ["avg", "max", "none"])
+@pytest.mark.parametrize("shape", [(2, 64, 25, 38), (3, 32, 50, 75), (2, 16, 13, 21)])
+def test_roi_align_channels_last_input(orc, pool, shape):
+    # a channels-last (NHWC) feature map is read in place by the plane kernel: same values as the NCHW run,
+    # bit for bit (same taps, same arithmetic), and within 1e-5 of the oracle
+    B, C, H, W = shape
+    g = torch.Generator().manual_seed(61)
+    feat = torch.randn(B, C, H, W, generator=g)
+    rois = syn.rois_for_batch(62, B, 40, H * 16.0, W * 16.0)
+    mode = {"avg": be.POOL_AVG, "max": be.POOL_MAX, "none": be.POOL_NONE}[pool]
+    a = 8 if pool == "none" else 7
+    nchw = be.roi_align_forward(cu(feat), cu(rois), a, a, 1 / 16.0, mode)
+    f_cl = cu(feat).contiguous(memory_format=torch.channels_last)
+    assert not f_cl.is_contiguous()
+    nhwc = be.roi_align_forward(f_cl, cu(rois), a, a, 1 / 16.0, mode)
+    assert torch.equal(nchw, nhwc)
+    ref = orc.roi_align(feat.numpy(), rois.numpy(), a, a, 1 / 16.0, pool_mode={"avg": orc.POOL_AVG, "max": orc.POOL_MAX,
+                                                                               "none": orc.POOL_NONE}[pool])
+    close(nhwc.cpu().numpy(), ref)
+    # the module surface takes it too, forward and backward (the gradient comes back NCHW-dense)
+    from rlobjectdetection_b200.model.roi_align.modules.roi_align import RoIAlignAvg
+    if pool == "avg":
+        x = f_cl.clone().requires_grad_(True)
+        y = RoIAlignAvg(7, 7, 1 / 16.0)(x, cu(rois))
+        y.backward(torch.ones_like(y))
+        x2 = cu(feat).clone().requires_grad_(True)
+        y2 = RoIAlignAvg(7, 7, 1 / 16.0)(x2, cu(rois))
+        y2.backward(torch.ones_like(y2))
+        assert torch.equal(y, y2)
+        close(x.grad.cpu().numpy(), x2.grad.cpu().numpy())
+
+
+def test_roi_pool_channels_last_input(orc):
+    B, C, H, W = 2, 64, 38, 63
+    g = torch.Generator().manual_seed(63)
+    feat = torch.randn(B, C, H, W, generator=g)
+    rois = syn.rois_for_batch(64, B, 64, H * 16.0, W * 16.0)
+    o1, a1 = be.roi_pool_forward(cu(feat), cu(rois), 7, 7, 1 / 16.0)
+    o2, a2 = be.roi_pool_forward(cu(feat).contiguous(memory_format=torch.channels_last), cu(rois), 7, 7, 1 / 16.0)
+    assert torch.equal(o1, o2) and torch.equal(a1, a2)   # argmax keeps its NCHW meaning
+    ro, ra = orc.roi_pool(feat.numpy(), rois.numpy(), 7, 7, 1 / 16.0)
+    assert np.array_equal(o2.cpu().numpy(), ro) and np.array_equal(a2.cpu().numpy(), ra)
+
+
+def test_feature_layouts_are_not_silently_copied():
+    feat = torch.randn(2, 8, 50, 75, device=DEV)
+    rois = cu(syn.rois_for_batch(65, 2, 16, 800.0, 1200.0))
+    with pytest.raises(ValueError, match="dense NCHW or channels-last"):
+        be.roi_align_forward(feat[:, :, ::2], rois, 7, 7, 1 / 16.0, be.POOL_AVG)       # strided view
+    with pytest.raises(TypeError):
+        be.roi_align_forward(feat.double(), rois, 7, 7, 1 / 16.0, be.POOL_AVG)
+    # channels-last + a shape the plane kernel does not cover (C % 4 != 0): refused, not copied
+    odd = torch.randn(2, 6, 20, 30, device=DEV).contiguous(memory_format=torch.channels_last)
+    with pytest.raises(RuntimeError, match="unsupported|not supported"):
+        be.roi_align_forward(odd, rois, 7, 7, 1 / 16.0, be.POOL_AVG)
+
+
 @pytest.mark.parametrize("nact,ties", [(16, False), (56, False), (16, True)])
 def test_reward_refine_equals_unfused(orc, nact, ties):
     # rlod_reward_refine == rlod_action_reward(RCNN) -> copy -> rlod_move_from_act(maxk=N, rewards as preds) -> pack,

@@ -46,8 +46,8 @@ def test_invalid_arguments_are_rejected_without_a_gpu():
     lib = be.lib()
     # argument validation happens before any CUDA call
     assert lib.rlod_nms(None, -1, 5, 0.5, 0, None, None, None, 0, None) == -1
-    assert lib.rlod_roi_align_forward(None, None, 1, 4, 1, 5, 3, 7, 7, 0.0625, 1, None, None, 0, None) == -1
-    assert lib.rlod_roi_align_forward(None, None, 1, 4, 5, 5, 3, 7, 7, 0.0625, 9, None, None, 0, None) == -1
+    assert lib.rlod_roi_align_forward(None, None, 1, 4, 1, 5, 3, 7, 7, 0.0625, 1, 0, None, None, 0, None) == -1
+    assert lib.rlod_roi_align_forward(None, None, 1, 4, 5, 5, 3, 7, 7, 0.0625, 9, 0, None, None, 0, None) == -1
     assert lib.rlod_proposal_forward(None, None, None, None, 1, 9, 4, 4, 16, 100, 10, 0.7, None, None,
                                      None, None, None, 0, None) == -1
     with pytest.raises(RuntimeError, match="invalid argument"):

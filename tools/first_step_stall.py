@@ -20,7 +20,7 @@ def one(rec):
     feat, rois = be.f32c(f_), be.f32c(lt[0].view(-1, 5)); t = lap("f32c", t)
     out = torch.empty(rois.size(0), 1024, 7, 7, dtype=torch.float32, device=dev); t = lap("empty 1.4GB", t)
     ws = be.workspace(be.lib().rlod_roi_align_workspace_bytes(24, rois.size(0), 7, 7, 1), dev); t = lap("empty ws", t)
-    be.check(be.lib().rlod_roi_align_forward(be.ptr(feat), be.ptr(rois), 24, 1024, 50, 75, rois.size(0), 7, 7, 1 / 16.0, 1,
+    be.check(be.lib().rlod_roi_align_forward(be.ptr(feat), be.ptr(rois), 24, 1024, 50, 75, rois.size(0), 7, 7, 1 / 16.0, 1, 0,
                                             be.ptr(out), be.ptr(ws), ws.numel(), be.stream_of(feat)), "x"); t = lap("C call align", t)
     nxt = step._light_work(cur, light, s_, d_, i_, g_, True); t = lap("light work", t)
     cur.wait_event(have_refined)
