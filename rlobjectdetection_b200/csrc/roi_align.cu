@@ -266,8 +266,9 @@ __device__ __forceinline__ void occ_set(Occ &o, int i) {
 }
 
 // Best tap order for the lane-axis tap pairs (L[k], R[k]) (bit k set: lane k fetches R first).
-// The 32 lanes of the warp split the 256 orders: lane bits 0-4 fix the order of taps 0-4,
-// the loop runs over the orders of taps 5-7.  Returns cost << 8 | bits of this lane's best.
+// Swapping EVERY lane's order only exchanges the two requests, so tap 7 keeps its natural order and
+// 128 orders remain: lane bits 0-4 fix the order of taps 0-4, the loop runs over the orders of taps
+// 5-6.  Returns cost << 8 | bits of this lane's best.
 template <bool WIDE>
 __device__ __forceinline__ unsigned tap_order_search(const int *L, const int *R, int base, int lane) {
   Occ f = {0ull, 0ull}, s = {0ull, 0ull};
@@ -279,7 +280,7 @@ __device__ __forceinline__ unsigned tap_order_search(const int *L, const int *R,
   }
   unsigned best = 0xffffffffu;
 #pragma unroll 1
-  for (int j = 0; j < 8; ++j) {
+  for (int j = 0; j < 4; ++j) {
     Occ ff = f, ss = s;
 #pragma unroll
     for (int k = 5; k < 8; ++k) {
@@ -1439,11 +1440,15 @@ RLOD_API int rlod_roi_align_forward(const float *feat, const float *rois, int B,
     cudaMemsetAsync(ws.flag, 0, 4 * sizeof(int), st);
     RLOD_LAUNCH(RLOD_KERNEL_ROI_PLAN, st,
                 k_roi_plan8_walk<<<(unsigned)cdiv(R, 4), 128, 0, st>>>(rois, R, B, H, W, P, spatial_scale, 0, ws));
-    RLOD_LAUNCH(RLOD_KERNEL_ROI_PLAN, st, k_roi_group_fixup<<<1, 32, 0, st>>>(R, B, ws));
     static const bool v1 = getenv("RLOD_FWD_V1") != nullptr;  // A/B switch: the scalar walk of round 1
-    if (!v1)  // every image's list partitioned by walk mode: the four rois of a warp stage alike
+    if (v1) {
+      RLOD_LAUNCH(RLOD_KERNEL_ROI_PLAN, st, k_roi_group_fixup<<<1, 32, 0, st>>>(R, B, ws));
+    } else {
+      // group fix-up + partition of every image's list by walk mode (the four rois of a warp then stage alike)
+      // in one launch
       RLOD_LAUNCH(RLOD_KERNEL_ROI_PLAN, st,
-                  k_roi_order_by_key<<<B, kOrderThreads, 0, st>>>(ws.ext, ws.order, ws.img_off, 0, 30, 2, ws.order2));
+                  k_roi_lists_finish<<<B, kOrderThreads, 0, st>>>(ws.ext, 0, 30, R, B, ws));
+    }
 #define RLOD_LAUNCH_FWD(POOL)                                                                  \
   do {                                                                                         \
     static bool attr_set = false;                                                              \

@@ -172,4 +172,110 @@ static __global__ void __launch_bounds__(kOrderThreads)
   }
 }
 
+
+// k_roi_lists_finish: group fix-up and 2-way partition in ONE launch, one CTA per image (the forward
+// RoIAlign runs this between the plan and the walk kernel; two launches -- a one-warp fix-up that
+// normally does nothing and a per-image sort -- cost ~11 us per call in the stream).
+//   * rois grouped by image (flag clear): the image's list is the range the plan kernel marked;
+//   * otherwise: the CTA collects its image's rois by scanning all of them (every CTA scans; the case
+//     is rare and the scan is R loads), and publishes its own img_off entry;
+//   * the list is then stably partitioned by one bit of the record (the walk mode), by ballots.
+// An image with more than kOrderMaxRois rois gets its list collected but not partitioned (any order is
+// correct for the walk kernel; the partition only keeps its staging stores bank-disjoint).
+static __global__ void __launch_bounds__(kOrderThreads)
+    k_roi_lists_finish(const int *__restrict__ ext, int word, int shift, int R, int B, AlignWs ws) {
+  __shared__ int s_ids[kOrderMaxRois];
+  __shared__ int s_wc[2][kOrderThreads / 32];
+  __shared__ int s_n, s_before;
+  const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const unsigned full = 0xffffffffu, below = (1u << lane) - 1u;
+  constexpr int NW = kOrderThreads / 32;
+  int n, first;
+  const bool grouped = ws.flag[0] == 0;
+  if (grouped) {
+    first = ws.img_off[b];
+    n = ws.img_off[b + 1] - first;
+  } else {
+    // how many rois belong to image b and to the images before it (every CTA scans all R batch indices)
+    int mine = 0, before = 0;
+    for (int r = t; r < R; r += kOrderThreads) {
+      const int rb = ws.roi_b[r];
+      mine += rb == b, before += rb < b;
+    }
+    mine = __reduce_add_sync(full, mine), before = __reduce_add_sync(full, before);
+    if (lane == 0) s_wc[0][warp] = mine, s_wc[1][warp] = before;
+    __syncthreads();
+    n = 0, first = 0;
+    for (int w2 = 0; w2 < NW; ++w2) n += s_wc[0][w2], first += s_wc[1][w2];
+    __syncthreads();
+    if (t == 0) {
+      ws.img_off[b] = first;
+      if (b == B - 1) ws.img_off[B] = first + n;
+    }
+  }
+  const bool fits = n <= kOrderMaxRois;  // else: the list is only collected, not partitioned
+  if (grouped) {
+    for (int i = t; i < n; i += kOrderThreads) {
+      const int id = ws.order[first + i];
+      if (fits) s_ids[i] = id;
+      else ws.order2[first + i] = id;
+    }
+  } else {
+    // ordered collection of the rois of image b
+    if (t == 0) s_n = 0;
+    __syncthreads();
+    for (int c0 = 0; c0 < R; c0 += kOrderThreads) {
+      const int r = c0 + t;
+      const int rb = r < R ? ws.roi_b[r] : -1;
+      const unsigned mine = __ballot_sync(full, rb == b);
+      if (lane == 0) s_wc[0][warp] = __popc(mine);
+      __syncthreads();
+      int pre = s_n, tot = 0;
+      for (int w2 = 0; w2 < NW; ++w2) {
+        if (w2 < warp) pre += s_wc[0][w2];
+        tot += s_wc[0][w2];
+      }
+      const int pos = pre + __popc(mine & below);
+      if (rb == b) {
+        if (fits) s_ids[pos] = r;
+        else ws.order2[first + pos] = r;
+      }
+      __syncthreads();
+      if (t == 0) s_n += tot;
+      __syncthreads();
+    }
+  }
+  if (!fits) return;
+  __syncthreads();
+  // stable 2-way partition by the key bit: zeros first
+  int run0 = 0, run1 = 0, n0 = 0;
+  for (int c0 = 0; c0 < n; c0 += kOrderThreads) {  // count the zeros
+    const int i = c0 + t;
+    const bool z = i < n && ((ext[(size_t)s_ids[i] * 32 + word] >> shift) & 1) == 0;
+    n0 += __popc(__ballot_sync(full, z));
+  }
+  if (lane == 0) s_wc[0][warp] = n0;
+  __syncthreads();
+  n0 = 0;
+  for (int w2 = 0; w2 < NW; ++w2) n0 += s_wc[0][w2];
+  __syncthreads();
+  for (int c0 = 0; c0 < n; c0 += kOrderThreads) {
+    const int i = c0 + t;
+    const int id = i < n ? s_ids[i] : 0;
+    const int key = i < n ? ((ext[(size_t)id * 32 + word] >> shift) & 1) : -1;
+    const unsigned m0 = __ballot_sync(full, key == 0), m1 = __ballot_sync(full, key == 1);
+    if (lane == 0) s_wc[0][warp] = __popc(m0), s_wc[1][warp] = __popc(m1);
+    __syncthreads();
+    int p0 = run0, p1 = run1, t0 = 0, t1 = 0;
+    for (int w2 = 0; w2 < NW; ++w2) {
+      if (w2 < warp) p0 += s_wc[0][w2], p1 += s_wc[1][w2];
+      t0 += s_wc[0][w2], t1 += s_wc[1][w2];
+    }
+    if (key == 0) ws.order2[first + p0 + __popc(m0 & below)] = id;
+    if (key == 1) ws.order2[first + n0 + p1 + __popc(m1 & below)] = id;
+    run0 += t0, run1 += t1;
+    __syncthreads();
+  }
+}
+
 }  // namespace rlod
