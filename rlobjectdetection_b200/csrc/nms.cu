@@ -20,6 +20,8 @@
 //     one CTA each with the mask in shared memory: one launch for thousands of segments.
 // No cudaMalloc, no mask D2H (18 MB per call at n=12000 in the reference), no host loop,
 // no default-stream sync.
+#include <cstdlib>
+
 #include "nms_device.cuh"
 
 namespace rlod {
@@ -272,7 +274,31 @@ __global__ void __launch_bounds__(kSmallThreads)
 // smem: float4 kbox[max_keep]; float kSa[max_keep].
 // ----------------------------------------------------------------------------------------
 constexpr int kLazyThreads = 1024;  // 64 candidates x 16 slices of the kept list: the walk is a latency chain
-constexpr int kLazyMaxKeep = 512;  // beyond: one CTA testing 64 candidates against K kept boxes is slower than the all-SM mask
+constexpr int kLazyMaxKeep = 512;  // beyond, the all-SM mask + scan is as fast: measured at C1 (12000 -> 2000 keeps, heavy
+                                   // suppression, ~180 chunks): cluster of 8 480 us, of 4 658 us, mask + scan 431 us
+constexpr int kLazyMaxCluster = 8;
+
+// The walk runs on a thread-block CLUSTER of cs CTAs per segment (cs = 1, 4 or 8, chosen by the launcher from
+// max_keep): every CTA keeps the whole kept list and all 64 candidates of the chunk, but tests the candidates
+// only against ITS share of the kept list (kept box kk belongs to CTA kk % cs); the cs partial 64-bit
+// "suppressed" masks are exchanged through distributed shared memory (one st.shared::cluster per peer, one
+// cluster barrier per chunk, double-buffered by chunk parity), after which every CTA resolves the chunk and
+// appends the survivors itself -- identical lists everywhere, no second exchange.  Measured at C4 (24 images,
+// 300 keeps from ~370 candidates): 1 CTA 43 us, cluster of 2 40 us, of 4 35 us, of 8 62 us (the barrier per chunk
+// costs more than the shorter kept-list share saves).
+__device__ __forceinline__ uint32_t lz_cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t lz_cluster_size() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void lz_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 
 __global__ void __launch_bounds__(kLazyThreads)
     k_nms_lazy(NmsSegs segs, float thresh, int max_keep, NmsOut o) {
@@ -284,8 +310,10 @@ __global__ void __launch_bounds__(kLazyThreads)
   __shared__ unsigned supw[kLazyThreads / 32];
   __shared__ unsigned diag32[64][2];
   __shared__ unsigned long long s_kept;
+  __shared__ unsigned long long s_part[2][kLazyMaxCluster];  // partial suppressed masks of the peers, by chunk parity
   __shared__ int s_base, s_total;
-  const int seg = blockIdx.x;
+  const uint32_t cs = lz_cluster_size(), cr = lz_cluster_ctarank();
+  const int seg = blockIdx.x / cs;
   int off, n;
   segs.get(seg, off, n);
   const int nblk = (n + 63) >> 6;
@@ -297,6 +325,7 @@ __global__ void __launch_bounds__(kLazyThreads)
   float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
   if (t < 64 && t < n) nxt = segs.load_box(off + t);
   __syncthreads();
+  if (cs > 1) lz_cluster_sync();  // every CTA of the cluster runs before anyone writes into a peer
   for (int k = 0; k < nblk; ++k) {
     const int valid = min(64, n - k * 64);
     if (t < 64) {
@@ -307,18 +336,18 @@ __global__ void __launch_bounds__(kLazyThreads)
     }
     __syncthreads();
     const int K = s_total;
-    // (a) candidate c against the kept list, slice-strided; kept-box reads are broadcasts
+    // (a) candidate c against this CTA's share of the kept list, slice-strided; kept-box reads are broadcasts
     {
       const float4 cb = cbox[c];
       const float2 cw = cwh[c];
       bool sup = false;
       if (c < valid) {
-        // two independent tests per trip: the test is a ~100-cycle dependent chain and a slice runs up
-        // to K / 16 of them back to back
-        int kk = slice;
-        for (; kk + kSlices < K && !sup; kk += 2 * kSlices) {
+        // two independent tests per trip: the test is a ~100-cycle dependent chain
+        const int step = kSlices * (int)cs;
+        int kk = (int)cr + slice * (int)cs;
+        for (; kk + step < K && !sup; kk += 2 * step) {
           const bool s0 = iou_gt(kbox[kk], kSa[kk], cb, cw, thresh, zf);
-          const bool s1 = iou_gt(kbox[kk + kSlices], kSa[kk + kSlices], cb, cw, thresh, zf);
+          const bool s1 = iou_gt(kbox[kk + step], kSa[kk + step], cb, cw, thresh, zf);
           sup = s0 | s1;
         }
         if (!sup && kk < K) sup = iou_gt(kbox[kk], kSa[kk], cb, cw, thresh, zf);
@@ -326,7 +355,7 @@ __global__ void __launch_bounds__(kLazyThreads)
       const unsigned bal = __ballot_sync(0xffffffffu, sup);
       if (lane == 0) supw[warp] = bal;
     }
-    // (b) diagonal tile: row i vs the later boxes j of the same chunk
+    // (b) diagonal tile: row i vs the later boxes j of the same chunk (every CTA, it is 4 tests per thread)
 #pragma unroll
     for (int q = 0; q < 4096 / kLazyThreads; ++q) {
       const int p = t + q * kLazyThreads;
@@ -340,16 +369,36 @@ __global__ void __launch_bounds__(kLazyThreads)
       if (lane == 0) diag32[i][j >> 5] = bal;
     }
     __syncthreads();
+    if (cs > 1) {
+      // my partial mask goes to every CTA of the cluster (lane q of warp 0 writes peer q), then one barrier
+      if (warp == 0) {
+        static_assert(kLazyThreads / 32 == 32, "one supw word per lane");
+        const unsigned v = supw[lane];
+        const unsigned lo = __reduce_or_sync(0xffffffffu, (lane & 1) ? 0u : v);
+        const unsigned hi = __reduce_or_sync(0xffffffffu, (lane & 1) ? v : 0u);
+        if (lane < (int)cs) {
+          const uint32_t local = smem_u32(&s_part[k & 1][cr]);
+          uint32_t remote;
+          asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"((uint32_t)lane));
+          asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(remote), "l"(((unsigned long long)hi << 32) | lo) : "memory");
+        }
+      }
+      lz_cluster_sync();
+    }
     if (warp == 0) {
       // Greedy resolve of the chunk by ONE WARP: every lane keeps the removed mask r; lane l owns the
       // diagonal rows l and l + 32 and hands row i out by shuffle.  The 128 shuffles do not depend on r, so
-      // they pipeline; the dependent chain per row is test / select / OR (a single thread walking the rows
-      // with the row loads behind the test cost ~1.5 us per chunk: a third of the kernel).
-      static_assert(kLazyThreads / 32 == 32, "one supw word per lane");
-      const unsigned v = supw[lane];
-      const unsigned lo = __reduce_or_sync(0xffffffffu, (lane & 1) ? 0u : v);
-      const unsigned hi = __reduce_or_sync(0xffffffffu, (lane & 1) ? v : 0u);
-      unsigned long long r = ((unsigned long long)hi << 32) | lo;
+      // they pipeline; the dependent chain per row is test / select / OR.
+      unsigned long long r;
+      if (cs > 1) {
+        r = 0ull;
+        for (uint32_t q = 0; q < cs; ++q) r |= s_part[k & 1][q];
+      } else {
+        const unsigned v = supw[lane];
+        const unsigned lo = __reduce_or_sync(0xffffffffu, (lane & 1) ? 0u : v);
+        const unsigned hi = __reduce_or_sync(0xffffffffu, (lane & 1) ? v : 0u);
+        r = ((unsigned long long)hi << 32) | lo;
+      }
       if (valid < 64) r |= ~0ull << valid;
       const unsigned long long rowA = ((unsigned long long)diag32[lane][1] << 32) | diag32[lane][0];
       const unsigned long long rowB = ((unsigned long long)diag32[lane + 32][1] << 32) | diag32[lane + 32][0];
@@ -396,13 +445,14 @@ __global__ void __launch_bounds__(kLazyThreads)
       const float2 w = cwh[t];
       kbox[rank] = b;
       kSa[rank] = __fmul_rn(w.x, w.y);
-      o.emit(seg, off, rank, k * 64 + t, segs);
+      if (cr == 0) o.emit(seg, off, rank, k * 64 + t, segs);
     }
-    if (total >= max_keep) break;  // CTA-uniform
+    if (total >= max_keep) break;  // uniform over the CTA and over the cluster (same data everywhere)
     __syncthreads();
   }
   __syncthreads();
-  o.finish(seg, off, n, s_total, t, kLazyThreads);
+  if (cr == 0) o.finish(seg, off, n, s_total, t, kLazyThreads);
+  if (cs > 1) lz_cluster_sync();  // nobody leaves while a peer may still write its partial mask here
 }
 
 static size_t small_smem(int max_pad) {
@@ -428,13 +478,30 @@ int nms_launch(const NmsSegs &segs, int nseg, int max_seg, float thresh, int max
     return launch_status();
   }
   if (max_keep > 0 && max_keep <= kLazyMaxKeep && !force_large) {
-    // bounded keeps (proposal layer): kept-list walk, no n x n mask, no workspace
+    // bounded keeps (proposal layer): kept-list walk, no n x n mask, no workspace.  Cluster size by the length of
+    // the kept list a chunk is tested against: 1 CTA up to 128 keeps, else 4
     const size_t smem = (size_t)max_keep * (sizeof(float4) + sizeof(float));
-    if (smem > 48 * 1024)
-      cudaFuncSetAttribute(k_nms_lazy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    RLOD_LAUNCH(RLOD_KERNEL_NMS_LAZY, st,
-                k_nms_lazy<<<nseg, kLazyThreads, smem, st>>>(segs, thresh, max_keep, out));
-    return launch_status();
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(k_nms_lazy, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+      attr_set = true;
+    }
+    static const int cs_env = getenv("RLOD_NMS_CLUSTER") ? atoi(getenv("RLOD_NMS_CLUSTER")) : 0;  // A/B switch
+    int cs = max_keep <= 128 ? 1 : 4;
+    if (cs_env == 1 || cs_env == 2 || cs_env == 4 || cs_env == 8) cs = cs_env;
+    ProfScope _ps(RLOD_KERNEL_NMS_LAZY, st);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(nseg * cs), 1, 1);
+    cfg.blockDim = dim3(kLazyThreads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)cs, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, k_nms_lazy, segs, thresh, max_keep, out);
+    return e != cudaSuccess ? (int)e : launch_status();
   }
   if (max_seg <= kSmallMaxN && !force_large) {
     const int max_pad = (max_seg + 63) / 64 * 64;

@@ -694,6 +694,6 @@ RLOD_API int rlod_proposal_forward(const float *scores, const float *deltas, con
   o.num_out = nkeep_out;
   o.rois = rois_out;
   o.post = post_nms_topN;
-  // post_nms_topN <= 512: kept-list walk (k_nms_lazy); larger: tiled mask + device scan
+  // post_nms_topN <= 512: kept-list walk on a cluster of 4 CTAs per image (k_nms_lazy); larger: tiled mask + device scan
   return nms_launch(segs, B, pre, nms_thresh, post_nms_topN, o, ws.mask, ws.mask_bytes, st, 0);
 }
