@@ -170,3 +170,48 @@ def test_two_rank_gather_equals_single_rank(tmp_path, gb):
     port = 29500 + (os.getpid() + gb) % 2000
     mp.spawn(_gloo_worker, args=(2, port, gb, str(tmp_path)), nprocs=2, join=True)
     assert [open(tmp_path / f"ok{r}").read() for r in range(2)] == ["1", "1"]
+
+
+def test_wtrans_code_recognises_the_reference_forms():
+    # Action.wtrans (action.py:7-10) -> kernel selector: Action's default, the drop-in's exp_abs, the reference's own
+    # Config.act_wtrans passed as a plain callable (config.py:48-51, recognised by probing), anything else = custom
+    from math import exp, fabs
+    from rlobjectdetection_b200.model import _backend as be
+    from rlobjectdetection_b200.model.Reinforcement.action import Action, exp_abs, wtrans_code
+    assert wtrans_code(Action([0.5])) == be.WTRANS_IDENTITY
+    assert wtrans_code(Action([0.5], wtrans=exp_abs)) == be.WTRANS_EXP_ABS
+    assert wtrans_code(Action([0.5], wtrans=lambda x: exp(fabs(x)))) == be.WTRANS_EXP_ABS
+    assert wtrans_code(Action([0.5], wtrans=lambda x: x)) == be.WTRANS_IDENTITY
+    assert wtrans_code(Action([0.5], wtrans=lambda x: x * x)) == be.WTRANS_RAW
+    assert wtrans_code(Action([0.5], wtrans=lambda x: x.clamp(min=0))) == be.WTRANS_RAW  # tensor-only callable
+
+
+def test_feature_layouts_without_a_gpu():
+    # dense NCHW and channels-last maps are taken in place, everything else is refused (never silently copied)
+    from rlobjectdetection_b200.model import _backend as be
+    x = torch.randn(2, 8, 6, 5)
+    assert be.feature_layout(x, "t") == (x, 0) or be.feature_layout(x, "t")[1] == 0
+    cl = x.contiguous(memory_format=torch.channels_last)
+    t, flag = be.feature_layout(cl, "t")
+    assert flag == 1 and t.data_ptr() == cl.data_ptr()
+    with pytest.raises(ValueError):
+        be.feature_layout(x[:, ::2], "t")
+    with pytest.raises(TypeError):
+        be.feature_layout(x.double(), "t")
+
+
+def test_reference_arm_runs_the_reference_python(orc):
+    # bench.py --impl reference: the vendored reference modules (baseline/_ref, present after build()) imported
+    # unmodified under the two stubs; its rois equal the oracle port's up to the expf ulp
+    from baseline import ref_arm
+    if not ref_arm.available():
+        pytest.skip("baseline/_ref not vendored (no /root/reference at build time)")
+    import bench
+    inp = [t[:1].contiguous() for t in bench.make_inputs(3, 1)]
+    rois, reward, refined, pooled, pooled2 = ref_arm.step(orc, inp, bench.STRIDE, bench.SCALES, bench.RATIOS, 600, 50, 0.7,
+                                                          bench.POOL, bench.ACT_DELTA)
+    anchors = orc.generate_anchors(16, bench.RATIOS, bench.SCALES).astype(np.float32)
+    ref = orc.proposal_layer(inp[0].numpy(), inp[1].numpy(), inp[2].numpy(), anchors, 16, 600, 50, 0.7)
+    np.testing.assert_allclose(rois, ref, rtol=3e-6, atol=2e-4)
+    assert reward.shape == (1, 50, 16) and pooled.shape == (50, 1024, 7, 7) and refined.shape == rois.shape
+    assert "baseline/_ref" in sys.modules["model.rpn.proposal_layer"].__file__.replace(os.sep, "/")
