@@ -1515,6 +1515,11 @@ RLOD_API int rlod_roi_align_backward(const float *grad_out, const float *rois, c
   const int GW = pool_mode == RLOD_POOL_NONE ? aw : aw + 1;
   AlignWs ws = carve_align_ws(workspace, B, R, GH, GW);
   if (workspace_bytes < ws.bytes) return RLOD_ENOSPC;
+  // lock-free kernel (roi_align_bwd.cu); the lock kernel below stays behind RLOD_BWD_V1=1 for A/B runs
+  static const bool bwd_v1 = getenv("RLOD_BWD_V1") != nullptr;
+  if (!bwd_v1 && GH == 8 && GW == 8 && (C % 4) == 0 && pool_mode != RLOD_POOL_MAX &&
+      ((uintptr_t)grad_out % 16) == 0 && bwd_own_supported(H, W, pool_mode))
+    return launch_bwd_own(grad_out, rois, B, C, H, W, R, spatial_scale, pool_mode, accumulate, grad_in, ws, st);
   const int P = walk_pitch(W);
   const size_t smem = fwd_walk_smem(H, W, pool_mode) + (size_t)((H + 2 + 3) & ~3) * sizeof(int) +
                       (size_t)kWalkWarps * 2 * sizeof(uint64_t) + 16;

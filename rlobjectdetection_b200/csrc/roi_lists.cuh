@@ -18,6 +18,7 @@ struct AlignWs {
   int *plan;     // [R * words]
   int *ext;      // [R * 32] forward-kernel record (8x8 grids only)
   int *order2;   // [R]   `order` with every image's list partitioned by walk mode (stable)
+  int *own;      // [R * 192] record of the lock-free backward kernel (roi_align_bwd.cu, 8x8 grids only)
   size_t bytes;
 };
 
@@ -38,6 +39,7 @@ static inline AlignWs carve_align_ws(void *base, int B, int R, int GH, int GW) {
   w.plan = (int *)take((size_t)(R > 0 ? R : 1) * (size_t)(2 * GH + 2 * GW) * sizeof(int));
   w.ext = (int *)take((GH == 8 && GW == 8) ? (size_t)(R > 0 ? R : 1) * 32 * sizeof(int) : 0);
   w.order2 = (int *)take((GH == 8 && GW == 8) ? (size_t)(R > 0 ? R : 1) * sizeof(int) : 0);
+  w.own = (int *)take((GH == 8 && GW == 8) ? (size_t)(R > 0 ? R : 1) * 192 * sizeof(int) : 0);
   w.bytes = off;
   return w;
 }
@@ -277,5 +279,11 @@ static __global__ void __launch_bounds__(kOrderThreads)
     __syncthreads();
   }
 }
+
+// roi_align_bwd.cu: the lock-free backward (one warp owns the planes of an image x 4 channels)
+bool bwd_own_supported(int H, int W, int pool_mode);
+int launch_bwd_own(const float *grad_out, const float *rois, int B, int C, int H, int W, int R,
+                   float spatial_scale, int pool_mode, int accumulate, float *grad_in, const AlignWs &ws,
+                   cudaStream_t st);
 
 }  // namespace rlod

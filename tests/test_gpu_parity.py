@@ -246,11 +246,46 @@ def test_roi_align_backward_c2_full_size(orc):
     gin = be.roi_align_backward(cu(gout), cu(rois), None, tuple(feat.shape), 7, 7, 1 / 16.0,
                                 be.POOL_AVG)
     close(gin.cpu().numpy(), ref, what="C2 bwd")
-    # run-to-run: rois of different warps add into a pixel in lock order (like the reference's
-    # atomics), so repeats agree to rounding, not bit for bit
+    # run to run: the flush token ring of k_align8_bwd_own fixes the order in which rois add into a pixel
+    # (the reference's atomicAdd order is not fixed), so repeats are bit-identical
     gin2 = be.roi_align_backward(cu(gout), cu(rois), None, tuple(feat.shape), 7, 7, 1 / 16.0,
                                  be.POOL_AVG)
-    close(gin2.cpu().numpy(), gin.cpu().numpy(), what="C2 bwd repeat")
+    assert torch.equal(gin2, gin), "RoIAlign backward is not bit-reproducible run to run"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [be.POOL_NONE, be.POOL_AVG])
+def test_roi_align_backward_tiny_and_clamped_rois(orc, mode):
+    """Rois whose 8 sample rows / columns fall into one or two pixels (every tap merged: up to 7 pooled
+    columns per pixel column), rois hanging over every border (clamped indices, ratios > 1, invalid
+    samples at either end), many rois on the same pixels (the token ring orders them), an image with a
+    single roi and an image with none."""
+    B, C, H, W = 4, 8, 20, 27
+    ah = 8 if mode == be.POOL_NONE else 7
+    g = torch.Generator().manual_seed(77)
+    rows = []
+    for k in range(40):  # sub-pixel to 3-pixel rois around the same spot of image 0
+        x1 = 100.0 + float(torch.rand(1, generator=g)) * 8
+        y1 = 80.0 + float(torch.rand(1, generator=g)) * 8
+        w = float(torch.rand(1, generator=g)) * 48
+        h = float(torch.rand(1, generator=g)) * 48
+        rows.append([0, x1, y1, x1 + w, y1 + h])
+    for k in range(24):  # over the borders of image 1
+        cx = float(torch.rand(1, generator=g)) * W * 16
+        cy = float(torch.rand(1, generator=g)) * H * 16
+        side = k % 4
+        if side == 0: rows.append([1, -60.0 - k, cy - 30, 50.0 + k, cy + 30])
+        if side == 1: rows.append([1, cx - 40, -35.0 - k, cx + 40, 20.0 + k])
+        if side == 2: rows.append([1, W * 16 - 50.0 - k, cy - 20, W * 16 + 80.0, cy + 25])
+        if side == 3: rows.append([1, cx - 25, H * 16 - 30.0 - k, cx + 25, H * 16 + 90.0])
+    rows.append([3, 17.0, 23.0, 17.0, 23.0])  # image 3: one roi of one pixel; image 2: none
+    rois = torch.tensor(rows, dtype=torch.float32)
+    feat = torch.randn(B, C, H, W, generator=g)
+    gout = torch.randn(rois.size(0), C, ah, ah, generator=g)
+    ref = orc.roi_align_bwd(gout.numpy(), feat.numpy(), rois.numpy(), ah, ah, 1 / 16.0, pool_mode=mode)
+    gin = be.roi_align_backward(cu(gout), cu(rois), cu(feat), tuple(feat.shape), ah, ah, 1 / 16.0, mode)
+    close(gin.cpu().numpy(), ref, what=f"roi_align bwd tiny / clamped rois, mode {mode}")
+    assert not gin[2].any(), "an image without rois must get a zero gradient"
 
 
 def test_roi_align_module_autograd(orc):
