@@ -67,6 +67,105 @@ __global__ void __launch_bounds__(64)
   mask[(size_t)seg * mask_seg_stride + (size_t)cb * npad + i] = bits;
 }
 
+// One row box against the 64 boxes of a column block -> 64 mask bits, branch-free: every pair runs the same
+// ~28 straight-line instructions of iou_gt's interval test (the divergent early exits of iou_gt leave the
+// schedulers at ~1 instruction per cycle on overlapping boxes such as RPN proposals) and is classified as
+// yes / no / undecided; only the undecided ones -- razor-edge ties and non-finite values -- take the exact
+// division afterwards.  Same decisions as iou_gt, pair by pair (thresh >= 0 only; else the plain loop).
+__device__ __forceinline__ void classify_pair(const float4 &a, float Sa, const float4 &b, const float2 &bwh,
+                                              float thresh, bool &yes, bool &und) {
+  const float w = fmaxf(__fadd_rn(__fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)), 1.f), 0.f);
+  const float h = fmaxf(__fadd_rn(__fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)), 1.f), 0.f);
+  const float inter = __fmul_rn(w, h);
+  const float u = __fsub_rn(__fmaf_rn(bwh.x, bwh.y, Sa), inter);
+  const float tq = __fmul_rn(thresh, u);
+  const bool empty = (w == 0.f) || (inter == 0.f);
+  const bool ranged = (tq > 1e-30f) && (tq < 1e30f) && (inter < 1e30f);
+  yes = !empty && ranged && (inter > __fmul_rn(tq, 1.000002f));
+  const bool no = empty || (ranged && (inter < __fmul_rn(tq, 0.999998f)));
+  und = !yes && !no;
+}
+
+__device__ __forceinline__ unsigned long long row_tile_bits(const float4 &a, float Sa, const float4 *cbox,
+                                                            const float2 *cwh, int j0, int jn, float thresh,
+                                                            bool fast) {
+  unsigned long long valid = ~0ull;
+  if (j0 > 0) valid &= j0 < 64 ? ~0ull << j0 : 0ull;
+  if (jn < 64) valid &= jn > 0 ? ~0ull >> (64 - jn) : 0ull;
+  unsigned ylo = 0u, yhi = 0u, ulo = 0xffffffffu, uhi = 0xffffffffu;
+  if (fast) {
+    ulo = uhi = 0u;
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j) {
+      bool y, q;
+      classify_pair(a, Sa, cbox[j], cwh[j], thresh, y, q);
+      ylo |= y ? 1u << j : 0u, ulo |= q ? 1u << j : 0u;
+    }
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j) {
+      bool y, q;
+      classify_pair(a, Sa, cbox[32 + j], cwh[32 + j], thresh, y, q);
+      yhi |= y ? 1u << j : 0u, uhi |= q ? 1u << j : 0u;
+    }
+  }
+  unsigned long long bits = (((unsigned long long)yhi << 32) | ylo) & valid;
+  unsigned long long und = (((unsigned long long)uhi << 32) | ulo) & valid;
+  while (und) {
+    const int j = __ffsll((long long)und) - 1;
+    und &= und - 1ull;
+    if (iou_gt(a, Sa, cbox[j], cwh[j], thresh, fast)) bits |= 1ull << j;
+  }
+  return bits;
+}
+
+// ----------------------------------------------------------------------------------------
+// tile kernel, row-major mask (for k_nms_scan3): mask[row][column block], row stride = nblk rounded up to 4
+// words.  A CTA takes one row block and FOUR column blocks, thread t owns row rb*64+t and writes its four
+// words as one full 32-byte sector.  The scan's far gather -- one kept row against all later column blocks --
+// then reads contiguous words (lanes = column blocks) instead of one 32-byte sector per 8-byte word: at
+// n = 12000 that gather, not the serial chain, bounded the scan (188 k sectors through one SM).
+// Words of column blocks left of the diagonal are written as zero and never read.
+// ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64)
+    k_nms_mask_rm(NmsSegs segs, float thresh, unsigned long long *__restrict__ mask, size_t mask_seg_stride) {
+  const int seg = blockIdx.z;
+  int off, n;
+  segs.get(seg, off, n);
+  const int nblk = (n + 63) >> 6;
+  const int rb = blockIdx.y, g = blockIdx.x;
+  if (rb >= nblk || g * 4 + 3 < rb || g * 4 >= nblk) return;
+  const int stride = (nblk + 3) & ~3;
+  __shared__ float4 cbox[256];
+  __shared__ float2 cwh[256];
+  const int t = threadIdx.x;
+  for (int q = t; q < 256; q += 64) {
+    const int j = g * 256 + q;
+    float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j < n) bx = segs.load_box(off + j);
+    cbox[q] = bx;
+    cwh[q] = make_float2(__fadd_rn(__fsub_rn(bx.z, bx.x), 1.f), __fadd_rn(__fsub_rn(bx.w, bx.y), 1.f));
+  }
+  __syncthreads();
+  const int i = rb * 64 + t;
+  unsigned long long bits[4] = {0ull, 0ull, 0ull, 0ull};
+  if (i < n) {
+    const float4 a = segs.load_box(off + i);
+    const float Sa = __fmul_rn(__fadd_rn(__fsub_rn(a.z, a.x), 1.f), __fadd_rn(__fsub_rn(a.w, a.y), 1.f));
+    const bool fast = thresh >= 0.f && thresh < 1e30f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int cb = g * 4 + c;
+      if (cb < rb || cb >= nblk) continue;
+      const int jn = min(64, n - cb * 64);
+      const int j0 = (rb == cb) ? t + 1 : 0;
+      bits[c] = row_tile_bits(a, Sa, cbox + c * 64, cwh + c * 64, j0, jn, thresh, fast);
+    }
+  }
+  ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(mask + (size_t)seg * mask_seg_stride + (size_t)i * stride + g * 4);
+  dst[0] = make_ulonglong2(bits[0], bits[1]);
+  dst[1] = make_ulonglong2(bits[2], bits[3]);
+}
+
 // ----------------------------------------------------------------------------------------
 // scan kernel: one CTA (1024 threads) per segment.
 // ----------------------------------------------------------------------------------------
@@ -165,6 +264,436 @@ __global__ void __launch_bounds__(kScanThreads)
   }
   __syncthreads();
   o.finish(seg, off, n, s_total, t, kScanThreads);
+}
+
+// ----------------------------------------------------------------------------------------
+// scan kernel, software-pipelined (round 2): the same greedy scan, for nblk <= 256 column blocks
+// (n <= 16384).  k_nms_scan pays one L2 round trip per block on its critical path (the kept rows of
+// block k are fetched after block k is resolved and OR-ed into remv[] before block k + 1 may start):
+// 308 us at n = 12000.  Here nothing on the path waits for memory:
+//   * the kept rows of block k are fetched for all far column blocks when k is resolved, but reduced and
+//     OR-ed into remv[] one step LATER (column block c belongs to warp c % 32, which keeps the pending
+//     words of its <= 6 columns in registers);
+//   * the three column blocks after k ("near": their loads could not land in time) are fetched
+//     speculatively, all 64 rows, two steps ahead, and masked by the keep bits once they are known;
+//   * the diagonal tile travels two steps ahead as well; two CTA barriers per step instead of three.
+// ----------------------------------------------------------------------------------------
+// Greedy resolve of one 64 x 64 diagonal tile by ONE thread: box i of the block is kept unless a kept
+// earlier box (or an earlier block: r) removed it; a kept box removes the boxes of its row.  Written on
+// 32-bit halves with selects instead of branches: the chain is test -> OR, ~10 cycles per box (the
+// branchy 64-bit form, one taken or not-taken branch per box, costs 2.5 us per tile of the scan's step).
+__device__ __forceinline__ void resolve_step(unsigned &rtest, unsigned &rother, unsigned &k, unsigned bit,
+                                             unsigned dtest, unsigned dother, bool both) {
+  // one test that sets a predicate, then predicated ORs: the dependent chain through r is two instructions
+  // per box (the select form ptxas derives from C++ is three)
+  if (both) {
+    asm("{\n"
+        ".reg .pred p;\n"
+        ".reg .b32 t;\n"
+        "and.b32 t, %0, %3;\n"
+        "setp.eq.u32 p, t, 0;\n"
+        "@p or.b32 %0, %0, %4;\n"
+        "@p or.b32 %1, %1, %5;\n"
+        "@p or.b32 %2, %2, %3;\n"
+        "}\n"
+        : "+r"(rtest), "+r"(rother), "+r"(k)
+        : "r"(bit), "r"(dtest), "r"(dother));
+  } else {
+    asm("{\n"
+        ".reg .pred p;\n"
+        ".reg .b32 t;\n"
+        "and.b32 t, %0, %2;\n"
+        "setp.eq.u32 p, t, 0;\n"
+        "@p or.b32 %0, %0, %3;\n"
+        "@p or.b32 %1, %1, %2;\n"
+        "}\n"
+        : "+r"(rtest), "+r"(k)
+        : "r"(bit), "r"(dtest));
+  }
+}
+
+__device__ __forceinline__ unsigned long long resolve_tile(unsigned long long r, const unsigned long long *dg) {
+  unsigned rlo = (unsigned)r, rhi = (unsigned)(r >> 32), klo = 0u, khi = 0u;
+  const uint2 *d2 = reinterpret_cast<const uint2 *>(dg);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const uint2 d = d2[i];
+    resolve_step(rlo, rhi, klo, 1u << i, d.x, d.y, true);
+  }
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const unsigned dh = d2[32 + i].y;  // row 32+i only removes boxes > 32+i: the upper half
+    unsigned dummy = 0u;
+    resolve_step(rhi, dummy, khi, 1u << i, dh, 0u, false);
+  }
+  return ((unsigned long long)khi << 32) | klo;
+}
+
+constexpr int kScan2MaxBlk = 192;  // 6 column slots per warp: the pending loads stay in registers
+constexpr int kScan2Near = 3;
+
+__global__ void __launch_bounds__(kScanThreads, 1)
+    k_nms_scan2(NmsSegs segs, int max_keep, const unsigned long long *__restrict__ mask,
+                size_t mask_seg_stride, NmsOut o) {
+  extern __shared__ unsigned long long remv[];  // [nblk]
+  __shared__ unsigned long long diag[2][64];
+  __shared__ unsigned long long s_kept;
+  __shared__ int s_base, s_total;
+  typedef unsigned long long u64;
+  constexpr int ND = kScan2Near;
+  constexpr int NU = kScan2MaxBlk / 32;  // column slots per warp
+  const int seg = blockIdx.x;
+  int off, n;
+  segs.get(seg, off, n);
+  const int nblk = (n + 63) >> 6, npad = nblk << 6;
+  const u64 *m = mask + (size_t)seg * mask_seg_stride;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const unsigned full = 0xffffffffu;
+  for (int w = t; w < nblk; w += kScanThreads) remv[w] = 0ull;
+  if (t == 0) s_total = 0;
+  // word of row `r` of row block rb in column block cb (0 when outside)
+  auto tile_word = [&](int rb, int cb, int r) -> u64 {
+    return (cb < nblk && rb < nblk) ? m[(size_t)cb * npad + rb * 64 + r] : 0ull;
+  };
+  // diagonal tiles, two steps ahead (threads 0..63)
+  u64 d_a = 0ull, d_b = 0ull;
+  if (t < 64) {
+    diag[0][t] = tile_word(0, 0, t);
+    d_a = tile_word(1, 1, t), d_b = tile_word(2, 2, t);
+  }
+  // near tiles (warps 0..ND-1: warp d-1 holds tile (k, k+d), rows lane and lane+32), two steps ahead
+  u64 nc0 = 0ull, nc1 = 0ull, na0 = 0ull, na1 = 0ull, nb0 = 0ull, nb1 = 0ull;
+  if (warp < ND) {
+    const int d = warp + 1;
+    nc0 = tile_word(0, d, lane), nc1 = tile_word(0, d, lane + 32);
+    na0 = tile_word(1, 1 + d, lane), na1 = tile_word(1, 1 + d, lane + 32);
+    nb0 = tile_word(2, 2 + d, lane), nb1 = tile_word(2, 2 + d, lane + 32);
+  }
+  // far columns of this warp (column w = warp + 32 u): the words loaded for the last resolved row block
+  u64 pend0[NU], pend1[NU];
+#pragma unroll
+  for (int u = 0; u < NU; ++u) pend0[u] = pend1[u] = 0ull;
+  __syncthreads();
+
+  for (int k = 0; k < nblk; ++k) {
+    if (t == 0) {
+      u64 r = remv[k];
+      const int valid = min(64, n - k * 64);
+      if (valid < 64) r |= ~0ull << valid;
+      const u64 kb0 = resolve_tile(r, diag[k & 1]);
+      u64 kb = kb0;
+      int total = s_total;
+      int cnt = __popcll(kb);
+      if (max_keep > 0 && total + cnt > max_keep) {
+        int need = max_keep - total;
+        u64 trimmed = 0ull, rest = kb;
+        while (need-- > 0) {
+          const u64 low = rest & (~rest + 1ull);
+          trimmed |= low;
+          rest ^= low;
+        }
+        kb = trimmed;
+        cnt = __popcll(kb);
+      }
+      s_kept = kb;
+      s_base = total;
+      s_total = total + cnt;
+    }
+    __syncthreads();
+    const u64 kb = s_kept;
+    const int base = s_base, total = s_total;
+    if (t < 64 && ((kb >> t) & 1ull)) {
+      const int rank = base + __popcll(kb & ((1ull << t) - 1ull));
+      o.emit(seg, off, rank, k * 64 + t, segs);
+    }
+    if (max_keep > 0 && total >= max_keep) break;  // CTA-uniform
+    const bool k0 = (kb >> lane) & 1ull, k1 = (kb >> (lane + 32)) & 1ull;
+    // next diagonal tile -> shared memory; the one after the next two starts travelling
+    if (t < 64) {
+      diag[(k + 1) & 1][t] = d_a;
+      d_a = d_b;
+      d_b = tile_word(k + 3, k + 3, t);
+    }
+    // near columns k+1 .. k+ND: mask the speculative rows by the keep bits
+    if (warp < ND) {
+      const int d = warp + 1;
+      const u64 v = (k0 ? nc0 : 0ull) | (k1 ? nc1 : 0ull);
+      const unsigned lo = __reduce_or_sync(full, (unsigned)v), hi = __reduce_or_sync(full, (unsigned)(v >> 32));
+      if (lane == 0 && k + d < nblk) atomicOr(&remv[k + d], ((u64)hi << 32) | lo);
+      nc0 = na0, nc1 = na1, na0 = nb0, na1 = nb1;
+      nb0 = tile_word(k + 3, k + 3 + d, lane), nb1 = tile_word(k + 3, k + 3 + d, lane + 32);
+    }
+    // far columns (>= k+ND+1) of this warp: reduce the words fetched for row block k-1 (they had a whole
+    // step to arrive) into remv[], then fetch the kept rows of row block k.  Column c is complete before it
+    // is resolved: row blocks <= c-ND-1 reach it this way by step c-ND, the last ND ones through the near path
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+      const int w = warp + 32 * u;
+      if (w >= k + ND && w < nblk) {  // fetched at step k-1 (warp-uniform)
+        const u64 v = pend0[u] | pend1[u];
+        const unsigned lo = __reduce_or_sync(full, (unsigned)v), hi = __reduce_or_sync(full, (unsigned)(v >> 32));
+        if (lane == 0 && (lo | hi)) atomicOr(&remv[w], ((u64)hi << 32) | lo);
+      }
+      pend0[u] = pend1[u] = 0ull;
+      if (w >= k + ND + 1 && w < nblk) {
+        const u64 *col = m + (size_t)w * npad + k * 64;
+        if (k0) pend0[u] = col[lane];
+        if (k1) pend1[u] = col[lane + 32];
+      }
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  o.finish(seg, off, n, s_total, t, kScanThreads);
+}
+
+// ----------------------------------------------------------------------------------------
+// scan kernel, decoupled (round 2, third form): the greedy scan as three groups of warps of ONE CTA that
+// never meet at a CTA barrier inside the loop.
+//   * warp 0, the RESOLVER, owns the serial chain: block k's removed word -> resolve_tile -> keep bits
+//     -> publish (kept[k], resolved = k+1) -> emit -> its own share of the next column (d = 1: the tile
+//     (k, k+1) was fetched speculatively, all 64 rows, two steps ahead, and is masked by the keep bits in
+//     registers).  Its step is ~0.5 us and contains no global-memory latency;
+//   * warps 1..ND, the NEAR warps, do the same for the columns k+2 .. k+ND+1 (tile (k, k+1+d) in
+//     registers two steps ahead, masked, reduced, atomicOr into remv[]) and tell the resolver through a
+//     named barrier pair; they trail the resolver by at most a step;
+//   * the remaining warps are the FAR threads: thread w owns column block w and ORs, for every row block
+//     j <= w-ND-2 and every KEPT row i of it, the word m[w][64 j + i] into a private register -- one load
+//     and one OR per (kept row, column), no reduction, no atomics (the per-step reductions of k_nms_scan /
+//     scan2 were 2 350 warp instructions per step on this single SM) -- following `resolved` at their
+//     own pace; when a column is complete it is handed to remv[] and flagged.
+// Valid for nblk <= 32 * (32 - 1 - ND) column blocks; larger inputs take k_nms_scan.
+// ----------------------------------------------------------------------------------------
+constexpr int kScan3Near = 3;
+constexpr int kScan3MaxBlk = 32 * (kScanThreads / 32 - 1 - kScan3Near);
+
+__device__ __forceinline__ int ld_volatile_s32(const int *p) {
+  int v;
+  asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(kScanThreads, 1)
+    k_nms_scan3(NmsSegs segs, int max_keep, const unsigned long long *__restrict__ mask,
+                size_t mask_seg_stride, NmsOut o) {
+  typedef unsigned long long u64;
+  extern __shared__ u64 sm_scan[];  // ring[kRing][2 + ND][64] | remv[nblk] | kept[nblk] | far_done[nblk] (int)
+  __shared__ int s_resolved, s_last, s_total_out;
+  constexpr int kRing = 4;  // tiles travel kRing - 1 steps ahead (8-byte async copies, no registers held)
+  constexpr int ND = kScan3Near;
+  constexpr int kFarWarps = kScanThreads / 32 - 1 - ND;
+  constexpr int kDone = 0x7fffffff;
+  const int seg = blockIdx.x;
+  int off, n;
+  segs.get(seg, off, n);
+  const int nblk = (n + 63) >> 6, stride = (nblk + 3) & ~3;
+  constexpr int kTiles = 2 + kScan3Near;  // per step: diagonal, (k, k+1) [resolver], (k, k+2 ..) [near warps]
+  u64 *ring = sm_scan;
+  u64 *remv = sm_scan + kRing * kTiles * 64, *kept = remv + nblk;
+  int *far_done = reinterpret_cast<int *>(kept + nblk);
+  const u64 *m = mask + (size_t)seg * mask_seg_stride;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const unsigned full = 0xffffffffu;
+  // a column's far row blocks are dealt to NP warps (row block j goes to part j % NP): each part then has NP
+  // resolver steps per row block to fetch its rows
+  const int groups = (nblk + 31) >> 5;
+  const int NP = groups * 4 <= kFarWarps ? 4 : (groups * 2 <= kFarWarps ? 2 : 1);
+  for (int w = t; w < nblk; w += kScanThreads) remv[w] = 0ull, far_done[w] = 0;
+  if (t == 0) s_resolved = 0, s_last = nblk - 1, s_total_out = 0;
+  __syncthreads();
+  // this warp's copy of tile (rb, cb) into ring slot `slot`, tile index ti: rows lane and lane + 32
+  auto fetch_tile = [&](int slot, int ti, int rb, int cb) {
+    u64 *dst = ring + (slot * kTiles + ti) * 64;
+    if (cb < nblk && rb < nblk) {
+      const u64 *src = m + (size_t)(rb * 64 + lane) * stride + cb;  // row-major mask: rows are `stride` words apart
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst + lane)), "l"(src) : "memory");
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst + lane + 32)), "l"(src + (size_t)32 * stride) : "memory");
+    } else {
+      dst[lane] = 0ull, dst[lane + 32] = 0ull;
+    }
+  };
+  auto commit = []() { asm volatile("cp.async.commit_group;" ::: "memory"); };
+  auto wait_oldest = [&]() {  // the group committed kRing - 1 steps ago has landed; make it visible to the warp
+    asm volatile("cp.async.wait_group %0;" ::"n"(kRing - 1) : "memory");
+    __syncwarp();
+  };
+
+  if (warp == 0) {
+    // ---- resolver ------------------------------------------------------------------------
+    for (int p = 0; p < kRing - 1; ++p) {
+      fetch_tile(p, 0, p, p);
+      fetch_tile(p, 1, p, p + 1);
+      commit();
+    }
+    u64 r_near = 0ull;  // what row block k-1 removes in column k
+    int total = 0;
+    for (int k = 0; k < nblk; ++k) {
+      {
+        const int kk = k + kRing - 1, slot = kk % kRing;  // the slot of step k-1: consumed
+        fetch_tile(slot, 0, kk, kk);
+        fetch_tile(slot, 1, kk, kk + 1);
+        commit();
+        wait_oldest();
+      }
+      const u64 *diag = ring + ((k % kRing) * kTiles + 0) * 64;
+      const u64 *near1 = ring + ((k % kRing) * kTiles + 1) * 64;
+      // the near warps' updates of remv[k] (row blocks k-ND-1 .. k-2) are complete with their step k-2
+      if (k >= 2) asm volatile("bar.sync %0, %1;" ::"r"(1 + (k & 1)), "n"(32 * (1 + ND)) : "memory");
+      u64 kb = 0ull;
+      bool done = false;
+      if (lane == 0) {
+        while (ld_volatile_s32(far_done + k) < NP) {
+        }
+        __threadfence_block();
+        u64 r = *reinterpret_cast<volatile u64 *>(remv + k) | r_near;
+        const int valid = min(64, n - k * 64);
+        if (valid < 64) r |= ~0ull << valid;
+        kb = resolve_tile(r, diag);
+        int cnt = __popcll(kb);
+        if (max_keep > 0 && total + cnt > max_keep) {
+          int need = max_keep - total;
+          u64 trimmed = 0ull, rest = kb;
+          while (need-- > 0) {
+            const u64 low = rest & (~rest + 1ull);
+            trimmed |= low;
+            rest ^= low;
+          }
+          kb = trimmed;
+          cnt = __popcll(kb);
+        }
+        total += cnt;
+        done = (max_keep > 0 && total >= max_keep) || k + 1 == nblk;
+        kept[k] = kb;
+        if (done) s_last = k, s_total_out = total;
+        __threadfence_block();
+        *reinterpret_cast<volatile int *>(&s_resolved) = done ? kDone : k + 1;
+      }
+      __syncwarp();
+      // hand the keep bits to the near warps (they sync on the same barrier)
+      asm volatile("bar.arrive %0, %1;" ::"r"(3 + (k & 1)), "n"(32 * (1 + ND)) : "memory");
+      kb = __shfl_sync(full, kb, 0);
+      total = __shfl_sync(full, total, 0);
+      if (__shfl_sync(full, (int)done, 0)) break;
+      // column k+1, row block k: mask the speculative tile by the keep bits
+      const bool k0 = (kb >> lane) & 1ull, k1 = (kb >> (lane + 32)) & 1ull;
+      const u64 v = (k0 ? near1[lane] : 0ull) | (k1 ? near1[lane + 32] : 0ull);
+      const unsigned lo = __reduce_or_sync(full, (unsigned)v), hi = __reduce_or_sync(full, (unsigned)(v >> 32));
+      r_near = ((u64)hi << 32) | lo;
+      __syncwarp();  // the slot is refilled two iterations from now; every lane is done with it
+    }
+  } else if (warp <= ND) {
+    // ---- near warps: column k+d of row block k, d = warp + 1; warp 1 also writes the kept boxes out -------
+    const int d = warp + 1;
+    for (int p = 0; p < kRing - 1; ++p) {
+      fetch_tile(p, d, p, p + d);
+      commit();
+    }
+    int base = 0, pr0 = -1, pr1 = -1;
+    float4 pb0 = make_float4(0.f, 0.f, 0.f, 0.f), pb1 = pb0;
+    auto store_pending = [&]() {
+      if (pr0 >= 0) {
+        float *q = o.rois + ((size_t)seg * o.post + pr0) * 5;
+        q[0] = (float)seg, q[1] = pb0.x, q[2] = pb0.y, q[3] = pb0.z, q[4] = pb0.w;
+      }
+      if (pr1 >= 0) {
+        float *q = o.rois + ((size_t)seg * o.post + pr1) * 5;
+        q[0] = (float)seg, q[1] = pb1.x, q[2] = pb1.y, q[3] = pb1.z, q[4] = pb1.w;
+      }
+      pr0 = pr1 = -1;
+    };
+    for (int k = 0; k < nblk; ++k) {
+      {
+        const int kk = k + kRing - 1;
+        fetch_tile(kk % kRing, d, kk, kk + d);
+        commit();
+        wait_oldest();
+      }
+      const u64 *nt = ring + ((k % kRing) * kTiles + d) * 64;
+      asm volatile("bar.sync %0, %1;" ::"r"(3 + (k & 1)), "n"(32 * (1 + ND)) : "memory");
+      const bool last = ld_volatile_s32(&s_resolved) == kDone && ld_volatile_s32(&s_last) == k;
+      const u64 kb = *reinterpret_cast<volatile u64 *>(kept + k);
+      const bool k0 = (kb >> lane) & 1ull, k1 = (kb >> (lane + 32)) & 1ull;
+      if (!last) {
+        const u64 v = (k0 ? nt[lane] : 0ull) | (k1 ? nt[lane + 32] : 0ull);
+        const unsigned lo = __reduce_or_sync(full, (unsigned)v), hi = __reduce_or_sync(full, (unsigned)(v >> 32));
+        if (lane == 0 && k + d < nblk && (lo | hi)) atomicOr(&remv[k + d], ((u64)hi << 32) | lo);
+        __threadfence_block();
+        // the resolver waits for this at its step k+2
+        if (k + 2 < nblk) asm volatile("bar.arrive %0, %1;" ::"r"(1 + (k & 1)), "n"(32 * (1 + ND)) : "memory");
+      }
+      if (warp == 1) {
+        // write-out, one step behind: the boxes fetched at the previous step are stored now, this step's are
+        // fetched (an L2 round trip that must not sit between two barrier hand-overs)
+        store_pending();
+        if (k0) {
+          const int rank = base + __popcll(kb & ((1ull << lane) - 1ull)), idx = k * 64 + lane;
+          if (o.keep) o.keep[off + rank] = idx;
+          if (o.rois && rank < o.post) pr0 = rank, pb0 = segs.load_box(off + idx);
+        }
+        if (k1) {
+          const int rank = base + __popcll(kb & ((1ull << (lane + 32)) - 1ull)), idx = k * 64 + lane + 32;
+          if (o.keep) o.keep[off + rank] = idx;
+          if (o.rois && rank < o.post) pr1 = rank, pb1 = segs.load_box(off + idx);
+        }
+        base += __popcll(kb);
+      }
+      if (last) break;
+      __syncwarp();
+    }
+    store_pending();
+  } else {
+    // ---- far warps: warp (group g, part q) owns columns 32 g + lane and their row blocks j = q (mod NP) ----
+    const int fw = warp - ND - 1;
+    const int q = fw % NP, g = fw / NP;
+    const int w = g * 32 + lane;
+    const bool mine = g < groups && w < nblk;
+    const int last_j = mine ? w - ND - 2 : -1;  // row blocks 0 .. last_j are far for column w
+    const int warp_last = __reduce_max_sync(full, last_j);
+    const u64 *col = m + (mine ? w : 0);  // lanes = consecutive column blocks: a kept row is one contiguous read
+    u64 r = 0ull;
+    int seen = 0;
+    bool open = mine;
+    // a part is handed over as soon as its last row block is in (the resolver waits for NP parts per column)
+    auto close_if_done = [&](int next_j) {
+      if (open && next_j > last_j) {
+        if (r) atomicOr(&remv[w], r);
+        __threadfence_block();
+        atomicAdd(far_done + w, 1);
+        open = false;
+      }
+    };
+    close_if_done(q);
+    for (int j = q; j <= warp_last; j += NP) {
+      if (seen <= j) {
+        if (lane == 0)
+          while ((seen = ld_volatile_s32(&s_resolved)) <= j) __nanosleep(64);
+        seen = __shfl_sync(full, seen, 0);
+        __threadfence_block();
+      }
+      if (seen == kDone && j > ld_volatile_s32(&s_last)) break;  // the resolver stopped before row block j
+      u64 kb = *reinterpret_cast<volatile u64 *>(kept + j);
+      if (j <= last_j) {
+        const u64 *row = col + (size_t)j * 64 * stride;
+        while (kb) {  // 8 loads in flight
+          u64 v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            v[e] = 0ull;
+            if (kb) {
+              const int i = __ffsll((long long)kb) - 1;
+              kb &= kb - 1ull;
+              v[e] = row[(size_t)i * stride];
+            }
+          }
+          r |= ((v[0] | v[1]) | (v[2] | v[3])) | ((v[4] | v[5]) | (v[6] | v[7]));
+        }
+      }
+      close_if_done(j + NP);
+    }
+    close_if_done(0x7fffffff);  // the resolver stopped early: nobody reads the column any more
+  }
+  __syncthreads();
+  o.finish(seg, off, n, s_total_out, t, kScanThreads);
 }
 
 // ----------------------------------------------------------------------------------------
@@ -464,8 +993,8 @@ static size_t small_smem(int max_pad) {
 size_t nms_mask_bytes(int nseg, int max_seg, int max_keep) {
   if (max_keep > 0 && max_keep <= kLazyMaxKeep) return 0;  // kept-list path: no mask
   if (nseg <= 0 || max_seg <= 0) return 0;
-  const size_t nblk = (size_t)(max_seg + 63) / 64;
-  return (size_t)nseg * nblk * nblk * 64 * sizeof(unsigned long long);
+  const size_t nblk = (size_t)(max_seg + 63) / 64, stride = (nblk + 3) / 4 * 4;  // row-major rows: 4-word sectors
+  return (size_t)nseg * nblk * stride * 64 * sizeof(unsigned long long);
 }
 
 int nms_launch(const NmsSegs &segs, int nseg, int max_seg, float thresh, int max_keep,
@@ -512,15 +1041,29 @@ int nms_launch(const NmsSegs &segs, int nseg, int max_seg, float thresh, int max
     return launch_status();
   }
   const int max_blk = (max_seg + 63) / 64;
-  const size_t seg_stride = (size_t)max_blk * max_blk * 64;
+  const size_t seg_stride = (size_t)max_blk * ((max_blk + 3) / 4 * 4) * 64;
   const size_t need = (size_t)nseg * seg_stride * sizeof(unsigned long long);
   if (!workspace || workspace_bytes < need) return RLOD_ENOSPC;
   if (nseg > 65535) return RLOD_EUNSUPPORTED;
   unsigned long long *mask = (unsigned long long *)workspace;
   const unsigned tiles = (unsigned)((long long)max_blk * (max_blk + 1) / 2);
+  static const bool scan_v1 = getenv("RLOD_NMS_SCAN_V1") != nullptr;  // A/B switch: the unpipelined scan
+  static const bool scan_v2 = getenv("RLOD_NMS_SCAN_V2") != nullptr;  // A/B switch: the pipelined, barrier-per-step scan
+  if (max_blk <= kScan3MaxBlk && !scan_v1 && !scan_v2 && nseg <= 65535) {
+    // row-major mask (rows of (max_blk rounded up to 4) words; fits the same workspace: 64 max_blk rows) + decoupled scan
+    const int g4 = (max_blk + 3) / 4;
+    RLOD_LAUNCH(RLOD_KERNEL_NMS_MASK, st, k_nms_mask_rm<<<dim3(g4, max_blk, nseg), 64, 0, st>>>(segs, thresh, mask, seg_stride));
+    RLOD_LAUNCH(RLOD_KERNEL_NMS_SCAN, st, k_nms_scan3<<<nseg, kScanThreads, (size_t)max_blk * 20 + 4 * (2 + kScan3Near) * 64 * 8 + 16, st>>>(
+        segs, max_keep, mask, seg_stride, out));
+    return launch_status();
+  }
   RLOD_LAUNCH(RLOD_KERNEL_NMS_MASK, st, k_nms_mask<<<dim3(tiles, nseg), 64, 0, st>>>(segs, thresh, max_blk, mask, seg_stride));
-  RLOD_LAUNCH(RLOD_KERNEL_NMS_SCAN, st, k_nms_scan<<<nseg, kScanThreads, (size_t)max_blk * sizeof(unsigned long long), st>>>(
-      segs, max_keep, mask, seg_stride, out));
+  if (max_blk <= kScan2MaxBlk && !scan_v1)
+    RLOD_LAUNCH(RLOD_KERNEL_NMS_SCAN, st, k_nms_scan2<<<nseg, kScanThreads, (size_t)max_blk * sizeof(unsigned long long), st>>>(
+        segs, max_keep, mask, seg_stride, out));
+  else
+    RLOD_LAUNCH(RLOD_KERNEL_NMS_SCAN, st, k_nms_scan<<<nseg, kScanThreads, (size_t)max_blk * sizeof(unsigned long long), st>>>(
+        segs, max_keep, mask, seg_stride, out));
   return launch_status();
 }
 
@@ -540,8 +1083,8 @@ RLOD_API int rlod_debug_nms_force_large(int on) {
 RLOD_API size_t rlod_nms_workspace_bytes(int nseg, int max_seg) {
   if (nseg <= 0 || max_seg <= 0) return 0;
   if (max_seg <= kSmallMaxN && !g_force_large) return 0;  // mask lives in shared memory
-  const size_t nblk = (size_t)(max_seg + 63) / 64;
-  return (size_t)nseg * nblk * nblk * 64 * sizeof(unsigned long long);
+  const size_t nblk = (size_t)(max_seg + 63) / 64, stride = (nblk + 3) / 4 * 4;  // row-major rows: 4-word sectors
+  return (size_t)nseg * nblk * stride * 64 * sizeof(unsigned long long);
 }
 
 RLOD_API int rlod_nms(const float *dets, int n, int stride, float thresh, int max_keep, int *keep,
