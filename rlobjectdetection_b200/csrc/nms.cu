@@ -266,18 +266,6 @@ __global__ void __launch_bounds__(kScanThreads)
   o.finish(seg, off, n, s_total, t, kScanThreads);
 }
 
-// ----------------------------------------------------------------------------------------
-// scan kernel, software-pipelined (round 2): the same greedy scan, for nblk <= 256 column blocks
-// (n <= 16384).  k_nms_scan pays one L2 round trip per block on its critical path (the kept rows of
-// block k are fetched after block k is resolved and OR-ed into remv[] before block k + 1 may start):
-// 308 us at n = 12000.  Here nothing on the path waits for memory:
-//   * the kept rows of block k are fetched for all far column blocks when k is resolved, but reduced and
-//     OR-ed into remv[] one step LATER (column block c belongs to warp c % 32, which keeps the pending
-//     words of its <= 6 columns in registers);
-//   * the three column blocks after k ("near": their loads could not land in time) are fetched
-//     speculatively, all 64 rows, two steps ahead, and masked by the keep bits once they are known;
-//   * the diagonal tile travels two steps ahead as well; two CTA barriers per step instead of three.
-// ----------------------------------------------------------------------------------------
 // Greedy resolve of one 64 x 64 diagonal tile by ONE thread: box i of the block is kept unless a kept
 // earlier box (or an earlier block: r) removed it; a kept box removes the boxes of its row.  Written on
 // 32-bit halves with selects instead of branches: the chain is test -> OR, ~10 cycles per box (the
@@ -329,126 +317,8 @@ __device__ __forceinline__ unsigned long long resolve_tile(unsigned long long r,
   return ((unsigned long long)khi << 32) | klo;
 }
 
-constexpr int kScan2MaxBlk = 192;  // 6 column slots per warp: the pending loads stay in registers
-constexpr int kScan2Near = 3;
-
-__global__ void __launch_bounds__(kScanThreads, 1)
-    k_nms_scan2(NmsSegs segs, int max_keep, const unsigned long long *__restrict__ mask,
-                size_t mask_seg_stride, NmsOut o) {
-  extern __shared__ unsigned long long remv[];  // [nblk]
-  __shared__ unsigned long long diag[2][64];
-  __shared__ unsigned long long s_kept;
-  __shared__ int s_base, s_total;
-  typedef unsigned long long u64;
-  constexpr int ND = kScan2Near;
-  constexpr int NU = kScan2MaxBlk / 32;  // column slots per warp
-  const int seg = blockIdx.x;
-  int off, n;
-  segs.get(seg, off, n);
-  const int nblk = (n + 63) >> 6, npad = nblk << 6;
-  const u64 *m = mask + (size_t)seg * mask_seg_stride;
-  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  const unsigned full = 0xffffffffu;
-  for (int w = t; w < nblk; w += kScanThreads) remv[w] = 0ull;
-  if (t == 0) s_total = 0;
-  // word of row `r` of row block rb in column block cb (0 when outside)
-  auto tile_word = [&](int rb, int cb, int r) -> u64 {
-    return (cb < nblk && rb < nblk) ? m[(size_t)cb * npad + rb * 64 + r] : 0ull;
-  };
-  // diagonal tiles, two steps ahead (threads 0..63)
-  u64 d_a = 0ull, d_b = 0ull;
-  if (t < 64) {
-    diag[0][t] = tile_word(0, 0, t);
-    d_a = tile_word(1, 1, t), d_b = tile_word(2, 2, t);
-  }
-  // near tiles (warps 0..ND-1: warp d-1 holds tile (k, k+d), rows lane and lane+32), two steps ahead
-  u64 nc0 = 0ull, nc1 = 0ull, na0 = 0ull, na1 = 0ull, nb0 = 0ull, nb1 = 0ull;
-  if (warp < ND) {
-    const int d = warp + 1;
-    nc0 = tile_word(0, d, lane), nc1 = tile_word(0, d, lane + 32);
-    na0 = tile_word(1, 1 + d, lane), na1 = tile_word(1, 1 + d, lane + 32);
-    nb0 = tile_word(2, 2 + d, lane), nb1 = tile_word(2, 2 + d, lane + 32);
-  }
-  // far columns of this warp (column w = warp + 32 u): the words loaded for the last resolved row block
-  u64 pend0[NU], pend1[NU];
-#pragma unroll
-  for (int u = 0; u < NU; ++u) pend0[u] = pend1[u] = 0ull;
-  __syncthreads();
-
-  for (int k = 0; k < nblk; ++k) {
-    if (t == 0) {
-      u64 r = remv[k];
-      const int valid = min(64, n - k * 64);
-      if (valid < 64) r |= ~0ull << valid;
-      const u64 kb0 = resolve_tile(r, diag[k & 1]);
-      u64 kb = kb0;
-      int total = s_total;
-      int cnt = __popcll(kb);
-      if (max_keep > 0 && total + cnt > max_keep) {
-        int need = max_keep - total;
-        u64 trimmed = 0ull, rest = kb;
-        while (need-- > 0) {
-          const u64 low = rest & (~rest + 1ull);
-          trimmed |= low;
-          rest ^= low;
-        }
-        kb = trimmed;
-        cnt = __popcll(kb);
-      }
-      s_kept = kb;
-      s_base = total;
-      s_total = total + cnt;
-    }
-    __syncthreads();
-    const u64 kb = s_kept;
-    const int base = s_base, total = s_total;
-    if (t < 64 && ((kb >> t) & 1ull)) {
-      const int rank = base + __popcll(kb & ((1ull << t) - 1ull));
-      o.emit(seg, off, rank, k * 64 + t, segs);
-    }
-    if (max_keep > 0 && total >= max_keep) break;  // CTA-uniform
-    const bool k0 = (kb >> lane) & 1ull, k1 = (kb >> (lane + 32)) & 1ull;
-    // next diagonal tile -> shared memory; the one after the next two starts travelling
-    if (t < 64) {
-      diag[(k + 1) & 1][t] = d_a;
-      d_a = d_b;
-      d_b = tile_word(k + 3, k + 3, t);
-    }
-    // near columns k+1 .. k+ND: mask the speculative rows by the keep bits
-    if (warp < ND) {
-      const int d = warp + 1;
-      const u64 v = (k0 ? nc0 : 0ull) | (k1 ? nc1 : 0ull);
-      const unsigned lo = __reduce_or_sync(full, (unsigned)v), hi = __reduce_or_sync(full, (unsigned)(v >> 32));
-      if (lane == 0 && k + d < nblk) atomicOr(&remv[k + d], ((u64)hi << 32) | lo);
-      nc0 = na0, nc1 = na1, na0 = nb0, na1 = nb1;
-      nb0 = tile_word(k + 3, k + 3 + d, lane), nb1 = tile_word(k + 3, k + 3 + d, lane + 32);
-    }
-    // far columns (>= k+ND+1) of this warp: reduce the words fetched for row block k-1 (they had a whole
-    // step to arrive) into remv[], then fetch the kept rows of row block k.  Column c is complete before it
-    // is resolved: row blocks <= c-ND-1 reach it this way by step c-ND, the last ND ones through the near path
-#pragma unroll
-    for (int u = 0; u < NU; ++u) {
-      const int w = warp + 32 * u;
-      if (w >= k + ND && w < nblk) {  // fetched at step k-1 (warp-uniform)
-        const u64 v = pend0[u] | pend1[u];
-        const unsigned lo = __reduce_or_sync(full, (unsigned)v), hi = __reduce_or_sync(full, (unsigned)(v >> 32));
-        if (lane == 0 && (lo | hi)) atomicOr(&remv[w], ((u64)hi << 32) | lo);
-      }
-      pend0[u] = pend1[u] = 0ull;
-      if (w >= k + ND + 1 && w < nblk) {
-        const u64 *col = m + (size_t)w * npad + k * 64;
-        if (k0) pend0[u] = col[lane];
-        if (k1) pend1[u] = col[lane + 32];
-      }
-    }
-    __syncthreads();
-  }
-  __syncthreads();
-  o.finish(seg, off, n, s_total, t, kScanThreads);
-}
-
 // ----------------------------------------------------------------------------------------
-// scan kernel, decoupled (round 2, third form): the greedy scan as three groups of warps of ONE CTA that
+// scan kernel, decoupled (round 2): the greedy scan as three groups of warps of ONE CTA that
 // never meet at a CTA barrier inside the loop.
 //   * warp 0, the RESOLVER, owns the serial chain: block k's removed word -> resolve_tile -> keep bits
 //     -> publish (kept[k], resolved = k+1) -> emit -> its own share of the next column (d = 1: the tile
@@ -459,8 +329,8 @@ __global__ void __launch_bounds__(kScanThreads, 1)
 //     named barrier pair; they trail the resolver by at most a step;
 //   * the remaining warps are the FAR threads: thread w owns column block w and ORs, for every row block
 //     j <= w-ND-2 and every KEPT row i of it, the word m[w][64 j + i] into a private register -- one load
-//     and one OR per (kept row, column), no reduction, no atomics (the per-step reductions of k_nms_scan /
-//     scan2 were 2 350 warp instructions per step on this single SM) -- following `resolved` at their
+//     and one OR per (kept row, column), no reduction, no atomics (the per-step warp reductions of
+//     k_nms_scan are 2 350 warp instructions per step on this single SM) -- following `resolved` at their
 //     own pace; when a column is complete it is handed to remv[] and flagged.
 // Valid for nblk <= 32 * (32 - 1 - ND) column blocks; larger inputs take k_nms_scan.
 // ----------------------------------------------------------------------------------------
@@ -1048,8 +918,7 @@ int nms_launch(const NmsSegs &segs, int nseg, int max_seg, float thresh, int max
   unsigned long long *mask = (unsigned long long *)workspace;
   const unsigned tiles = (unsigned)((long long)max_blk * (max_blk + 1) / 2);
   static const bool scan_v1 = getenv("RLOD_NMS_SCAN_V1") != nullptr;  // A/B switch: the unpipelined scan
-  static const bool scan_v2 = getenv("RLOD_NMS_SCAN_V2") != nullptr;  // A/B switch: the pipelined, barrier-per-step scan
-  if (max_blk <= kScan3MaxBlk && !scan_v1 && !scan_v2 && nseg <= 65535) {
+  if (max_blk <= kScan3MaxBlk && !scan_v1 && force_large != 2 && nseg <= 65535) {
     // row-major mask (rows of (max_blk rounded up to 4) words; fits the same workspace: 64 max_blk rows) + decoupled scan
     const int g4 = (max_blk + 3) / 4;
     RLOD_LAUNCH(RLOD_KERNEL_NMS_MASK, st, k_nms_mask_rm<<<dim3(g4, max_blk, nseg), 64, 0, st>>>(segs, thresh, mask, seg_stride));
@@ -1058,12 +927,8 @@ int nms_launch(const NmsSegs &segs, int nseg, int max_seg, float thresh, int max
     return launch_status();
   }
   RLOD_LAUNCH(RLOD_KERNEL_NMS_MASK, st, k_nms_mask<<<dim3(tiles, nseg), 64, 0, st>>>(segs, thresh, max_blk, mask, seg_stride));
-  if (max_blk <= kScan2MaxBlk && !scan_v1)
-    RLOD_LAUNCH(RLOD_KERNEL_NMS_SCAN, st, k_nms_scan2<<<nseg, kScanThreads, (size_t)max_blk * sizeof(unsigned long long), st>>>(
-        segs, max_keep, mask, seg_stride, out));
-  else
-    RLOD_LAUNCH(RLOD_KERNEL_NMS_SCAN, st, k_nms_scan<<<nseg, kScanThreads, (size_t)max_blk * sizeof(unsigned long long), st>>>(
-        segs, max_keep, mask, seg_stride, out));
+  RLOD_LAUNCH(RLOD_KERNEL_NMS_SCAN, st, k_nms_scan<<<nseg, kScanThreads, (size_t)max_blk * sizeof(unsigned long long), st>>>(
+      segs, max_keep, mask, seg_stride, out));
   return launch_status();
 }
 

@@ -40,7 +40,7 @@ def _sorted_dets(seed, n, im=600.0, smin=8.0, smax=200.0):
     return torch.cat([bx, sc[:, None]], 1).contiguous()
 
 
-@pytest.mark.parametrize("force_large", [0, 1])
+@pytest.mark.parametrize("force_large", [0, 1, 2])  # 2: the scan kernel of segments beyond 57 344 boxes
 @pytest.mark.parametrize("n", [1, 2, 63, 64, 65, 300, 511, 513, 1000, 3000])
 @pytest.mark.parametrize("thresh", [0.3, 0.7])
 def test_nms_bit_exact(orc, n, thresh, force_large):
@@ -67,6 +67,20 @@ def test_nms_max_keep(orc, max_keep):
     assert np.array_equal(keep[:k].cpu().numpy(), ref)
 
 
+@pytest.mark.parametrize("max_keep", [0, 600, 777, 1500])
+@pytest.mark.parametrize("smax", [60.0, 400.0])
+def test_nms_decoupled_scan_early_stop(orc, max_keep, smax):
+    """Row-major mask + decoupled scan (n > 512, more than 512 keeps allowed): light and heavy suppression,
+    stops in the middle of a block and of the far warps' row-block schedule, ragged last block."""
+    dets = _sorted_dets(31, 5003, smax=smax)
+    ref = orc.nms(dets.numpy(), 0.6, max_keep=max_keep)
+    keep, num = be.nms_padded(cu(dets), 0.6, max_keep=max_keep)
+    k = int(num.item())
+    assert k == len(ref)
+    assert np.array_equal(keep[:k].cpu().numpy(), ref)
+    assert (keep[k:].cpu().numpy() == -1).all()
+
+
 def test_nms_near_threshold_and_degenerate(orc):
     # integer boxes whose IoU sits exactly on / one ulp around the threshold, duplicates,
     # inverted and zero-size boxes: decisions must equal the IEEE-division reference
@@ -81,7 +95,7 @@ def test_nms_near_threshold_and_degenerate(orc):
     dets = np.concatenate([boxes, np.linspace(1, 0, len(boxes), dtype=np.float32)[:, None]], 1)
     for thresh in (0.5, 0.25, 1.0 / 3.0, 0.7, 0.0, 0.9999999, -0.5, 1.5):
         ref = orc.nms(dets, thresh)
-        for fl in (0, 1):
+        for fl in (0, 1, 2):
             prev = be.lib().rlod_debug_nms_force_large(fl)
             try:
                 keep, num = be.nms_padded(cu(dets), thresh)
