@@ -31,11 +31,12 @@ def test_workspace_queries_are_pure_host_arithmetic():
     from rlobjectdetection_b200.model import _backend as be
     lib = be.lib()
     assert lib.rlod_nms_workspace_bytes(1, 300) == 0                      # shared-memory path
-    assert lib.rlod_nms_workspace_bytes(1, 12000) == 188 * 188 * 64 * 8   # [col_block][row] mask
-    assert lib.rlod_nms_workspace_bytes(24, 6000) == 24 * 94 * 94 * 64 * 8
+    assert lib.rlod_nms_workspace_bytes(1, 12000) == 188 * 188 * 64 * 8   # [row][col_block] mask, rows of 4-word sectors
+    assert lib.rlod_nms_workspace_bytes(24, 6000) == 24 * 94 * 96 * 64 * 8
     small = lib.rlod_roi_align_workspace_bytes(4, 1024, 7, 7, be.POOL_AVG)
-    # 128-byte plan + 128-byte forward-kernel record + 4-byte order entry per roi (8x8 sample grid)
-    assert 1024 * 260 <= small < 1024 * 260 + 64 * 1024
+    # per roi (8x8 sample grid): 128-byte plan + 128-byte forward-kernel record + 768-byte backward-kernel record
+    # + order entries
+    assert 1024 * (260 + 768) <= small < 1024 * (260 + 768) + 64 * 1024
     # post_nms_topN <= 512: kept-list NMS, no n x n mask in the proposal workspace; beyond: the mask
     assert 12000 * 16 <= lib.rlod_proposal_workspace_bytes(1, 9, 37, 62, 12000, 300) < 12000 * 16 + 188 * 188 * 512
     assert lib.rlod_proposal_workspace_bytes(1, 9, 37, 62, 12000, 2000) >= 12000 * 16 + 188 * 188 * 512
