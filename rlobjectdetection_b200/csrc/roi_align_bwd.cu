@@ -11,10 +11,11 @@
 //     columns of grad_out (2 for a wide roi, up to 7 when the whole roi sits inside two pixels; the
 //     1/4 of the average pooling is folded in as 1/2 per axis).  Lanes of one instruction therefore
 //     never meet in a pixel, whatever the roi's size -- no rank rounds, no intra-warp exclusion.
-//   * All lanes walk the 8 sample rows together (the walk codes are per roi, i.e. warp-uniform) with
-//     the forward kernel's two line slots: a slot accumulates while consecutive sample rows share
-//     the pixel row and is handed to one of 16 static flush slots when the row is left, so a roi adds
-//     to every DISTINCT pixel it touches exactly once.  The flushes of a roi hit distinct rows by
+//   * All lanes walk the 8 sample rows together with the forward kernel's two line slots: a slot
+//     accumulates while consecutive sample rows share the pixel row and is handed to one of 16 static
+//     flush slots when the row is left, so a roi adds to every DISTINCT pixel it touches exactly once.
+//     The slot logic is pure arithmetic on two 0 / 1 factors per sample row that the plan supplies (keep,
+//     shift): five packed operations per sample row, no integer instruction, no select.  The flushes of a roi hit distinct rows by
 //     construction, so they are issued as independent batches (8 LDS.64, 8 packed adds, 8 STS.64, twice);
 //     slots that are not flushed point at a dump row behind the planes instead of being predicated.
 //   * Exclusion between the warps of a CTA (4-12 warps share the planes) is a TOKEN RING instead of
@@ -35,8 +36,9 @@
 // sample gradient to its four taps) after the avg_pool2d(2, 1) backward of
 // lib/model/roi_align/modules/roi_align.py:26-29.  Rounding order differs from the reference's
 // atomicAdd order (which is not fixed); tolerance 1e-5 in the tests.  Zero-weight padding of the column
-// windows multiplies the roi's own grad_out values by 0: a non-finite grad_out value can therefore
-// reach every column of its roi as NaN, where the reference confines it to the taps of its samples.
+// windows and the 0 / 1 factors of the row walk multiply the roi's own grad_out values by 0: a non-finite
+// grad_out value can therefore reach every tap of its roi as NaN, where the reference confines it to the taps
+// of its samples.
 #include "roi_lists.cuh"
 
 namespace rlod {
@@ -46,17 +48,16 @@ typedef unsigned long long u64;
 constexpr int kOwnWords = 192;  // record words per roi (768 bytes)
 // record layout (32-bit words):
 //   [0..127]   column slot n (0..15): 8 weights over grad_out columns a_n .. a_n + L_n - 1
-//   [128..143] column slot n: x * 16 (bits 0-15) | a_n << 16 (3 bits) | L_n << 20 (4 bits; 0 = unused slot)
+//   [128..143] column slot n: x * 16 (bits 0-15) | a_n << 16 (3 bits) | L_n << 20 (4 bits; 0 = unused slot) | max L << 24
 //   [144..159] flush slot k: byte offset of the pixel row it adds to (y * W * 16), or H * W * 16 = the
 //              dump row behind the planes when the slot is not flushed.  Slot 2t-2 / 2t-1 (t = 1..7) holds the
 //              upper / lower line slot as it is when the walk reaches sample row t, slots 14 / 15 the two at
 //              the end
-//   [160..167] sample row t: weight of the upper tap row   (1 - ratio) [* 1/2 for AVG]
-//   [168..175] sample row t: weight of the lower tap row   ratio       [* 1/2 for AVG]
-//   [176]      walk codes, 2 bits per sample row: 0 keep both line slots, 1 lower slot becomes upper
-//              (flush upper), 2 flush both and restart, 3 restart without flush
-//   [177]      max L_n
-//   [178..191] unused
+//   [160..191] sample row t: {weight of the upper tap row (1 - ratio), of the lower tap row (ratio) [* 1/2 for AVG],
+//              mT, mS}: the walk's line slots as arithmetic -- upper' = mT * upper + mS * lower + wt * G,
+//              lower' = mT * lower + wb * G, with (mT, mS) = (1, 0) when sample row t shares its tap rows with
+//              t - 1, (0, 1) when its upper row is the previous lower row, (0, 0) when it starts afresh
+//   column-slot word bits 24-27: max L_n over the slots (the same in every slot)
 
 __device__ __forceinline__ u64 pack2f(float lo, float hi) {
   u64 r;
@@ -189,7 +190,7 @@ __global__ void __launch_bounds__(128)
       for (int q = 0; q < 8; ++q)
         if (q >= qa && q <= qb) wr[q - a] = __float_as_int(wv[q]);
     }
-    rec[128 + lane] = Ln > 0 ? ((X * 16) | (a << 16) | (Ln << 20)) : 0;
+    rec[128 + lane] = (Ln > 0 ? ((X * 16) | (a << 16) | (Ln << 20)) : 0) | (Lmax << 24);
   }
 
   // ---- rows ------------------------------------------------------------------------------
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(128)
     axis8(roi[2], roi[4], scale, H, bvalid, cy);
     const float f = avg ? 0.5f : 1.f;
     const int dump = H * W * 16, rowb = W * 16;
-    int cur = -1, codes = 0;
+    int cur = -1;
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
       int code;
@@ -215,18 +216,17 @@ __global__ void __launch_bounds__(128)
         code = cur >= 0 ? 2 : 3;
         cur = -1;
       }
-      codes |= code << (2 * t);
       if (t > 0) {
         rec[144 + 2 * t - 2] = (code == 1 || code == 2) ? prev * rowb : dump;
         rec[144 + 2 * t - 1] = code == 2 ? (prev + 1) * rowb : dump;
       }
-      rec[160 + t] = __float_as_int(wt);
-      rec[168 + t] = __float_as_int(wb);
+      rec[160 + 4 * t] = __float_as_int(wt);
+      rec[161 + 4 * t] = __float_as_int(wb);
+      rec[162 + 4 * t] = __float_as_int(code == 0 ? 1.f : 0.f);
+      rec[163 + 4 * t] = __float_as_int(code == 1 ? 1.f : 0.f);
     }
     rec[144 + 14] = cur >= 0 ? cur * rowb : dump;
     rec[144 + 15] = cur >= 0 ? (cur + 1) * rowb : dump;
-    rec[176] = codes;
-    rec[177] = Lmax;
   }
 }
 
@@ -296,7 +296,12 @@ __global__ void __launch_bounds__(NW * 32, 24 / NW)
 
   const int nslot = lane >> 1, h = lane & 1;
   const uint32_t pl = smem_u32(planes) + 8u * (uint32_t)h;
-  int r = roi_at(0), r_next = roi_at(1);
+  // this warp's roi ids, 32 at a time: lane l holds the id of its (kbase + l)-th roi
+  int ids = roi_at(lane), kbase = 0;
+  auto roi_id = [&](int k) {  // kbase <= k < kbase + 32 (warp-uniform k)
+    return __shfl_sync(0xffffffffu, ids, k - kbase);
+  };
+  int r = roi_id(0), r_next = roi_id(1);
   auto prefetch_rec = [&](int rr) {  // 768 bytes = 6 lines
     if (rr >= 0 && lane < 6) asm volatile("prefetch.global.L1 [%0];" ::"l"(rec + (size_t)rr * kOwnWords + lane * 32));
   };
@@ -305,16 +310,19 @@ __global__ void __launch_bounds__(NW * 32, 24 / NW)
   for (int k = 0; r >= 0; ++k) {
     const int *rp = rec + (size_t)r * kOwnWords;
     prefetch_rec(r_next);
-    const int r_refill = roi_at(k + NS);
-    const int r_nn = roi_at(k + 2);
+    if (k + NS >= kbase + 32) {  // the ring holds ids k .. ; refill it so that k + NS is inside
+      kbase = k;
+      ids = roi_at(k + lane);
+    }
+    const int r_refill = roi_id(k + NS);
+    const int r_nn = roi_id(k + 2);
     const int meta = __ldg(rp + 128 + nslot);
     const float4 w0 = __ldg(reinterpret_cast<const float4 *>(rp + nslot * 8));
-    const int2 hd = __ldg(reinterpret_cast<const int2 *>(rp + 176));  // walk codes, max L
-    const int Lmax = hd.y;
+    const int Lmax = (meta >> 24) & 15;
     float4 w1 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (Lmax > 4) w1 = __ldg(reinterpret_cast<const float4 *>(rp + nslot * 8) + 1);
     const int an = (meta >> 16) & 7;
-    const bool act = (meta >> 20) != 0;
+    const bool act = ((meta >> 20) & 15) != 0;
     const uint32_t pa = pl + ((uint32_t)meta & 0xffffu);
     const float wcol[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 
@@ -345,22 +353,22 @@ __global__ void __launch_bounds__(NW * 32, 24 / NW)
       G[7] = hv[6];
     }
 
-    // ---- row walk: two line slots, 16 static flush slots -------------------------------------
-    const float4 t0 = __ldg(reinterpret_cast<const float4 *>(rp + 160)), t1 = __ldg(reinterpret_cast<const float4 *>(rp + 164));
-    const float4 b0 = __ldg(reinterpret_cast<const float4 *>(rp + 168)), b1 = __ldg(reinterpret_cast<const float4 *>(rp + 172));
-    const float wts[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
-    const float wbs[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-    const int codes = hd.x;
+    // ---- row walk: two line slots, 16 static flush slots.  The slot logic is arithmetic on (mT, mS) from
+    // the plan: no integer instruction, no select -- five packed operations per sample row
     u64 sv[16];
-    u64 accT = mul2(pack2f(wts[0], wts[0]), G[0]), accB = mul2(pack2f(wbs[0], wbs[0]), G[0]);
+    u64 accT, accB;
+    {
+      const float4 wk = __ldg(reinterpret_cast<const float4 *>(rp + 160));
+      accT = mul2(pack2f(wk.x, wk.x), G[0]), accB = mul2(pack2f(wk.y, wk.y), G[0]);
+    }
 #pragma unroll
     for (int t = 1; t < 8; ++t) {
-      const int code = (codes >> (2 * t)) & 3;
+      const float4 wk = __ldg(reinterpret_cast<const float4 *>(rp + 160 + 4 * t));
       sv[2 * t - 2] = accT, sv[2 * t - 1] = accB;
-      const u64 inT = code == 0 ? accT : (code == 1 ? accB : 0ull);
-      const u64 inB = code == 0 ? accB : 0ull;
-      accT = fma2(pack2f(wts[t], wts[t]), G[t], inT);
-      accB = fma2(pack2f(wbs[t], wbs[t]), G[t], inB);
+      const u64 mT = pack2f(wk.z, wk.z), mS = pack2f(wk.w, wk.w);
+      const u64 x = fma2(mT, accT, mul2(mS, accB));
+      accB = fma2(pack2f(wk.y, wk.y), G[t], mul2(mT, accB));
+      accT = fma2(pack2f(wk.x, wk.x), G[t], x);
     }
     sv[14] = accT, sv[15] = accB;
 
