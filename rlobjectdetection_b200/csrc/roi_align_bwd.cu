@@ -179,18 +179,38 @@ __global__ void __launch_bounds__(128)
   // every slot reads Lmax consecutive grad_out columns (zero weights where it has fewer): its window
   // is shifted left where it would leave the row, so only the roi's own values are ever multiplied
   const int Lmax = __reduce_max_sync(full, Ln);
-  if (lane < 16) {
-    const int OWp = avg ? 7 : 8;
-    const int a = Ln > 0 ? (qa + Lmax <= OWp ? qa : OWp - Lmax) : 0;
+  // slot of every column: a flush request serves slots 0-7 and 8-15 as two half-warps, each conflict-free
+  // when its eight pixel columns differ mod 8 (16-byte pixels, 128-byte bank window).  Greedy, in column
+  // order: the first half-warp that does not hold the residue yet
+  int dest = lane;
+  {
+    unsigned mA = 0u, mB = 0u;
+    int cA = 0, cB = 0;
+    for (int nn = 0; nn < ncols; ++nn) {  // warp-uniform
+      const int rn = __shfl_sync(full, X, nn) & 7;
+      int d;
+      if (!((mA >> rn) & 1u) && cA < 8) d = cA++, mA |= 1u << rn;
+      else if (!((mB >> rn) & 1u) && cB < 8) d = 8 + cB++, mB |= 1u << rn;
+      else if (cA < 8) d = cA++;
+      else d = 8 + cB++;
+      if (nn == lane) dest = d;
+    }
+  }
+  if (lane < 16) {  // every slot empty first, then the used ones
     int *wr = rec + lane * 8;
 #pragma unroll
     for (int i = 0; i < 8; ++i) wr[i] = 0;
-    if (Ln > 0) {
+    rec[128 + lane] = Lmax << 24;
+  }
+  __syncwarp();
+  if (lane < ncols && Ln > 0) {
+    const int OWp = avg ? 7 : 8;
+    const int a = qa + Lmax <= OWp ? qa : OWp - Lmax;
+    int *wr = rec + dest * 8;
 #pragma unroll
-      for (int q = 0; q < 8; ++q)
-        if (q >= qa && q <= qb) wr[q - a] = __float_as_int(wv[q]);
-    }
-    rec[128 + lane] = (Ln > 0 ? ((X * 16) | (a << 16) | (Ln << 20)) : 0) | (Lmax << 24);
+    for (int q = 0; q < 8; ++q)
+      if (q >= qa && q <= qb) wr[q - a] = __float_as_int(wv[q]);
+    rec[128 + dest] = (X * 16) | (a << 16) | (Ln << 20) | (Lmax << 24);
   }
 
   // ---- rows ------------------------------------------------------------------------------
@@ -242,8 +262,10 @@ __device__ __forceinline__ void sts64(uint32_t a, u64 v) {
   asm volatile("st.shared.b64 [%0], %1;" ::"r"(a), "l"(v) : "memory");
 }
 
-template <int POOL, int NW>
-__global__ void __launch_bounds__(NW * 32, 24 / NW)
+// B16: all 16 read-modify-writes of a flush as ONE batch (one shared-memory latency under the token instead of
+// two; needs 16 more registers, so only the instances that run three or fewer CTAs per SM use it)
+template <int POOL, int NW, bool B16>
+__global__ void __launch_bounds__(NW * 32, B16 ? (18 / NW > 0 ? 18 / NW : 1) : 24 / NW)
     k_align8_bwd_own(const float *__restrict__ gout, const int *__restrict__ rec,
                      const int *__restrict__ order, const int *__restrict__ img_off, int C, int H,
                      int W, int n_quads, int ns_log2, int accumulate, float *__restrict__ gin) {
@@ -392,13 +414,21 @@ __global__ void __launch_bounds__(NW * 32, 24 / NW)
                  "r"(fa[8]), "r"(fa[9]), "r"(fa[10]), "r"(fa[11]), "r"(fa[12]), "r"(fa[13]), "r"(fa[14]), "r"(fa[15]));
     if (i_glob > 0) asm volatile("bar.sync %0, 64;" ::"r"(1 + warp) : "memory");
     if (act) {
+      if (B16) {
+        u64 old[16];
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        u64 old[8];
+        for (int j = 0; j < 16; ++j) old[j] = lds64(fa[j]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) old[j] = lds64(fa[half * 8 + j]);
+        for (int j = 0; j < 16; ++j) sts64(fa[j], addp2(old[j], sv[j]));
+      } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) sts64(fa[half * 8 + j], addp2(old[j], sv[half * 8 + j]));
+        for (int half = 0; half < 2; ++half) {
+          u64 old[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) old[j] = lds64(fa[half * 8 + j]);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) sts64(fa[half * 8 + j], addp2(old[j], sv[half * 8 + j]));
+        }
       }
     }
     if (i_glob + 1 < n) asm volatile("bar.arrive %0, 64;" ::"r"(warp + 1 == NW ? 1 : warp + 2) : "memory");
@@ -467,30 +497,39 @@ int launch_bwd_own(const float *grad_out, const float *rois, int B, int C, int H
   if (smem > (size_t)kMaxSmemPerCta) return RLOD_EUNSUPPORTED;
   const int n_quads = C / 4;
   const unsigned grid = (unsigned)(B * n_quads);
-#define RLOD_LAUNCH_OWN(POOL, NWW)                                                               \
+#define RLOD_LAUNCH_OWN(POOL, NWW, BB)                                                           \
   do {                                                                                           \
     static bool attr_set = false;                                                                \
     if (!attr_set) {                                                                             \
-      cudaFuncSetAttribute(k_align8_bwd_own<POOL, NWW>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+      cudaFuncSetAttribute(k_align8_bwd_own<POOL, NWW, BB>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                            kMaxSmemPerCta);                                                      \
       attr_set = true;                                                                           \
     }                                                                                            \
     ProfScope _ps(RLOD_KERNEL_ALIGN_BWD, st);                                                    \
-    k_align8_bwd_own<POOL, NWW><<<grid, NWW * 32, smem, st>>>(grad_out, ws.own, ws.order, ws.img_off, \
-                                                              C, H, W, n_quads, ns_log2, accumulate, \
-                                                              grad_in);                          \
+    k_align8_bwd_own<POOL, NWW, BB><<<grid, NWW * 32, smem, st>>>(grad_out, ws.own, ws.order, ws.img_off, \
+                                                                  C, H, W, n_quads, ns_log2, accumulate, \
+                                                                  grad_in);                      \
   } while (0)
+#define RLOD_LAUNCH_OWN_NW(POOL, BB)                    \
+  do {                                                  \
+    if (nw == 4) RLOD_LAUNCH_OWN(POOL, 4, BB);          \
+    else if (nw == 6) RLOD_LAUNCH_OWN(POOL, 6, BB);     \
+    else if (nw == 8) RLOD_LAUNCH_OWN(POOL, 8, BB);     \
+    else RLOD_LAUNCH_OWN(POOL, 12, BB);                 \
+  } while (0)
+  // one-batch flush where shared memory (not registers) limits the resident CTAs to 18 warps or fewer
+  static const int env_b16 = getenv("RLOD_BWD_B16") ? atoi(getenv("RLOD_BWD_B16")) : -1;
+  bool b16 = ctas(1 << ns_log2, nw) * nw <= 18;
+  if (env_b16 == 0) b16 = false;
+  if (env_b16 == 1 && ctas(1 << ns_log2, nw) * nw <= 18) b16 = true;
   if (pool_mode == RLOD_POOL_NONE) {
-    if (nw == 4) RLOD_LAUNCH_OWN(RLOD_POOL_NONE, 4);
-    else if (nw == 6) RLOD_LAUNCH_OWN(RLOD_POOL_NONE, 6);
-    else if (nw == 8) RLOD_LAUNCH_OWN(RLOD_POOL_NONE, 8);
-    else RLOD_LAUNCH_OWN(RLOD_POOL_NONE, 12);
+    if (b16) RLOD_LAUNCH_OWN_NW(RLOD_POOL_NONE, true);
+    else RLOD_LAUNCH_OWN_NW(RLOD_POOL_NONE, false);
   } else {
-    if (nw == 4) RLOD_LAUNCH_OWN(RLOD_POOL_AVG, 4);
-    else if (nw == 6) RLOD_LAUNCH_OWN(RLOD_POOL_AVG, 6);
-    else if (nw == 8) RLOD_LAUNCH_OWN(RLOD_POOL_AVG, 8);
-    else RLOD_LAUNCH_OWN(RLOD_POOL_AVG, 12);
+    if (b16) RLOD_LAUNCH_OWN_NW(RLOD_POOL_AVG, true);
+    else RLOD_LAUNCH_OWN_NW(RLOD_POOL_AVG, false);
   }
+#undef RLOD_LAUNCH_OWN_NW
 #undef RLOD_LAUNCH_OWN
   return launch_status();
 }
