@@ -151,7 +151,7 @@ class DetectRefineStep:
             self._prefetched = (self._key(ns, nd, ni, ng), self._light_work(cur, light, ns, nd, ni, ng, next_ready))
         cur.wait_event(have_refined)
         pooled_refined = self.align(feat, lt["refined"].view(-1, 5))
-        out = {n: lt[n].clone() for n in LIGHT_NAMES if n in lt and (n in self.outputs or (n == "refined" and self.backward))}
+        out = _copy_light(lt, [n for n in LIGHT_NAMES if n in lt and (n in self.outputs or (n == "refined" and self.backward))])
         consumed = torch.cuda.Event()
         consumed.record(cur)
         self._inflight.append((consumed, lt))
@@ -167,6 +167,27 @@ class DetectRefineStep:
     def capture(self, scores, deltas, im_info, feat, gt, next_inputs=None):
         """Record the step over these (fixed) input buffers into a CUDA graph -> GraphedStep."""
         return GraphedStep(self, (scores, deltas, im_info, feat, gt), next_inputs)
+
+
+def _copy_light(lt, names):
+    """The caller's copies of the light stream's tensors, made on the CURRENT stream: everything the fused
+    reward / refine kernel wrote lives in one allocation (lt.flat), so it is one device copy for all of
+    them plus one for the rois (two launches on the critical stream instead of one per tensor)."""
+    out = {}
+    flat = getattr(lt, "flat", None)
+    fused = [n for n in names if n != "rois"] if flat is not None else []
+    if len(fused) > 1:
+        mine = flat.clone()
+        base = flat.data_ptr()
+        for n in fused:
+            t = lt[n]
+            off = (t.data_ptr() - base) // 4
+            v = mine[off:off + t.numel()]
+            out[n] = (v.view(torch.int32) if t.dtype == torch.int32 else v).view(t.shape)
+    for n in names:
+        if n not in out:
+            out[n] = lt[n].clone()
+    return out
 
 
 def _kernel_wtrans(action):

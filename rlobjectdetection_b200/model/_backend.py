@@ -373,6 +373,11 @@ def move_from_act(boxes, preds, targets, act, maxk, corners=False):
     return correct
 
 
+class FusedOutputs(dict):
+    """{name: tensor} whose tensors are views into one allocation, `flat` (reward_refine)."""
+    flat = None
+
+
 def reward_refine(rois, gt, act, ngt=None, iou_thres=0.0, pos_wratio=1.0, neg_wratio=1.0, first_image=0,
                   wtrans=WTRANS_EXP_ABS, want=("reward", "label", "weight", "refined", "packed", "moved")):
     """rlod_reward_refine: rewards of every (box, action), the best positive action applied to every
@@ -387,17 +392,29 @@ def reward_refine(rois, gt, act, ngt=None, iou_thres=0.0, pos_wratio=1.0, neg_wr
     dev = rois.device
     if ngt is not None:
         ngt = ngt.to(torch.int32).contiguous()
-    out = {}
-    for name, shape in (("reward", (B, N, A)), ("label", (B, N, A)), ("weight", (B, N, A)), ("refined", (B, N, 5)),
-                        ("packed", (B, N, 5 + A))):
-        out[name] = torch.empty(shape, dtype=torch.float32, device=dev) if name in want else None
-    out["moved"] = torch.zeros(1, dtype=torch.int32, device=dev) if "moved" in want else None
+    # every requested tensor is a view into ONE allocation (the result's .flat): a caller on another stream takes its
+    # copy of the whole result with a single device copy (hotpath.DetectRefineStep) instead of one per tensor
+    shapes = [(name, shape) for name, shape in (("reward", (B, N, A)), ("label", (B, N, A)), ("weight", (B, N, A)),
+                                                ("refined", (B, N, 5)), ("packed", (B, N, 5 + A))) if name in want]
+    sizes = [(name, shape, (shape[0] * shape[1] * shape[2] + 3) // 4 * 4) for name, shape in shapes]  # 16-byte slices
+    total = sum(sz for _, _, sz in sizes) + 4
+    flat = torch.empty(total, dtype=torch.float32, device=dev)
+    out = {name: None for name in ("reward", "label", "weight", "refined", "packed", "moved")}
+    pos = 0
+    for name, shape, sz in sizes:
+        out[name] = flat[pos:pos + shape[0] * shape[1] * shape[2]].view(shape)
+        pos += sz
+    if "moved" in want:
+        out["moved"] = flat[pos:pos + 1].view(torch.int32)
+        out["moved"].zero_()
     with torch.cuda.device(dev):
         check(lib().rlod_reward_refine(ptr(rois), ptr(gt), ptr(ngt), ptr(act), B, N, A, G, int(wtrans),
                                        float(iou_thres), float(pos_wratio), float(neg_wratio), int(first_image),
                                        ptr(out["reward"]), ptr(out["label"]), ptr(out["weight"]), ptr(out["refined"]),
                                        ptr(out["packed"]), ptr(out["moved"]), stream_of(rois)), "rlod_reward_refine")
-    return {k: v for k, v in out.items() if v is not None}
+    res = FusedOutputs((k, v) for k, v in out.items() if v is not None)
+    res.flat = flat
+    return res
 
 
 def detect_postprocess(rois, cls_prob, bbox_pred, im_info, thresh=0.0, nms_thresh=0.3, max_per_image=100,
