@@ -39,3 +39,47 @@ def gather_results(packed, global_batch, group=None):
     if all(c == cmax for c in counts):
         return out
     return torch.cat([out[r * cmax:r * cmax + counts[r]] for r in range(world)], 0)
+
+
+class PipelinedGather:
+    """The same all-gather, taken off the step's critical path: `submit(packed)` copies the step's packed rows
+    into one of two staging buffers on the current stream and starts the collective asynchronously (NCCL runs
+    it on its own stream), so the next step's kernels are enqueued without waiting for it; a staging pair is
+    reused two steps later, after its collective has been waited for.  `result()` waits for the newest
+    collective on the current stream and returns its (global_batch, N, 5+A) tensor.  Equal shards only
+    (global_batch divisible by the world size); anything else falls back to gather_results."""
+
+    def __init__(self, packed_like, global_batch, group=None):
+        self.group, self.global_batch = group, global_batch
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.equal = self.world > 1 and global_batch % self.world == 0
+        if self.equal:
+            b, n, k = packed_like.shape
+            self.stage = [torch.empty_like(packed_like) for _ in range(2)]
+            self.out = [packed_like.new_empty(self.world * b, n, k) for _ in range(2)]
+        self.work = [None, None]
+        self.i = 0
+        self.last = None
+
+    def submit(self, packed):
+        if not self.equal:
+            self.last = (gather_results(packed, self.global_batch, self.group), None)
+            return
+        i = self.i & 1
+        self.i += 1
+        if self.work[i] is not None:
+            self.work[i].wait()  # stream-ordered: the collective that read stage[i] / wrote out[i] two steps ago
+        self.stage[i].copy_(packed)
+        self.work[i] = dist.all_gather_into_tensor(self.out[i], self.stage[i], group=self.group, async_op=True)
+        self.last = (self.out[i], self.work[i])
+
+    def result(self):
+        out, work = self.last
+        if work is not None:
+            work.wait()
+        return out
+
+    def drain(self):
+        for w in self.work:
+            if w is not None:
+                w.wait()

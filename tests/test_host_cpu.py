@@ -160,6 +160,17 @@ def _gloo_worker(rank, world, port, gb, tmp):
         out = gather_results(pack_results(local, full_reward[lo:hi], lo), gb)
         expect = torch.cat([full_rois, full_reward], 2)
         ok = out.shape == expect.shape and torch.equal(out, expect)
+        # the pipelined form (staging copy + asynchronous collective, two steps in flight): step s gathers the
+        # packed rows scaled by s + 1, the staging buffers are reused from step 2 on
+        from rlobjectdetection_b200.shard import PipelinedGather
+        mine = pack_results(local, full_reward[lo:hi], lo)
+        pg = PipelinedGather(mine, gb)
+        for s_ in range(5):
+            pg.submit(mine * float(s_ + 1))
+            if s_ in (0, 3, 4):
+                got = pg.result()
+                ok = ok and got.shape == expect.shape and torch.equal(got, expect * float(s_ + 1))
+        pg.drain()
         open(os.path.join(tmp, f"ok{rank}"), "w").write("1" if ok else "0")
     finally:
         dist.destroy_process_group()
