@@ -127,43 +127,58 @@ __device__ __forceinline__ unsigned long long row_tile_bits(const float4 &a, flo
 // Words of column blocks left of the diagonal are written as zero and never read.
 // ----------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(64)
-    k_nms_mask_rm(NmsSegs segs, float thresh, unsigned long long *__restrict__ mask, size_t mask_seg_stride) {
-  const int seg = blockIdx.z;
-  int off, n;
-  segs.get(seg, off, n);
-  const int nblk = (n + 63) >> 6;
-  const int rb = blockIdx.y, g = blockIdx.x;
-  if (rb >= nblk || g * 4 + 3 < rb || g * 4 >= nblk) return;
-  const int stride = (nblk + 3) & ~3;
+    k_nms_mask_rm(NmsSegs segs, float thresh, unsigned long long *__restrict__ mask, size_t mask_seg_stride,
+                  int max_blk, int nseg) {
+  // persistent grid (24 CTAs per SM) over the (row block, column group) units, unit = blockIdx.x + i * gridDim.x:
+  // 131 -> 111 us at n = 12000 against one CTA per unit (half of those exit at once, the rest share the SMs 32 deep)
   __shared__ float4 cbox[256];
   __shared__ float2 cwh[256];
   const int t = threadIdx.x;
-  for (int q = t; q < 256; q += 64) {
-    const int j = g * 256 + q;
-    float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (j < n) bx = segs.load_box(off + j);
-    cbox[q] = bx;
-    cwh[q] = make_float2(__fadd_rn(__fsub_rn(bx.z, bx.x), 1.f), __fadd_rn(__fsub_rn(bx.w, bx.y), 1.f));
-  }
-  __syncthreads();
-  const int i = rb * 64 + t;
-  unsigned long long bits[4] = {0ull, 0ull, 0ull, 0ull};
-  if (i < n) {
-    const float4 a = segs.load_box(off + i);
-    const float Sa = __fmul_rn(__fadd_rn(__fsub_rn(a.z, a.x), 1.f), __fadd_rn(__fsub_rn(a.w, a.y), 1.f));
-    const bool fast = thresh >= 0.f && thresh < 1e30f;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const int cb = g * 4 + c;
-      if (cb < rb || cb >= nblk) continue;
-      const int jn = min(64, n - cb * 64);
-      const int j0 = (rb == cb) ? t + 1 : 0;
-      bits[c] = row_tile_bits(a, Sa, cbox + c * 64, cwh + c * 64, j0, jn, thresh, fast);
+  const int G = (max_blk + 3) >> 2;
+  // units of one segment, row blocks ascending: row block rb has the column groups rb/4 .. G-1
+  const long long per_seg = 4LL * ((long long)(max_blk >> 2) * G - (long long)(max_blk >> 2) * ((max_blk >> 2) - 1) / 2) +
+                            (long long)(max_blk & 3) * (G - (max_blk >> 2));
+  const long long total = per_seg * nseg;
+  for (long long u = blockIdx.x; u < total; u += gridDim.x) {
+    const int seg = (int)(u / per_seg);
+    long long v = u - (long long)seg * per_seg;
+    // quad q = rb >> 2 holds 4 (G - q) units
+    int q = 0;
+    while (v >= 4LL * (G - q)) v -= 4LL * (G - q), ++q;
+    const int rb = 4 * q + (int)(v / (G - q)), g = q + (int)(v % (G - q));
+    int off, n;
+    segs.get(seg, off, n);
+    const int nblk = (n + 63) >> 6;
+    if (rb >= nblk || g * 4 >= nblk) continue;  // a shorter segment: nothing to compute, nobody waits for it
+    const int stride = (nblk + 3) & ~3;
+    __syncthreads();  // the previous unit's column boxes are no longer read
+    for (int c4 = t; c4 < 256; c4 += 64) {
+      const int j = g * 256 + c4;
+      float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (j < n) bx = segs.load_box(off + j);
+      cbox[c4] = bx;
+      cwh[c4] = make_float2(__fadd_rn(__fsub_rn(bx.z, bx.x), 1.f), __fadd_rn(__fsub_rn(bx.w, bx.y), 1.f));
     }
+    __syncthreads();
+    const int i = rb * 64 + t;
+    unsigned long long bits[4] = {0ull, 0ull, 0ull, 0ull};
+    if (i < n) {
+      const float4 a = segs.load_box(off + i);
+      const float Sa = __fmul_rn(__fadd_rn(__fsub_rn(a.z, a.x), 1.f), __fadd_rn(__fsub_rn(a.w, a.y), 1.f));
+      const bool fast = thresh >= 0.f && thresh < 1e30f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int cb = g * 4 + c;
+        if (cb < rb || cb >= nblk) continue;
+        const int jn = min(64, n - cb * 64);
+        const int j0 = (rb == cb) ? t + 1 : 0;
+        bits[c] = row_tile_bits(a, Sa, cbox + c * 64, cwh + c * 64, j0, jn, thresh, fast);
+      }
+    }
+    ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(mask + (size_t)seg * mask_seg_stride + (size_t)i * stride + g * 4);
+    dst[0] = make_ulonglong2(bits[0], bits[1]);
+    dst[1] = make_ulonglong2(bits[2], bits[3]);
   }
-  ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(mask + (size_t)seg * mask_seg_stride + (size_t)i * stride + g * 4);
-  dst[0] = make_ulonglong2(bits[0], bits[1]);
-  dst[1] = make_ulonglong2(bits[2], bits[3]);
 }
 
 // ----------------------------------------------------------------------------------------
@@ -921,7 +936,11 @@ int nms_launch(const NmsSegs &segs, int nseg, int max_seg, float thresh, int max
   if (max_blk <= kScan3MaxBlk && !scan_v1 && force_large != 2 && nseg <= 65535) {
     // row-major mask (rows of (max_blk rounded up to 4) words; fits the same workspace: 64 max_blk rows) + decoupled scan
     const int g4 = (max_blk + 3) / 4;
-    RLOD_LAUNCH(RLOD_KERNEL_NMS_MASK, st, k_nms_mask_rm<<<dim3(g4, max_blk, nseg), 64, 0, st>>>(segs, thresh, mask, seg_stride));
+    const long long units = (long long)nseg * g4 * max_blk;  // an upper bound of the units (the kernel counts exactly)
+    const long long cap = (long long)kSmCount * 24;
+    const int mask_ctas = (int)(units < cap ? units : cap);
+    RLOD_LAUNCH(RLOD_KERNEL_NMS_MASK, st,
+                k_nms_mask_rm<<<mask_ctas, 64, 0, st>>>(segs, thresh, mask, seg_stride, max_blk, nseg));
     RLOD_LAUNCH(RLOD_KERNEL_NMS_SCAN, st, k_nms_scan3<<<nseg, kScanThreads, (size_t)max_blk * 20 + 4 * (2 + kScan3Near) * 64 * 8 + 16, st>>>(
         segs, max_keep, mask, seg_stride, out));
     return launch_status();

@@ -1,2 +1,2 @@
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
-for i in 1 2; do python bench.py --steps 50 --warmup 5 --no-cpu-baseline 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['roofline']['frac'])"; done
+timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_legacy.py -x -q -m gpu -k "nms or proposal or detect" 2>&1 | tail -2
+timeout 120 python tools/time_proposal.py C1 30
