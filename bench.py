@@ -160,6 +160,14 @@ def workload_config(images_per_gpu, world, arm, global_batch=None):
     }
 
 
+REPOOL_NOTE = {
+    "merged": "the proposals and the refined boxes (which come from the IoU rewards, not from the pooled features) are "
+              "pooled by ONE RoIAlignAvg call on their concatenation: every feature plane is staged once per step and "
+              "the rois are planned once; outputs identical to two calls (other_repool_form times those)",
+    "separate": "two RoIAlignAvg calls per step (proposals, refined boxes)",
+}
+
+
 # ------------------------------------------------------------------------------------------
 # clocks
 # ------------------------------------------------------------------------------------------
@@ -329,9 +337,10 @@ def run_ours(args, rank, local_rank, world):
     host = [t[lo:hi].contiguous().pin_memory() for t in full]
     n_act = 4 * len(ACT_DELTA) * 2
 
-    def new_step(first_image):
+    def new_step(first_image, repool=None):
         return DetectRefineStep(STRIDE, SCALES, RATIOS, "TEST", POOL, ACT_DELTA, backward=False,
-                                outputs=("packed",), first_image=first_image)  # the rows of the gathered result
+                                outputs=("packed",), first_image=first_image,  # the rows of the gathered result
+                                repool=repool or args.repool)
     step = new_step(lo)
 
     def barrier():
@@ -526,6 +535,19 @@ def run_ours(args, rank, local_rank, world):
         del w_in, w_step
         torch.cuda.empty_cache()
 
+    # ---- the other form of the step (two RoIAlign launches instead of one), short leg, N = 1 only ----
+    other_form = None
+    if world == 1 and not graphed:
+        o_name = "separate" if args.repool == "merged" else "merged"
+        o_step = new_step(lo, o_name)
+
+        def o_fn():
+            eager_step(o_step, dev_in, IMAGES, True, dev_in, True)
+        o_steps = max(10, args.steps // 2)
+        ms_o = timed(o_fn, o_steps, 3)
+        other_form = {"repool": o_name, "value": IMAGES * o_steps / (ms_o * 1e-3), "unit": UNIT,
+                      "ms_per_step": ms_o / o_steps, "steps": o_steps}
+        del o_step
     # ---- N > 1: the gathered result of the sharded batch == one rank running the whole batch ----
     multi_ok = None
     if world > 1 and rank == 0:
@@ -537,7 +559,7 @@ def run_ours(args, rank, local_rank, world):
     if rank != 0:
         return
     # ---- roofline of the dominant kernel ---------------------------------------------------
-    R = nb * POST
+    R = nb * POST * (2 if args.repool == "merged" else 1)  # rois per launch: proposals + refined boxes when merged
     alg_bytes = 4 * (nb * C * FH * FW + 5 * R + R * C * POOL * POOL)  # feat once + rois + out once
     peaks, peak_src = {}, "fallback"
     try:
@@ -603,6 +625,7 @@ def run_ours(args, rank, local_rank, world):
         "cpu_baseline": cpu,
         "verified": verified,
         "weak_scaling": weak,
+        "other_repool_form": other_form,
         "ops": ops,
         "kernel_ms_per_step": kernel_ms,
         # one event per step on the caller's stream.  The first step after the synchronise has nothing queued
@@ -618,6 +641,7 @@ def run_ours(args, rank, local_rank, world):
                           "steps.  For the light stream's kernels this is launch-to-finish time, queueing behind the "
                           "RoIAlign launches for a free SM included",
     }
+    line["config"]["repool"] = REPOOL_NOTE[args.repool]
     line["config"]["launch"] = ("one CUDA graph per step and rank (hotpath.GraphedStep, pipelined) + one NCCL all_gather"
                                 if graphed else "eager launches on two streams")
     print(json.dumps(line), flush=True)
@@ -879,6 +903,9 @@ def main():
     ap.add_argument("--no-ops", action="store_true", help="skip the per-config `ops` object of the bench line")
     ap.add_argument("--no-verify", action="store_true", help="skip the oracle check of the timed step")
     ap.add_argument("--eager", action="store_true", help="N > 1: eager launches instead of the CUDA graph")
+    ap.add_argument("--repool", default="merged", choices=["merged", "separate"],
+                    help="merged: the proposals and the refined boxes are pooled by one RoIAlign call (default); "
+                         "separate: two calls")
     ap.add_argument("--ops", action="store_true", help="per-op table vs the reference's legacy CUDA kernels")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
