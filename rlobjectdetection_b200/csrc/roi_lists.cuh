@@ -223,28 +223,30 @@ static __global__ void __launch_bounds__(kOrderThreads)
       else ws.order2[first + i] = id;
     }
   } else {
-    // ordered collection of the rois of image b
-    if (t == 0) s_n = 0;
+    // ordered collection of the rois of image b: every warp takes one contiguous range of roi ids, counts its
+    // matches, and after one prefix over the warps writes them out in order (two passes over the batch indices,
+    // no CTA barrier inside them -- the former chunk-by-chunk collection paid two barriers per 256 rois)
+    const int per_warp = ((R + NW - 1) / NW + 31) & ~31;
+    const int lo = warp * per_warp, hi = min(R, lo + per_warp);
+    int mine = 0;
+    for (int c0 = lo; c0 < hi; c0 += 32) {
+      const int r = c0 + lane;
+      mine += __popc(__ballot_sync(full, r < hi && ws.roi_b[r] == b));
+    }
+    if (lane == 0) s_wc[0][warp] = mine;
     __syncthreads();
-    for (int c0 = 0; c0 < R; c0 += kOrderThreads) {
-      const int r = c0 + t;
-      const int rb = r < R ? ws.roi_b[r] : -1;
-      const unsigned mine = __ballot_sync(full, rb == b);
-      if (lane == 0) s_wc[0][warp] = __popc(mine);
-      __syncthreads();
-      int pre = s_n, tot = 0;
-      for (int w2 = 0; w2 < NW; ++w2) {
-        if (w2 < warp) pre += s_wc[0][w2];
-        tot += s_wc[0][w2];
+    int pos = 0;
+    for (int w2 = 0; w2 < warp; ++w2) pos += s_wc[0][w2];
+    for (int c0 = lo; c0 < hi; c0 += 32) {
+      const int r = c0 + lane;
+      const bool hit = r < hi && ws.roi_b[r] == b;
+      const unsigned m = __ballot_sync(full, hit);
+      if (hit) {
+        const int p = pos + __popc(m & below);
+        if (fits) s_ids[p] = r;
+        else ws.order2[first + p] = r;
       }
-      const int pos = pre + __popc(mine & below);
-      if (rb == b) {
-        if (fits) s_ids[pos] = r;
-        else ws.order2[first + pos] = r;
-      }
-      __syncthreads();
-      if (t == 0) s_n += tot;
-      __syncthreads();
+      pos += __popc(m);
     }
   }
   if (!fits) return;
