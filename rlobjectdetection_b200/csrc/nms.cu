@@ -6,16 +6,23 @@
 // iou = inter / (S - inter) (IEEE division), bit = iou > thresh.
 //
 // What differs is everything around it:
-//   - k_nms_mask computes only the upper-triangular 64x64 tiles, for all segments (images /
-//     (image,class) pairs) in one launch, and stores the mask column-block-major
-//     ([col_block][row]) so both the tile write (512 B) and the scan's reads are coalesced.
-//     A division-free interval test decides all but the razor-edge pairs; those fall through
-//     to the exact IEEE division, so the bits never differ from the reference's.
-//   - k_nms_scan resolves the serial greedy dependency ON THE DEVICE, one CTA per segment:
-//     per 64-box block one thread walks the diagonal tile, then 8 warps OR the kept rows
-//     into the running removed-bitmap with warp-wide OR reductions.  It stops as soon as
-//     max_keep boxes are kept (the proposal layer only uses the first post_nms_topN) and
-//     can emit the padded (B, post, 5) roi tensor directly.
+//   - k_nms_mask_rm computes the upper triangle of the n x n bit mask for all segments (images /
+//     (image, class) pairs) in one launch and stores it ROW-major (a thread writes its four
+//     words of a 64 x 256 unit as one 32-byte sector; a persistent grid walks the units in row
+//     order).  Pairs are classified branch-free by a division-free interval test; only the
+//     razor-edge ones take the exact IEEE division, so the bits never differ from the
+//     reference's.
+//   - k_nms_scan3 resolves the serial greedy dependency ON THE DEVICE, one CTA per segment, as
+//     three decoupled groups of warps: a resolver warp that owns the serial chain (one thread
+//     walks the 64 x 64 diagonal tile, two instructions per box), near warps that apply the
+//     keep bits to speculatively fetched tiles of the next columns, and far warps that own one
+//     column block per thread and OR the kept rows of every earlier row block into a register.
+//     It stops as soon as max_keep boxes are kept (the proposal layer only uses the first
+//     post_nms_topN) and can emit the padded (B, post, 5) roi tensor directly.
+//   - k_nms_mask + k_nms_scan (round 1: column-major tiles, one CTA barrier and one L2 round
+//     trip per 64-box block) remain for segments beyond 57 344 boxes.
+//   - k_nms_lazy: bounded keeps (post_nms_topN <= 512) need no mask at all -- a kept-list walk
+//     on a cluster of 4 CTAs per segment.
 //   - k_nms_small handles short segments (<= 512 boxes, e.g. per-class test-time NMS) in
 //     one CTA each with the mask in shared memory: one launch for thousands of segments.
 // No cudaMalloc, no mask D2H (18 MB per call at n=12000 in the reference), no host loop,

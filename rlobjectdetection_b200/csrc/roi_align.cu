@@ -17,9 +17,11 @@
 //      2x2 pooling fused, each (roi, 4 channels) result leaves as ONE 784-byte bulk async
 //      store (TMA engine).  The feature map is read from HBM exactly once and no 8x8
 //      intermediate tensor exists.
-//   3. backward (k_align8_bwd_walk): the transpose -- gradient planes accumulated in shared
-//      memory under per-row spin locks, grad_out tiles by bulk async load, grad_in written
-//      once, coalesced; no global atomics, no memset.
+//   3. backward: the transpose -- gradient planes accumulated in shared memory, grad_out tiles by
+//      bulk async load, grad_in written once, coalesced; no global atomics, no memset.  The
+//      shipped kernel is k_align8_bwd_own (roi_align_bwd.cu: whole-roi warps, merged taps, a
+//      token ring between the warps of a CTA); k_align8_bwd_walk below (per-row spin locks) is
+//      round 1's kernel, kept behind RLOD_BWD_V1=1 for A/B runs.
 //   Generic kernels (any grid size / channel count / plane size, and RoIAlignMax backward)
 //   cover everything the fast paths do not.
 #include <cstdlib>
