@@ -1411,46 +1411,46 @@ RLOD_API size_t rlod_roi_align_workspace_bytes(int B, int R, int ah, int aw, int
   return carve_align_ws(nullptr, B, R, GH, GW).bytes;
 }
 
-RLOD_API int rlod_roi_align_forward(const float *feat, const float *rois, int B, int C, int H,
-                                    int W, int R, int ah, int aw, float spatial_scale,
-                                    int pool_mode, int channels_last, float *out, void *workspace,
-                                    size_t workspace_bytes, rlod_stream_t stream) {
-  int rc = check_align_args(rois, B, C, H, W, R, ah, aw, pool_mode);
-  if (rc != RLOD_OK) return rc;
-  if (R == 0 || C == 0) return RLOD_OK;
-  if (!feat || !out || !workspace || B < 1) return RLOD_EINVAL;
-  const int GH = pool_mode == RLOD_POOL_NONE ? ah : ah + 1;
-  const int GW = pool_mode == RLOD_POOL_NONE ? aw : aw + 1;
-  AlignWs ws = carve_align_ws(workspace, B, R, GH, GW);
-  if (workspace_bytes < ws.bytes) return RLOD_ENOSPC;
-  cudaStream_t st = (cudaStream_t)stream;
+// The forward in two phases, so that a caller may plan the rois on another stream while the previous pooling is
+// still running (rlod_roi_align_plan + rlod_roi_align_forward_planned); rlod_roi_align_forward is the two in a row.
+// Which kernels run depends on the geometry only (pointer alignment is a precondition of the plane kernel that the
+// planned entry point checks).
+namespace rlod {
 
+static bool align_fwd_geometry_fast(int B, int C, int H, int W, int R, int GH, int GW, int pool_mode) {
   const size_t smem = fwd_walk_smem(H, W, pool_mode) + 16;  // + the fill mbarrier
-  const bool fast = GH == 8 && GW == 8 && (C % 4) == 0 && smem <= (size_t)kMaxSmemPerCta &&
-                    (H + 2) * walk_pitch(W) <= 8192 && ((uintptr_t)out % 16) == 0 && R >= 2 * B;
-  // a channels-last map is only read by the plane kernel (its taps are contiguous float4s there); the
-  // generic kernels index NCHW planes
-  if (channels_last && (!fast || ((uintptr_t)feat % 16) != 0)) return RLOD_EUNSUPPORTED;
+  return GH == 8 && GW == 8 && (C % 4) == 0 && smem <= (size_t)kMaxSmemPerCta && (H + 2) * walk_pitch(W) <= 8192 &&
+         R >= 2 * B;
+}
+
+static int align_fwd_plan(const float *rois, int B, int H, int W, int R, int GH, int GW, float spatial_scale,
+                          bool fast, const AlignWs &ws, cudaStream_t st) {
+  if (!fast) return build_plan(rois, B, H, W, R, GH, GW, spatial_scale, ws, st);
+  // one launch: sample grid + orientation / tap-order search + walk record + roi lists
+  cudaMemsetAsync(ws.flag, 0, 4 * sizeof(int), st);
+  RLOD_LAUNCH(RLOD_KERNEL_ROI_PLAN, st,
+              k_roi_plan8_walk<<<(unsigned)cdiv(R, 4), 128, 0, st>>>(rois, R, B, H, W, walk_pitch(W), spatial_scale, 0, ws));
+  static const bool v1 = getenv("RLOD_FWD_V1") != nullptr;  // A/B switch: the scalar walk of round 1
+  if (v1) {
+    RLOD_LAUNCH(RLOD_KERNEL_ROI_PLAN, st, k_roi_group_fixup<<<1, 32, 0, st>>>(R, B, ws));
+  } else {
+    // group fix-up + partition of every image's list by walk mode (the four rois of a warp then stage alike)
+    // in one launch
+    RLOD_LAUNCH(RLOD_KERNEL_ROI_PLAN, st, k_roi_lists_finish<<<B, kOrderThreads, 0, st>>>(ws.ext, 0, 30, R, B, ws));
+  }
+  return launch_status();
+}
+
+static int align_fwd_run(const float *feat, int B, int C, int H, int W, int R, int ah, int aw, int GH, int GW,
+                         int pool_mode, int channels_last, bool fast, float *out, const AlignWs &ws, cudaStream_t st) {
   if (fast) {
-    static const bool v1_ = getenv("RLOD_FWD_V1") != nullptr;
-    if (channels_last && v1_) return RLOD_EUNSUPPORTED;
+    static const bool v1 = getenv("RLOD_FWD_V1") != nullptr;
+    if (channels_last && v1) return RLOD_EUNSUPPORTED;
+    const size_t smem = fwd_walk_smem(H, W, pool_mode) + 16;
     const int tma_fill = channels_last ? 2 : (fwd_tma_fill_ok(feat, H, W, pool_mode) ? 1 : 0);
     const int n_chunks = C / 4;
     const unsigned grid = (unsigned)(B * n_chunks);
     const int P = walk_pitch(W);
-    // one launch: sample grid + orientation / tap-order search + walk record + roi lists
-    cudaMemsetAsync(ws.flag, 0, 4 * sizeof(int), st);
-    RLOD_LAUNCH(RLOD_KERNEL_ROI_PLAN, st,
-                k_roi_plan8_walk<<<(unsigned)cdiv(R, 4), 128, 0, st>>>(rois, R, B, H, W, P, spatial_scale, 0, ws));
-    static const bool v1 = getenv("RLOD_FWD_V1") != nullptr;  // A/B switch: the scalar walk of round 1
-    if (v1) {
-      RLOD_LAUNCH(RLOD_KERNEL_ROI_PLAN, st, k_roi_group_fixup<<<1, 32, 0, st>>>(R, B, ws));
-    } else {
-      // group fix-up + partition of every image's list by walk mode (the four rois of a warp then stage alike)
-      // in one launch
-      RLOD_LAUNCH(RLOD_KERNEL_ROI_PLAN, st,
-                  k_roi_lists_finish<<<B, kOrderThreads, 0, st>>>(ws.ext, 0, 30, R, B, ws));
-    }
 #define RLOD_LAUNCH_FWD(POOL)                                                                  \
   do {                                                                                         \
     static bool attr_set = false;                                                              \
@@ -1480,8 +1480,6 @@ RLOD_API int rlod_roi_align_forward(const float *feat, const float *rois, int B,
 #undef RLOD_LAUNCH_FWD
     return launch_status();
   }
-  rc = build_plan(rois, B, H, W, R, GH, GW, spatial_scale, ws, st);
-  if (rc) return rc;
   const long long total = (long long)R * C * ah * aw;
   const unsigned grid = (unsigned)(cdiv(total, 256) < (1LL << 30) ? cdiv(total, 256) : (1LL << 30));
   if (pool_mode == RLOD_POOL_NONE)
@@ -1494,6 +1492,64 @@ RLOD_API int rlod_roi_align_forward(const float *feat, const float *rois, int B,
     RLOD_LAUNCH(RLOD_KERNEL_ALIGN_FWD_GENERIC, st, k_align_fwd_generic<RLOD_POOL_MAX>
         <<<grid, 256, 0, st>>>(feat, ws.plan, ws.roi_b, C, H, W, GH, GW, total, out));
   return launch_status();
+}
+
+}  // namespace rlod
+
+RLOD_API int rlod_roi_align_forward(const float *feat, const float *rois, int B, int C, int H,
+                                    int W, int R, int ah, int aw, float spatial_scale,
+                                    int pool_mode, int channels_last, float *out, void *workspace,
+                                    size_t workspace_bytes, rlod_stream_t stream) {
+  int rc = check_align_args(rois, B, C, H, W, R, ah, aw, pool_mode);
+  if (rc != RLOD_OK) return rc;
+  if (R == 0 || C == 0) return RLOD_OK;
+  if (!feat || !out || !workspace || B < 1) return RLOD_EINVAL;
+  const int GH = pool_mode == RLOD_POOL_NONE ? ah : ah + 1;
+  const int GW = pool_mode == RLOD_POOL_NONE ? aw : aw + 1;
+  AlignWs ws = carve_align_ws(workspace, B, R, GH, GW);
+  if (workspace_bytes < ws.bytes) return RLOD_ENOSPC;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool fast = align_fwd_geometry_fast(B, C, H, W, R, GH, GW, pool_mode) && ((uintptr_t)out % 16) == 0;
+  // a channels-last map is only read by the plane kernel (its taps are contiguous float4s there); the
+  // generic kernels index NCHW planes
+  if (channels_last && (!fast || ((uintptr_t)feat % 16) != 0)) return RLOD_EUNSUPPORTED;
+  rc = align_fwd_plan(rois, B, H, W, R, GH, GW, spatial_scale, fast, ws, st);
+  if (rc) return rc;
+  return align_fwd_run(feat, B, C, H, W, R, ah, aw, GH, GW, pool_mode, channels_last, fast, out, ws, st);
+}
+
+RLOD_API int rlod_roi_align_plan(const float *rois, int B, int C, int H, int W, int R, int ah, int aw,
+                                 float spatial_scale, int pool_mode, void *workspace, size_t workspace_bytes,
+                                 rlod_stream_t stream) {
+  int rc = check_align_args(rois, B, C, H, W, R, ah, aw, pool_mode);
+  if (rc != RLOD_OK) return rc;
+  if (R == 0 || C == 0) return RLOD_OK;
+  if (!workspace || B < 1) return RLOD_EINVAL;
+  const int GH = pool_mode == RLOD_POOL_NONE ? ah : ah + 1;
+  const int GW = pool_mode == RLOD_POOL_NONE ? aw : aw + 1;
+  AlignWs ws = carve_align_ws(workspace, B, R, GH, GW);
+  if (workspace_bytes < ws.bytes) return RLOD_ENOSPC;
+  return align_fwd_plan(rois, B, H, W, R, GH, GW, spatial_scale, align_fwd_geometry_fast(B, C, H, W, R, GH, GW, pool_mode),
+                        ws, (cudaStream_t)stream);
+}
+
+RLOD_API int rlod_roi_align_forward_planned(const float *feat, int B, int C, int H, int W, int R, int ah, int aw,
+                                            int pool_mode, int channels_last, float *out, void *workspace,
+                                            size_t workspace_bytes, rlod_stream_t stream) {
+  if (B < 0 || C < 0 || R < 0 || ah < 1 || aw < 1 || H < 2 || W < 2) return RLOD_EINVAL;
+  if (pool_mode < RLOD_POOL_NONE || pool_mode > RLOD_POOL_MAX) return RLOD_EINVAL;
+  if ((long long)B * C * H * W >= (1LL << 31)) return RLOD_EUNSUPPORTED;
+  if (R == 0 || C == 0) return RLOD_OK;
+  if (!feat || !out || !workspace || B < 1) return RLOD_EINVAL;
+  const int GH = pool_mode == RLOD_POOL_NONE ? ah : ah + 1;
+  const int GW = pool_mode == RLOD_POOL_NONE ? aw : aw + 1;
+  AlignWs ws = carve_align_ws(workspace, B, R, GH, GW);
+  if (workspace_bytes < ws.bytes) return RLOD_ENOSPC;
+  const bool fast = align_fwd_geometry_fast(B, C, H, W, R, GH, GW, pool_mode);
+  // the plan in the workspace is the plane kernel's: it needs a 16-byte aligned output (and map, when channels-last)
+  if (fast && ((uintptr_t)out % 16) != 0) return RLOD_EINVAL;
+  if (channels_last && (!fast || ((uintptr_t)feat % 16) != 0)) return RLOD_EUNSUPPORTED;
+  return align_fwd_run(feat, B, C, H, W, R, ah, aw, GH, GW, pool_mode, channels_last, fast, out, ws, (cudaStream_t)stream);
 }
 
 RLOD_API int rlod_roi_align_backward(const float *grad_out, const float *rois, const float *feat,

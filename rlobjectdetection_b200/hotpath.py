@@ -11,6 +11,7 @@ Two forms:
     small (3 images per GPU when BASELINE config 4's batch of 24 is split over 8 GPUs) that
     the ~25 launches of a step cost more host time than the GPU needs to run them."""
 import collections
+import os
 
 import torch
 
@@ -69,6 +70,10 @@ class DetectRefineStep:
         if repool not in ("merged", "separate"):
             raise ValueError("repool must be 'merged' or 'separate'")
         self.repool = repool
+        # RLOD_PLAN_AHEAD=1 plans the rois of the pooling call on the light stream (RoIAlignAvg.plan / forward_planned).
+        # Off by default: measured at C4, N=1 it lengthens the step (0.892 -> 0.941 ms) -- the plan kernels then
+        # compete with the running pooling for SM slots and stretch it by more than their own time
+        self.plan_ahead = os.environ.get("RLOD_PLAN_AHEAD", "0") == "1"
         self.max_ahead = 2
         self._light = {}
         self._inflight = collections.deque()  # (event on the caller's stream, the light stream's tensors)
@@ -92,7 +97,7 @@ class DetectRefineStep:
     def _key(scores, deltas, im_info, gt):
         return tuple((t.data_ptr(), tuple(t.shape), t._version) for t in (scores, deltas, im_info, gt))
 
-    def _light_kernels(self, scores, deltas, im_info, gt, after_rois=None):
+    def _light_kernels(self, scores, deltas, im_info, gt, after_rois=None, feat_size=None):
         """proposal -> NMS -> fused reward / refine / pack on the CURRENT stream: three launches.
         Returns {name: tensor} with rois, refined and the requested outputs."""
         rois = self.proposal((scores, deltas, im_info, self.cfg_key))          # (B, post, 5)
@@ -104,13 +109,21 @@ class DetectRefineStep:
         t["rois"] = rois
         if self.repool == "merged":
             t["both"] = torch.cat([rois.view(-1, 5), t["refined"].view(-1, 5)])   # (2 B N, 5): proposals, then refined
+            if feat_size is not None and self.plan_ahead:
+                # the plan of the one pooling call, here on the light stream: ~45 us of small launches that leave
+                # the GPU mostly idle when they sit between two poolings on the caller's stream
+                t.plan = self.align.plan(t["both"], feat_size)
         return t
 
     def _pool(self, feat, lt, between=None):
         """pooled, pooled_refined for the light stream's roi sets: one RoIAlign call (merged) or two; `between`
         runs after the first launch has been enqueued (the next step's light work goes there)."""
         if self.repool == "merged":
-            both = self.align(feat, lt["both"])
+            plan = getattr(lt, "plan", None)
+            if plan is not None and plan.geometry[:4] == tuple(feat.shape) and not torch.is_grad_enabled():
+                both = self.align.forward_planned(feat, plan)
+            else:
+                both = self.align(feat, lt["both"])
             if between is not None:
                 between()
             n = lt["rois"].numel() // 5
@@ -120,7 +133,7 @@ class DetectRefineStep:
             between()
         return pooled, self.align(feat, lt["refined"].view(-1, 5))
 
-    def _light_work(self, cur, light, scores, deltas, im_info, gt, ready):
+    def _light_work(self, cur, light, scores, deltas, im_info, gt, ready, feat_size=None):
         """The light kernels on the light stream; returns the events the caller's stream has to
         wait for and the (light-stream-owned) tensors."""
         if ready is None:
@@ -134,7 +147,8 @@ class DetectRefineStep:
             light.wait_event(consumed)
         with torch.cuda.stream(light):
             have_rois = torch.cuda.Event()
-            t = self._light_kernels(scores, deltas, im_info, gt, after_rois=lambda: have_rois.record(light))
+            t = self._light_kernels(scores, deltas, im_info, gt, after_rois=lambda: have_rois.record(light),
+                                    feat_size=feat_size)
             have_refined = torch.cuda.Event()
             have_refined.record(light)
         return have_rois, have_refined, t
@@ -165,7 +179,7 @@ class DetectRefineStep:
                 consumed.record(light)
                 self._inflight.append((consumed, cand[2]))
         if rec is None:
-            rec = self._light_work(cur, light, scores, deltas, im_info, gt, inputs_ready)
+            rec = self._light_work(cur, light, scores, deltas, im_info, gt, inputs_ready, tuple(feat.shape))
         have_rois, have_refined, lt = rec
         if next_inputs is not None and next_ready is None:
             raise ValueError("next_inputs need next_ready = True or an event")
@@ -173,7 +187,8 @@ class DetectRefineStep:
         def enqueue_next():
             if next_inputs is not None:
                 ns, nd, ni, ng = next_inputs
-                self._prefetched = (self._key(ns, nd, ni, ng), self._light_work(cur, light, ns, nd, ni, ng, next_ready))
+                self._prefetched = (self._key(ns, nd, ni, ng),
+                                    self._light_work(cur, light, ns, nd, ni, ng, next_ready, tuple(feat.shape)))
 
         if self.repool == "merged":
             cur.wait_event(have_refined)
@@ -275,10 +290,13 @@ class GraphedStep:
         cap.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(cap):
             # eager warm-up: function attributes, cached tables, allocator pools
-            lt = step._light_kernels(scores, deltas, im_info, gt)
+            lt = step._light_kernels(scores, deltas, im_info, gt, feat_size=tuple(feat.shape))
             self._heavy(feat, lt)
             if self.next_inputs is not None:
-                self._hand = {k: v.clone() for k, v in lt.items()}
+                self._hand = be.FusedOutputs((k, v.clone()) for k, v in lt.items())
+                plan = getattr(lt, "plan", None)
+                if plan is not None:  # the hand-over carries the planned rois of the step to pool next
+                    self._hand.plan = be.RoiAlignPlan(plan.ws.clone(), plan.geometry, plan.n_rois, None)
             del lt
         cap.synchronize()
         with torch.cuda.graph(self.graph, stream=cap):
@@ -306,12 +324,14 @@ class GraphedStep:
                 hand = self._hand
                 side.wait_stream(cap)                                    # fork: the NEXT step's light kernels
                 with torch.cuda.stream(side):
-                    nxt = step._light_kernels(ns, nd, ni, ng)
+                    nxt = step._light_kernels(ns, nd, ni, ng, feat_size=tuple(feat.shape))
                 pooled, pooled_refined = self._heavy(feat, hand)
                 out = {n: hand[n].clone() for n in LIGHT_NAMES if n in hand and n in step.outputs}
                 cap.wait_stream(side)                                    # join, then hand over
                 for k in hand:
                     hand[k].copy_(nxt[k])
+                if getattr(hand, "plan", None) is not None:
+                    hand.plan.ws.copy_(nxt.plan.ws)
             out.update(pooled=pooled, pooled_refined=pooled_refined)
             self.out = out
         cap.synchronize()
@@ -323,9 +343,11 @@ class GraphedStep:
             return
         scores, deltas, im_info, feat, gt = self.inputs
         cur = torch.cuda.current_stream(self.device)
-        lt = self.step._light_kernels(scores, deltas, im_info, gt)
+        lt = self.step._light_kernels(scores, deltas, im_info, gt, feat_size=tuple(feat.shape))
         for k in self._hand:
             self._hand[k].copy_(lt[k])
+        if getattr(self._hand, "plan", None) is not None:
+            self._hand.plan.ws.copy_(lt.plan.ws)
         cur.synchronize()
 
     def replay(self):

@@ -41,6 +41,8 @@ SIGNATURES = {
     "rlod_nms_batched": (_I, [_P, _I, _P, _I, _I, _F, _I, _P, _P, _P, _Z, _P]),
     "rlod_roi_align_workspace_bytes": (_Z, [_I, _I, _I, _I, _I]),
     "rlod_roi_align_forward": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _I, _I, _P, _P, _Z, _P]),
+    "rlod_roi_align_plan": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P, _Z, _P]),
+    "rlod_roi_align_forward_planned": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _Z, _P]),
     "rlod_roi_align_backward": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _I, _I, _P, _P,
                                      _Z, _P]),
     "rlod_roi_pool_workspace_bytes": (_Z, [_I, _I]),
@@ -221,6 +223,49 @@ def roi_align_forward(features, rois, ah, aw, scale, pool_mode):
         check(l.rlod_roi_align_forward(ptr(features), ptr(rois), B, C, H, W, R, ah, aw,
                                        float(scale), pool_mode, nhwc, ptr(out), ptr(ws), ws.numel(),
                                        stream_of(features)), "rlod_roi_align_forward")
+    return out
+
+
+class RoiAlignPlan:
+    """The planned rois of one RoIAlign forward call: the workspace rlod_roi_align_plan filled, the geometry it
+    was filled for and the stream it was filled on (roi_align_plan -> roi_align_forward_planned)."""
+
+    def __init__(self, ws, geometry, n_rois, stream):
+        self.ws, self.geometry, self.n_rois, self.stream = ws, geometry, n_rois, stream
+
+
+def roi_align_plan(rois, feature_size, ah, aw, scale, pool_mode):
+    """rlod_roi_align_plan on the current stream.  feature_size = (B, C, H, W) of the map that will be pooled.
+    The returned plan owns its workspace (a fresh allocation: the shared per-device workspace may be rewritten
+    before the planned call runs)."""
+    require_cuda("roi_align_plan", rois)
+    rois = f32c(rois)
+    if rois.dim() != 2 or rois.size(1) != 5:
+        raise ValueError("rois must be (R, 5)")
+    B, C, H, W = (int(v) for v in feature_size)
+    R = rois.size(0)
+    l = lib()
+    with torch.cuda.device(rois.device):
+        ws = torch.empty(max(int(l.rlod_roi_align_workspace_bytes(B, R, ah, aw, pool_mode)), 16), dtype=torch.uint8,
+                         device=rois.device)
+        check(l.rlod_roi_align_plan(ptr(rois), B, C, H, W, R, ah, aw, float(scale), pool_mode, ptr(ws), ws.numel(),
+                                    stream_of(rois)), "rlod_roi_align_plan")
+    return RoiAlignPlan(ws, (B, C, H, W, ah, aw, pool_mode), R, torch.cuda.current_stream(rois.device))
+
+
+def roi_align_forward_planned(features, plan):
+    """rlod_roi_align_forward_planned on the current stream; the caller orders it after the plan (same stream, or
+    an event recorded behind roi_align_plan)."""
+    require_cuda("roi_align", features)
+    features, nhwc = feature_layout(features, "roi_align")
+    B, C, H, W, ah, aw, pool_mode = plan.geometry
+    if tuple(features.shape) != (B, C, H, W):
+        raise ValueError(f"the plan was made for a {(B, C, H, W)} map, not {tuple(features.shape)}")
+    out = torch.empty(plan.n_rois, C, ah, aw, dtype=torch.float32, device=features.device)
+    with torch.cuda.device(features.device):
+        check(lib().rlod_roi_align_forward_planned(ptr(features), B, C, H, W, plan.n_rois, ah, aw, pool_mode, nhwc,
+                                                   ptr(out), ptr(plan.ws), plan.ws.numel(), stream_of(features)),
+              "rlod_roi_align_forward_planned")
     return out
 
 

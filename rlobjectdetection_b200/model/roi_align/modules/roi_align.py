@@ -21,6 +21,17 @@ class _RoIAlignBase(Module):
         return RoIAlignFunction(self.aligned_height, self.aligned_width, self.spatial_scale,
                                 self.pool_mode)(features, rois)
 
+    # Inference-only extension of the reference's interface: the forward in two calls, so that the rois can be
+    # planned early (on another stream) and only the pooling kernel sits on the caller's critical stream.
+    def plan(self, rois, feature_size):
+        """-> a plan of `rois` for a (B, C, H, W) = feature_size map (rlod_roi_align_plan, current stream)."""
+        return be.roi_align_plan(rois, feature_size, self.aligned_height, self.aligned_width, self.spatial_scale,
+                                 self.pool_mode)
+
+    def forward_planned(self, features, plan):
+        """forward(features, the planned rois) without autograd; order it after the plan (same stream or an event)."""
+        return be.roi_align_forward_planned(features, plan)
+
 
 class RoIAlign(_RoIAlignBase):
     pool_mode = be.POOL_NONE

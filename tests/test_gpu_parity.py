@@ -216,6 +216,37 @@ def test_roi_align_images_without_rois_and_empty_input(orc):
     assert tuple(empty.shape) == (0, 8, 7, 7)
 
 
+@pytest.mark.parametrize("case", [
+    dict(B=3, C=12, H=38, W=63, n_per=40, mode=be.POOL_AVG),   # plane kernel
+    dict(B=2, C=6, H=19, W=23, n_per=12, mode=be.POOL_MAX),    # generic kernels (C % 4 != 0)
+    dict(B=2, C=8, H=16, W=16, n_per=9, mode=be.POOL_NONE),    # plane kernel, 8 x 8 output
+])
+def test_roi_align_planned_forward_equals_forward(case):
+    """rlod_roi_align_plan + rlod_roi_align_forward_planned (the plan made on ANOTHER stream, ordered by an event)
+    == rlod_roi_align_forward, bit for bit, for rois grouped by image and for a concatenation of two roi sets."""
+    from rlobjectdetection_b200.model.roi_align.modules.roi_align import RoIAlign, RoIAlignAvg, RoIAlignMax
+    feat, rois = _align_case(21, case["B"], case["C"], case["H"], case["W"], case["n_per"])
+    _, rois2 = _align_case(22, case["B"], case["C"], case["H"], case["W"], case["n_per"])
+    mod = {be.POOL_AVG: RoIAlignAvg, be.POOL_MAX: RoIAlignMax, be.POOL_NONE: RoIAlign}[case["mode"]]
+    p = 8 if case["mode"] == be.POOL_NONE else 7
+    layer = mod(p, p, 1 / 16.0)
+    f = cu(feat)
+    for r in (cu(rois), cu(torch.cat([rois, rois2]))):
+        ref = layer(f, r)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            plan = layer.plan(r, tuple(f.shape))
+            done = torch.cuda.Event()
+            done.record(side)
+        torch.cuda.current_stream().wait_event(done)
+        with torch.no_grad():
+            out = layer.forward_planned(f, plan)
+        assert torch.equal(out, ref)
+    with pytest.raises(ValueError):
+        layer.forward_planned(f[:, :, :-1], plan)
+
+
 def test_roi_align_c2_full_size(orc):
     # config 2: Res-101 C4 at 600x1000 -> (4,1024,38,63), 4 x 256 rois, 7x7
     feat, rois = _align_case(1, 4, 1024, 38, 63, 256)
