@@ -571,7 +571,8 @@ def run_ours(args, rank, local_rank, world):
     traffic = None
     if world == 1:
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("align_fwd_bytes")
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(
+                "align_fwd_merged_bytes" if args.repool == "merged" else "align_fwd_bytes")
         except (OSError, ValueError):
             pass
     roofline = {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None,
