@@ -815,6 +815,39 @@ def test_graphed_step_equals_eager(pipelined):
     for k in keys:
         assert torch.equal(out[k], ref2[k]), k
 
+@pytest.mark.parametrize("graphed", [False, True])
+def test_step_merged_repool_equals_separate(graphed):
+    """repool="merged" (one RoIAlign call pools the proposals and the refined boxes) == repool="separate" (two
+    calls), bit for bit, eager and graphed, with and without the step-ahead light work."""
+    from rlobjectdetection_b200.hotpath import DetectRefineStep
+    B, C, H, W, G = 3, 32, 25, 38, 6
+    outs = ("rois", "reward", "label", "refined", "packed", "moved")
+    mk = lambda form: DetectRefineStep(cfg_key="TEST", backward=False, outputs=outs, first_image=2, repool=form)  # noqa: E731
+    merged, separate = mk("merged"), mk("separate")
+    A = merged.proposal._num_anchors
+    g = torch.Generator().manual_seed(13)
+    feat = cu(torch.randn(B, C, H, W, generator=g))
+    scores, deltas, im_info = (cu(t) for t in syn.rpn_outputs(23, B, A, H, W, H * 16, W * 16))
+    gt = cu(syn.gt_boxes(41, B, G, H * 16, W * 16)[0])
+    keys = outs + ("pooled", "pooled_refined")
+    ref = {k: v.clone() for k, v in separate(scores, deltas, im_info, feat, gt).items()}
+    assert not torch.equal(ref["pooled"], ref["pooled_refined"])
+    if graphed:
+        gs = merged.capture(scores, deltas, im_info, feat, gt, next_inputs=(scores, deltas, im_info, gt))
+        gs.prime()
+        for _ in range(2):
+            out = gs.replay()
+    else:
+        nxt = (scores, deltas, im_info, gt)
+        merged(scores, deltas, im_info, feat, gt, inputs_ready=True, next_inputs=nxt, next_ready=True)
+        out = merged(scores, deltas, im_info, feat, gt, inputs_ready=True, next_inputs=nxt, next_ready=True)
+    torch.cuda.synchronize()
+    for k in keys:
+        assert torch.equal(out[k], ref[k]), k
+    with pytest.raises(ValueError):
+        mk("both")
+
+
 def test_hotpath_step_matches_oracle_chain(orc):
     from rlobjectdetection_b200.hotpath import DetectRefineStep
     B, C, H, W, G = 2, 16, 25, 38, 6
