@@ -126,7 +126,7 @@ class DetectRefineStep:
                 both = self.align(feat, lt["both"])
             if between is not None:
                 between()
-            n = lt["rois"].numel() // 5
+            n = both.size(0) // 2
             return both[:n], both[n:]
         pooled = self.align(feat, lt["rois"].view(-1, 5))
         if between is not None:
@@ -293,7 +293,9 @@ class GraphedStep:
             lt = step._light_kernels(scores, deltas, im_info, gt, feat_size=tuple(feat.shape))
             self._heavy(feat, lt)
             if self.next_inputs is not None:
-                self._hand = be.FusedOutputs((k, v.clone()) for k, v in lt.items())
+                # what the next replay needs of this step's light results: the roi set(s) it pools and the outputs
+                keep = set(step.outputs) | ({"both"} if step.repool == "merged" else {"rois", "refined"})
+                self._hand = be.FusedOutputs((k, v.clone()) for k, v in lt.items() if k in keep)
                 plan = getattr(lt, "plan", None)
                 if plan is not None:  # the hand-over carries the planned rois of the step to pool next
                     self._hand.plan = be.RoiAlignPlan(plan.ws.clone(), plan.geometry, plan.n_rois, None)
