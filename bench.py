@@ -762,6 +762,9 @@ def measure_ops(iters=20, legacy_iters=8):
             leg.ROIPoolBackwardLaucher(dp(gout), 1 / 16.0, B, R, H, W, C, 7, 7, dp(rois), dp(bottom), dp(arg), st())
         lgb = time_us(legacy_pool_bwd, iters=3, warm=1)
     add("RoIPool fwd C2", pb, ours, lg)
+    ours_inf = time_us(lambda: be.roi_pool_forward(feat, rois, 7, 7, 1 / 16.0, want_argmax=False))
+    add("RoIPool fwd C2, inference (no argmax buffer)", 4 * (B * C * H * W + 5 * R + R * C * 49), ours_inf, lg,
+        "legacy = the same ROIPoolForwardLaucher (it always writes argmax)")
     ours = time_us(lambda: be.roi_pool_backward(gout, am, rois, (B, C, H, W), 7, 7, 1 / 16.0))
     add("RoIPool bwd C2", pb, ours, lgb, "legacy = O(B*C*H*W*R) gather")
     # RoICrop (POOLING_MODE 'crop'): 14x14 sampling grid + 2x2 max pool, C2 shape

@@ -71,6 +71,9 @@ __global__ void k_pool_plan(const float *__restrict__ rois, int R, int B, int H,
   roi_list_mark(rois, r, R, B, bvalid ? bi : 0, ws);
 }
 
+// AM = false: the caller passed no argmax buffer (inference: nothing will be back-propagated) -- the scan keeps
+// only the running maximum (one FMNMX per pixel and channel instead of compare + two selects)
+template <bool AM>
 __global__ void __launch_bounds__(kPoolThreads, 2)
     k_roi_pool7_fwd_planes(const float *__restrict__ feat, const int *__restrict__ rec,
                            const int *__restrict__ order, const int *__restrict__ img_off, int C,
@@ -144,11 +147,16 @@ __global__ void __launch_bounds__(kPoolThreads, 2)
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const int pix = rowpix + dw + j;
-            if (v[j].x > mv.x) mv.x = v[j].x, mi.x = pix;
-            if (v[j].y > mv.y) mv.y = v[j].y, mi.y = pix;
-            if (v[j].z > mv.z) mv.z = v[j].z, mi.z = pix;
-            if (v[j].w > mv.w) mv.w = v[j].w, mi.w = pix;
+            if (AM) {
+              const int pix = rowpix + dw + j;
+              if (v[j].x > mv.x) mv.x = v[j].x, mi.x = pix;
+              if (v[j].y > mv.y) mv.y = v[j].y, mi.y = pix;
+              if (v[j].z > mv.z) mv.z = v[j].z, mi.z = pix;
+              if (v[j].w > mv.w) mv.w = v[j].w, mi.w = pix;
+            } else {  // same values: a NaN never wins either form, the -FLT_MAX sentinel never beats a pixel
+              mv.x = fmaxf(mv.x, v[j].x), mv.y = fmaxf(mv.y, v[j].y);
+              mv.z = fmaxf(mv.z, v[j].z), mv.w = fmaxf(mv.w, v[j].w);
+            }
           }
         }
       }
@@ -158,8 +166,10 @@ __global__ void __launch_bounds__(kPoolThreads, 2)
         float *qv = tile_v + ph * 7 + k;
         int *qi = tile_i + ph * 7 + k;
         qv[0] = empty ? 0.f : mv.x, qv[49] = empty ? 0.f : mv.y, qv[98] = empty ? 0.f : mv.z, qv[147] = empty ? 0.f : mv.w;
-        qi[0] = mi.x < 0 ? -1 : chan_base + mi.x, qi[49] = mi.y < 0 ? -1 : chan_base + HW + mi.y;
-        qi[98] = mi.z < 0 ? -1 : chan_base + 2 * HW + mi.z, qi[147] = mi.w < 0 ? -1 : chan_base + 3 * HW + mi.w;
+        if (AM) {
+          qi[0] = mi.x < 0 ? -1 : chan_base + mi.x, qi[49] = mi.y < 0 ? -1 : chan_base + HW + mi.y;
+          qi[98] = mi.z < 0 ? -1 : chan_base + 2 * HW + mi.z, qi[147] = mi.w < 0 ? -1 : chan_base + 3 * HW + mi.w;
+        }
       }
     }
     fence_async_smem();
@@ -168,7 +178,7 @@ __global__ void __launch_bounds__(kPoolThreads, 2)
       if (r >= 0) {
         const size_t o = ((size_t)r * C + (size_t)chunk * 4) * 49;
         bulk_s2g_nocommit(out + o, tile_v, 196 * 4);
-        if (argmax) bulk_s2g_nocommit(argmax + o, tile_i, 196 * 4);
+        if (AM) bulk_s2g_nocommit(argmax + o, tile_i, 196 * 4);
       }
       bulk_commit();
     }
@@ -355,10 +365,17 @@ RLOD_API int rlod_roi_pool_forward(const float *feat, const float *rois, int B, 
     RLOD_LAUNCH(RLOD_KERNEL_ROI_PLAN, st,
                 k_roi_order_by_key<<<B, kOrderThreads, 0, st>>>(ws.plan, ws.order, ws.img_off, 31, 0, 64, ws.order2));
     const int n_chunks = C / 4;
-    cudaFuncSetAttribute(k_roi_pool7_fwd_planes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    RLOD_LAUNCH(RLOD_KERNEL_POOL_FWD, st,
-                k_roi_pool7_fwd_planes<<<(unsigned)(B * n_chunks), kPoolThreads, smem, st>>>(
-                    feat, ws.plan, ws.order2, ws.img_off, C, H, W, P, n_chunks, channels_last, out, argmax));
+    if (argmax) {
+      cudaFuncSetAttribute(k_roi_pool7_fwd_planes<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      RLOD_LAUNCH(RLOD_KERNEL_POOL_FWD, st,
+                  k_roi_pool7_fwd_planes<true><<<(unsigned)(B * n_chunks), kPoolThreads, smem, st>>>(
+                      feat, ws.plan, ws.order2, ws.img_off, C, H, W, P, n_chunks, channels_last, out, argmax));
+    } else {
+      cudaFuncSetAttribute(k_roi_pool7_fwd_planes<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      RLOD_LAUNCH(RLOD_KERNEL_POOL_FWD, st,
+                  k_roi_pool7_fwd_planes<false><<<(unsigned)(B * n_chunks), kPoolThreads, smem, st>>>(
+                      feat, ws.plan, ws.order2, ws.img_off, C, H, W, P, n_chunks, channels_last, out, argmax));
+    }
     return launch_status();
   }
   const long long total = (long long)R * C * ph * pw;

@@ -293,7 +293,9 @@ def roi_align_backward(grad_out, rois, features, feature_size, ah, aw, scale, po
     return grad_in
 
 
-def roi_pool_forward(features, rois, ph, pw, scale):
+def roi_pool_forward(features, rois, ph, pw, scale, want_argmax=True):
+    """-> (out, argmax).  want_argmax=False (inference: nothing will be back-propagated) returns (out, None) and
+    lets the kernel track the maxima only."""
     require_cuda("roi_pool", features, rois)
     _check_rois(features, rois)
     features, nhwc = feature_layout(features, "roi_pool")
@@ -301,7 +303,7 @@ def roi_pool_forward(features, rois, ph, pw, scale):
     B, C, H, W = features.shape
     R = rois.size(0)
     out = torch.empty(R, C, ph, pw, dtype=torch.float32, device=features.device)
-    argmax = torch.empty(R, C, ph, pw, dtype=torch.int32, device=features.device)
+    argmax = torch.empty(R, C, ph, pw, dtype=torch.int32, device=features.device) if want_argmax else None
     l = lib()
     with torch.cuda.device(features.device):
         ws = workspace(l.rlod_roi_pool_workspace_bytes(B, R), features.device)

@@ -35,6 +35,13 @@ class RoIPoolFunction:
             # the reference's CPU branch reads NCHW memory with NHWC indexing (a latent bug,
             # functions/roi_pool.py:20-23); there is deliberately no CPU path here
             raise NotImplementedError
+        import torch
+        if not (torch.is_grad_enabled() and features.requires_grad):
+            # inference (test_net.py runs under volatile / no_grad): no backward will ask for the argmax, so the
+            # kernel tracks maxima only (2x faster); `.argmax` is None then
+            out, self.argmax = be.roi_pool_forward(features, rois, self.pooled_height, self.pooled_width,
+                                                   self.spatial_scale, want_argmax=False)
+            return out
         out, self.argmax = _RoIPoolOp.apply(features, rois, self.pooled_height, self.pooled_width,
                                             self.spatial_scale)
         return out

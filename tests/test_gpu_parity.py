@@ -386,6 +386,13 @@ def test_roi_pool(orc, case):
     out, arg = be.roi_pool_forward(cu(feat), cu(rois), 7, 7, 1 / 16.0)
     assert np.array_equal(out.cpu().numpy(), ro)     # max of fp32 values: bit-exact
     assert np.array_equal(arg.cpu().numpy(), ra)     # flat NCHW argmax, -1 for empty bins
+    # inference form (no argmax buffer: the kernel tracks maxima only): same values; the module picks it under no_grad
+    out_inf, none = be.roi_pool_forward(cu(feat), cu(rois), 7, 7, 1 / 16.0, want_argmax=False)
+    assert none is None and torch.equal(out_inf, out)
+    from rlobjectdetection_b200.model.roi_pooling.modules.roi_pool import _RoIPooling
+    layer = _RoIPooling(7, 7, 1 / 16.0)
+    with torch.no_grad():
+        assert torch.equal(layer(cu(feat), cu(rois)), out)
     g = torch.Generator().manual_seed(13)
     gout = torch.randn(out.shape, generator=g)
     ref = orc.roi_pool_bwd(gout.numpy(), ra, tuple(feat.shape), rois.numpy(), 1 / 16.0)
