@@ -247,6 +247,27 @@ def test_roi_align_planned_forward_equals_forward(case):
         layer.forward_planned(f[:, :, :-1], plan)
 
 
+@pytest.mark.parametrize("grouped", [True, False])
+def test_roi_align_long_roi_lists(orc, grouped):
+    """More rois per image than the list kernels hold in shared memory (2048): the lists are collected but not
+    partitioned by walk mode; grouped by image and as a concatenation of two roi sets; forward and backward."""
+    B, C, H, W, n_per = 2, 8, 24, 31, 1300
+    feat, ra = _align_case(31, B, C, H, W, n_per)
+    _, rb = _align_case(32, B, C, H, W, n_per)
+    if grouped:
+        rois = torch.cat([ra.view(B, n_per, 5), rb.view(B, n_per, 5)], 1).reshape(-1, 5).contiguous()
+    else:
+        rois = torch.cat([ra, rb]).contiguous()
+    ref = orc.roi_align(feat.numpy(), rois.numpy(), 7, 7, 1 / 16.0, pool_mode=orc.POOL_AVG)
+    out = be.roi_align_forward(cu(feat), cu(rois), 7, 7, 1 / 16.0, be.POOL_AVG)
+    close(out.cpu().numpy(), ref, what="long roi lists fwd")
+    g = torch.Generator().manual_seed(5)
+    gout = torch.randn(rois.size(0), C, 7, 7, generator=g)
+    gref = orc.roi_align_bwd(gout.numpy(), feat.numpy(), rois.numpy(), 7, 7, 1 / 16.0, pool_mode=orc.POOL_AVG)
+    gin = be.roi_align_backward(cu(gout), cu(rois), None, tuple(feat.shape), 7, 7, 1 / 16.0, be.POOL_AVG)
+    close(gin.cpu().numpy(), gref, what="long roi lists bwd")
+
+
 def test_roi_align_c2_full_size(orc):
     # config 2: Res-101 C4 at 600x1000 -> (4,1024,38,63), 4 x 256 rois, 7x7
     feat, rois = _align_case(1, 4, 1024, 38, 63, 256)
