@@ -359,6 +359,13 @@ __device__ __forceinline__ unsigned long long resolve_tile(unsigned long long r,
 constexpr int kScan3Near = 3;
 constexpr int kScan3MaxBlk = 32 * (kScanThreads / 32 - 1 - kScan3Near);
 
+// remv[] |= (hi:lo) as two native 32-bit shared-memory ORs (a 64-bit atomicOr in shared memory is a CAS loop)
+__device__ __forceinline__ void or64_shared(unsigned long long *p, unsigned lo, unsigned hi) {
+  unsigned *q = reinterpret_cast<unsigned *>(p);
+  if (lo) atomicOr(q, lo);
+  if (hi) atomicOr(q + 1, hi);
+}
+
 __device__ __forceinline__ int ld_volatile_s32(const int *p) {
   int v;
   asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
@@ -508,7 +515,7 @@ __global__ void __launch_bounds__(kScanThreads, 1)
       if (!last) {
         const u64 v = (k0 ? nt[lane] : 0ull) | (k1 ? nt[lane + 32] : 0ull);
         const unsigned lo = __reduce_or_sync(full, (unsigned)v), hi = __reduce_or_sync(full, (unsigned)(v >> 32));
-        if (lane == 0 && k + d < nblk && (lo | hi)) atomicOr(&remv[k + d], ((u64)hi << 32) | lo);
+        if (lane == 0 && k + d < nblk && (lo | hi)) or64_shared(&remv[k + d], lo, hi);
         __threadfence_block();
         // the resolver waits for this at its step k+2
         if (k + 2 < nblk) asm volatile("bar.arrive %0, %1;" ::"r"(1 + (k & 1)), "n"(32 * (1 + ND)) : "memory");
@@ -548,7 +555,7 @@ __global__ void __launch_bounds__(kScanThreads, 1)
     // a part is handed over as soon as its last row block is in (the resolver waits for NP parts per column)
     auto close_if_done = [&](int next_j) {
       if (open && next_j > last_j) {
-        if (r) atomicOr(&remv[w], r);
+        if (r) or64_shared(&remv[w], (unsigned)r, (unsigned)(r >> 32));
         __threadfence_block();
         atomicAdd(far_done + w, 1);
         open = false;
