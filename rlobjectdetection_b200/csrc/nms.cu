@@ -573,10 +573,10 @@ __global__ void __launch_bounds__(kScanThreads, 1)
       u64 kb = *reinterpret_cast<volatile u64 *>(kept + j);
       if (j <= last_j) {
         const u64 *row = col + (size_t)j * 64 * stride;
-        while (kb) {  // 8 loads in flight
-          u64 v[8];
+        while (kb) {  // 16 loads in flight
+          u64 v[16];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
+          for (int e = 0; e < 16; ++e) {
             v[e] = 0ull;
             if (kb) {
               const int i = __ffsll((long long)kb) - 1;
@@ -584,7 +584,8 @@ __global__ void __launch_bounds__(kScanThreads, 1)
               v[e] = row[(size_t)i * stride];
             }
           }
-          r |= ((v[0] | v[1]) | (v[2] | v[3])) | ((v[4] | v[5]) | (v[6] | v[7]));
+#pragma unroll
+          for (int e = 0; e < 16; ++e) r |= v[e];
         }
       }
       close_if_done(j + NP);
