@@ -15,7 +15,10 @@
 //   rlod_roi_crop_backward :120-199: gradient w.r.t. the feature map (the reference computes no
 //                         grid gradient: its dot products are never stored).  One RED per tap.
 // (grid.y = C / 32 must stay below 65536: C < 2^21.)
-// Every fp32 operation rounds separately, in the reference's order.
+// Every fp32 operation rounds separately, in the reference's order (the plane-resident forward contracts the tap sum
+// into FMAs, as nvcc does for the reference's kernel: see k_roi_crop_planes).
+#include <cstdlib>
+
 #include "rlod_common.cuh"
 
 namespace rlod {
@@ -299,6 +302,110 @@ static unsigned crop_grid(long long total) {
   return (unsigned)(blocks < (1LL << 22) ? blocks : (1LL << 22));
 }
 
+// ----------------------------------------------------------------------------------------
+// forward, plane-resident (round 2, second session): the RoIAlign forward's structure for the crop sampler.
+// CTA = (image, 4 G channels), G = 1 or 2: the planes are staged in shared memory once, interleaved per pixel in
+// groups of four (one LDS.128 = a tap of 4 channels), with a ZERO FRAME so that a tap outside the map needs no
+// mask: padded pixel (y, x), y in [-1, H + 1], x in [-1, W - 1], sits at (y + 1) * P + (x + 1) with P = W + 1 --
+// the pixel right of column W - 1 is the next row's (zero) left border.  A warp owns a contiguous range of the
+// image's rois and walks their sample points as ONE flat list, 32 per iteration (no ragged last iteration per
+// roi: 196 points are 6.125 warps), so the grid is read as one contiguous stream (8 bytes per point, shared by
+// the image's CTAs through L2) and consecutive lanes store consecutive floats of an output plane.  A sample
+// whose four taps all lie outside the map reads the zero rows below it.  The coordinate arithmetic of a point
+// is done once for 4 G channels; the taps are summed in the reference's order, two channels per packed
+// instruction: v = w00 a; v = fma(w01, b, v); v = fma(w10, c, v); v = fma(w11, d, v) -- the contraction nvcc
+// applies to the reference's own expression (roi_crop_cuda_kernel.cu:103-106); ptxas 12.9 contracts
+// mul.rn.f32x2 + add.rn.f32x2 into FFMA2 regardless, so it is written out.  Against the gather kernel above
+// (separate roundings) the results differ in the last bit; both sit within 1e-5 of the reference.
+// Any grid is accepted (no separability assumed).  The gather kernel remains for C % 4 != 0, R % B != 0 and maps
+// beyond shared memory.
+// ----------------------------------------------------------------------------------------
+constexpr int kCropPlWarps = 16;
+constexpr int kCropPlThreads = kCropPlWarps * 32;
+
+__device__ __forceinline__ unsigned long long crop_pack2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ unsigned long long crop_mul2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long crop_fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
+template <int G>
+__global__ void __launch_bounds__(kCropPlThreads, 2)
+    k_roi_crop_planes(const float *__restrict__ feat, const float *__restrict__ grid, int C, int H, int W,
+                      int ghw, int rpi, int n_chunks, float *__restrict__ out) {
+  extern __shared__ __align__(128) unsigned char crop_raw[];
+  float4 *planes4 = reinterpret_cast<float4 *>(crop_raw);  // [G][(H + 3) * P]
+  const int P = W + 1, HW = H * W;
+  const int n_pad = (H + 3) * P;
+  const int b = blockIdx.x / n_chunks, chunk = blockIdx.x - b * n_chunks;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < G * n_pad; i += kCropPlThreads) planes4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+#pragma unroll
+  for (int g = 0; g < G; ++g)
+    fill_planes4_async<kCropPlThreads>(planes4 + g * n_pad + P + 1,
+                                       feat + ((size_t)b * C + (size_t)chunk * 4 * G + 4 * g) * HW, H, W, P, HW);
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  const uint32_t pbase = smem_u32(planes4);
+  const uint32_t zero_tl = (uint32_t)((H + 1) * P) * 16u;  // a 2 x 2 block of zero pixels below the map
+  const uint32_t gstride = (uint32_t)n_pad * 16u, rowb = (uint32_t)P * 16u;
+  const int r_lo = (int)((long long)rpi * warp / kCropPlWarps), r_hi = (int)((long long)rpi * (warp + 1) / kCropPlWarps);
+  const long long nq = (long long)(r_hi - r_lo) * ghw;
+  const float2 *gp = reinterpret_cast<const float2 *>(grid) + ((size_t)b * rpi + r_lo) * ghw;
+  float *ob = out + (((size_t)b * rpi + r_lo) * C + (size_t)chunk * 4 * G) * ghw;
+  const size_t roi_stride = (size_t)C * ghw;
+  int p = lane;
+  float *orow = ob;
+  while (p >= ghw) p -= ghw, orow += roi_stride;
+#pragma unroll 2
+  for (long long q = lane; q < nq; q += 32) {
+    const float2 yx = __ldg(gp + q);
+    int x0, y0;
+    float xw, yw;
+    crop_top_left(yx.y, W, x0, xw);
+    crop_top_left(yx.x, H, y0, yw);
+    const bool any = x0 >= -1 && x0 <= W - 1 && y0 >= -1 && y0 <= H - 1;
+    const uint32_t tl = pbase + (any ? (uint32_t)((y0 + 1) * P + (x0 + 1)) * 16u : zero_tl);
+    const float ixw = __fsub_rn(1.f, xw), iyw = __fsub_rn(1.f, yw);
+    const float w00 = __fmul_rn(xw, yw), w01 = __fmul_rn(ixw, yw), w10 = __fmul_rn(xw, iyw), w11 = __fmul_rn(ixw, iyw);
+    const unsigned long long q00 = crop_pack2(w00, w00), q01 = crop_pack2(w01, w01);
+    const unsigned long long q10 = crop_pack2(w10, w10), q11 = crop_pack2(w11, w11);
+    float *o = orow + p;
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const uint32_t t = tl + (uint32_t)g * gstride;
+      unsigned long long a0, a1, b0, b1, c0, c1, d0, d1;
+      asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a0), "=l"(a1) : "r"(t));
+      asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(b0), "=l"(b1) : "r"(t + 16u));
+      asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(c0), "=l"(c1) : "r"(t + rowb));
+      asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(d0), "=l"(d1) : "r"(t + rowb + 16u));
+      unsigned long long v0 = crop_mul2(q00, a0), v1 = crop_mul2(q00, a1);
+      v0 = crop_fma2(q01, b0, v0), v1 = crop_fma2(q01, b1, v1);
+      v0 = crop_fma2(q10, c0, v0), v1 = crop_fma2(q10, c1, v1);
+      v0 = crop_fma2(q11, d0, v0), v1 = crop_fma2(q11, d1, v1);
+      float2 lo, hi;
+      asm("mov.b64 {%0, %1}, %2;" : "=f"(lo.x), "=f"(lo.y) : "l"(v0));
+      asm("mov.b64 {%0, %1}, %2;" : "=f"(hi.x), "=f"(hi.y) : "l"(v1));
+      float *og = o + (size_t)(4 * g) * ghw;
+      __stcs(og, lo.x), __stcs(og + ghw, lo.y), __stcs(og + 2 * (size_t)ghw, hi.x), __stcs(og + 3 * (size_t)ghw, hi.y);
+    }
+    p += 32;
+    while (p >= ghw) p -= ghw, orow += roi_stride;
+  }
+}
+
 }  // namespace rlod
 
 using namespace rlod;
@@ -322,6 +429,36 @@ RLOD_API int rlod_roi_crop_forward(const float *feat, const float *grid_yx, int 
   if (!feat || !grid_yx || !out) return RLOD_EINVAL;
   if (R < B) return RLOD_EINVAL;  // roiPerImage = R / B = 0 divides by zero in the reference
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    // plane kernel: every image has the same number of rois and the zero-framed planes of 4 (G = 1) or 8 (G = 2)
+    // channels fit one CTA's shared memory; G = 2 where two CTAs of it still share an SM
+    const int ghw = gh * gw;
+    const size_t plane = (size_t)(H + 3) * (W + 1) * 16;
+    static const bool crop_v1 = getenv("RLOD_CROP_V1") != nullptr;  // A/B switch: the gather kernel
+    static const int force_g = getenv("RLOD_CROP_G") ? atoi(getenv("RLOD_CROP_G")) : 0;
+    if (!crop_v1 && (C % 4) == 0 && (R % B) == 0 && plane <= (size_t)kMaxSmemPerCta && (long long)B * (C / 4) < (1LL << 31) &&
+        ((uintptr_t)grid_yx % 8) == 0) {
+      int G = ((C % 8) == 0 && 2 * plane <= (size_t)kMaxSmemPerCta / 2) ? 2 : 1;
+      if (force_g == 1 || (force_g == 2 && (C % 8) == 0 && 2 * plane <= (size_t)kMaxSmemPerCta)) G = force_g;
+      static bool attr_set = false;
+      if (!attr_set) {
+        cudaFuncSetAttribute(k_roi_crop_planes<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemPerCta);
+        cudaFuncSetAttribute(k_roi_crop_planes<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemPerCta);
+        attr_set = true;
+      }
+      const int n_chunks = C / (4 * G);
+      if (G == 2) {
+        RLOD_LAUNCH(RLOD_KERNEL_CROP, st,
+                    k_roi_crop_planes<2><<<(unsigned)(B * n_chunks), kCropPlThreads, 2 * plane, st>>>(
+                        feat, grid_yx, C, H, W, ghw, R / B, n_chunks, out));
+      } else {
+        RLOD_LAUNCH(RLOD_KERNEL_CROP, st,
+                    k_roi_crop_planes<1><<<(unsigned)(B * n_chunks), kCropPlThreads, plane, st>>>(
+                        feat, grid_yx, C, H, W, ghw, R / B, n_chunks, out));
+      }
+      return launch_status();
+    }
+  }
   RLOD_LAUNCH(RLOD_KERNEL_CROP, st,
               k_roi_crop<false><<<dim3((unsigned)R, (unsigned)((C + kCropChunk - 1) / kCropChunk)), kCropThreads, 0, st>>>(
                   feat, grid_yx, B, C, H, W, R, gh, gw, R / B, out));

@@ -1114,6 +1114,51 @@ def test_roi_crop_backward_general_grids(orc):
     close(acc.cpu().numpy(), base.numpy() + gin, what="roi_crop bwd accumulate")
 
 
+def test_roi_crop_forward_plane_kernel_general_grids(orc):
+    """C % 4 == 0, equal rois per image and gh * gw % 4 == 0 take the plane-resident forward (k_roi_crop_planes):
+    zero-framed planes instead of per-tap masks.  Mirrored, far-outside, corner-straddling, non-separable and
+    exactly-on-the-border grids must equal the oracle's masked taps (within 1e-5: the plane kernel sums the taps
+    with FMAs, as the reference's own CUDA build does; exact zeros where no tap is inside)."""
+    B, C, H, W, n_per, gs = 2, 40, 20, 31, 12, 14
+    feat, rois = _crop_case(31, B, C, H, W, n_per, gs)
+    rois = rois.clone()
+    rois[1, [1, 3]] = rois[1, [3, 1]]
+    rois[2, [2, 4]] = rois[2, [4, 2]]
+    rois[3, 1:5] = torch.tensor([-300.0, -200.0, -120.0, -90.0])
+    rois[4, 1:5] = torch.tensor([-40.0, -30.0, 60.0, 50.0])
+    rois[5, 1:5] = torch.tensor([W * 16.0 - 50, H * 16.0 - 40, W * 16.0 + 80, H * 16.0 + 90])
+    rois[8, 1:5] = torch.tensor([0.0, 0.0, W * 16.0, H * 16.0])    # the whole map: samples on both borders
+    grid_xy = orc.affine_grid(rois.numpy(), H, W, gs, True)
+    grid_yx = np.ascontiguousarray(np.stack([grid_xy[..., 1], grid_xy[..., 0]], 3)).astype(np.float32)
+    rng = np.random.default_rng(4)
+    grid_yx[6] += rng.normal(0, 0.02, grid_yx[6].shape).astype(np.float32)
+    grid_yx[9, 0, 0] = (-1.0, -1.0)                                # exactly the first pixel
+    grid_yx[9, 0, 1] = (1.0, 1.0)                                  # exactly the last pixel
+    grid_yx[9, 0, 2] = (1e30, -1e30)                               # saturating coordinates
+    grid_yx[9, 0, 3] = (np.nextafter(np.float32(-1.0), np.float32(-2.0)), 0.0)   # one ulp above the map
+    out = be.roi_crop_forward(cu(feat), cu(grid_yx)).cpu().numpy()
+    ref = orc.roi_crop(feat.numpy(), grid_yx)
+    close(out, ref, what="roi_crop fwd planes")
+    assert not out[3].any() and not out[9, :, 0, 2].any()          # no tap inside: exact zeros
+    np.testing.assert_array_equal(out[9, :, 0, 0], feat[0, :, 0, 0].numpy())      # weight 1 on one pixel: exact
+    np.testing.assert_array_equal(out[9, :, 0, 1], feat[0, :, H - 1, W - 1].numpy())
+    # the same call with an odd channel count takes the gather kernel, 36 channels the 4-channel planes
+    out39 = be.roi_crop_forward(cu(feat[:, :39].contiguous()), cu(grid_yx)).cpu().numpy()
+    close(out39, ref[:, :39], what="roi_crop fwd gather")
+    out36 = be.roi_crop_forward(cu(feat[:, :36].contiguous()), cu(grid_yx)).cpu().numpy()
+    np.testing.assert_array_equal(out36, out[:, :36])               # G = 1 and G = 2: the same arithmetic
+    # fewer rois per image than warps, and a single image
+    feat1, rois1 = _crop_case(32, 1, 4, 9, 11, 3, 6)
+    g1 = orc.affine_grid(rois1.numpy(), 9, 11, 6, True)
+    g1 = np.ascontiguousarray(np.stack([g1[..., 1], g1[..., 0]], 3)).astype(np.float32)
+    close(be.roi_crop_forward(cu(feat1), cu(g1)).cpu().numpy(), orc.roi_crop(feat1.numpy(), g1), what="roi_crop fwd small")
+    # more rois than warps with a point count that is no multiple of 32 nor of 4 (5 x 5), rois split unevenly over warps
+    feat2, rois2 = _crop_case(33, 2, 8, 12, 17, 21, 5)
+    g2 = orc.affine_grid(rois2.numpy(), 12, 17, 5, True)
+    g2 = np.ascontiguousarray(np.stack([g2[..., 1], g2[..., 0]], 3)).astype(np.float32)
+    close(be.roi_crop_forward(cu(feat2), cu(g2)).cpu().numpy(), orc.roi_crop(feat2.numpy(), g2), what="roi_crop fwd 5x5")
+
+
 def test_roi_crop_module_and_crop_pool(orc):
     from rlobjectdetection_b200.model.roi_crop.modules.roi_crop import _RoICrop
     from rlobjectdetection_b200.model.utils.net_utils import crop_pool

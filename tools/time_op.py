@@ -21,7 +21,13 @@ gout = torch.randn(rois.size(0), C, 7, 7, generator=g).to(dev)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 if op == "pool_bwd":
     _, am = be.roi_pool_forward(feat, rois, 7, 7, 1 / 16.0)
+if op.startswith("crop"):
+    grid = be.affine_grid(rois, (H, W), 14)
+    gyx = torch.stack([grid[..., 1], grid[..., 0]], 3).contiguous()
+    gout14 = torch.randn(rois.size(0), C, 14, 14, generator=g).to(dev)
 fns = {
+    "crop_fwd": lambda: be.roi_crop_forward(feat, gyx),
+    "crop_bwd": lambda: be.roi_crop_backward(gout14, gyx, (B, C, H, W)),
     "align_fwd": lambda: be.roi_align_forward(feat, rois, 7, 7, 1 / 16.0, be.POOL_AVG),
     "align_bwd": lambda: be.roi_align_backward(gout, rois, None, (B, C, H, W), 7, 7, 1 / 16.0, be.POOL_AVG),
     "pool_fwd": lambda: be.roi_pool_forward(feat, rois, 7, 7, 1 / 16.0),
