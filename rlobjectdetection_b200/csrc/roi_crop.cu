@@ -24,7 +24,9 @@
 namespace rlod {
 
 __device__ __forceinline__ void crop_top_left(float x, int width, int &point, float &weight) {
-  const float xcoord = __fdiv_rn(__fmul_rn(__fadd_rn(x, 1.f), (float)(width - 1)), 2.f);
+  // (x + 1) * (width - 1) / 2: halving is exact in binary floating point (the correctly rounded value of the same
+  // real number), so the multiplication by 0.5 replaces the division sequence (FCHK + Newton step + slow-path call)
+  const float xcoord = __fmul_rn(__fmul_rn(__fadd_rn(x, 1.f), (float)(width - 1)), 0.5f);
   const float fl = floorf(xcoord);
   point = (int)fl;
   weight = __fsub_rn(1.f, __fsub_rn(xcoord, fl));
@@ -339,10 +341,13 @@ __device__ __forceinline__ unsigned long long crop_fma2(unsigned long long a, un
   return r;
 }
 
-template <int G>
+// GHW = 196: the 14 x 14 grid of crop_pool (POOLING_SIZE * 2) as a compile-time constant -- the eight output planes
+// of a point are then immediate offsets from one address; GHW = 0: any grid
+template <int G, int GHW>
 __global__ void __launch_bounds__(kCropPlThreads, 2)
     k_roi_crop_planes(const float *__restrict__ feat, const float *__restrict__ grid, int C, int H, int W,
-                      int ghw, int rpi, int n_chunks, float *__restrict__ out) {
+                      int ghw_arg, int rpi, int n_chunks, float *__restrict__ out) {
+  const int ghw = GHW ? GHW : ghw_arg;
   extern __shared__ __align__(128) unsigned char crop_raw[];
   float4 *planes4 = reinterpret_cast<float4 *>(crop_raw);  // [G][(H + 3) * P]
   const int P = W + 1, HW = H * W;
@@ -369,9 +374,13 @@ __global__ void __launch_bounds__(kCropPlThreads, 2)
   int p = lane;
   float *orow = ob;
   while (p >= ghw) p -= ghw, orow += roi_stride;
+  // the grid point of the NEXT iteration is fetched one iteration ahead: everything below depends on it, and an L2
+  // round trip per iteration left the warps waiting on it (long-scoreboard stall 7.9 per issue before)
+  float2 yx_next = lane < nq ? __ldg(gp + lane) : make_float2(0.f, 0.f);
 #pragma unroll 2
   for (long long q = lane; q < nq; q += 32) {
-    const float2 yx = __ldg(gp + q);
+    const float2 yx = yx_next;
+    if (q + 32 < nq) yx_next = __ldg(gp + q + 32);
     int x0, y0;
     float xw, yw;
     crop_top_left(yx.y, W, x0, xw);
@@ -442,20 +451,24 @@ RLOD_API int rlod_roi_crop_forward(const float *feat, const float *grid_yx, int 
       if (force_g == 1 || (force_g == 2 && (C % 8) == 0 && 2 * plane <= (size_t)kMaxSmemPerCta)) G = force_g;
       static bool attr_set = false;
       if (!attr_set) {
-        cudaFuncSetAttribute(k_roi_crop_planes<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemPerCta);
-        cudaFuncSetAttribute(k_roi_crop_planes<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemPerCta);
+        cudaFuncSetAttribute(k_roi_crop_planes<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemPerCta);
+        cudaFuncSetAttribute(k_roi_crop_planes<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemPerCta);
+        cudaFuncSetAttribute(k_roi_crop_planes<1, 196>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemPerCta);
+        cudaFuncSetAttribute(k_roi_crop_planes<2, 196>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemPerCta);
         attr_set = true;
       }
       const int n_chunks = C / (4 * G);
-      if (G == 2) {
-        RLOD_LAUNCH(RLOD_KERNEL_CROP, st,
-                    k_roi_crop_planes<2><<<(unsigned)(B * n_chunks), kCropPlThreads, 2 * plane, st>>>(
-                        feat, grid_yx, C, H, W, ghw, R / B, n_chunks, out));
-      } else {
-        RLOD_LAUNCH(RLOD_KERNEL_CROP, st,
-                    k_roi_crop_planes<1><<<(unsigned)(B * n_chunks), kCropPlThreads, plane, st>>>(
-                        feat, grid_yx, C, H, W, ghw, R / B, n_chunks, out));
-      }
+      static const bool any_ghw = getenv("RLOD_CROP_GHW0") != nullptr;  // A/B switch: the run-time grid size
+      const bool g196 = ghw == 196 && !any_ghw;
+#define RLOD_CROP_PLANES(GG, HW_)                                                                              \
+  RLOD_LAUNCH(RLOD_KERNEL_CROP, st,                                                                            \
+              k_roi_crop_planes<GG, HW_><<<(unsigned)(B * n_chunks), kCropPlThreads, GG * plane, st>>>(        \
+                  feat, grid_yx, C, H, W, ghw, R / B, n_chunks, out))
+      if (G == 2 && g196) RLOD_CROP_PLANES(2, 196);
+      else if (G == 2) RLOD_CROP_PLANES(2, 0);
+      else if (g196) RLOD_CROP_PLANES(1, 196);
+      else RLOD_CROP_PLANES(1, 0);
+#undef RLOD_CROP_PLANES
       return launch_status();
     }
   }
