@@ -37,6 +37,27 @@ class ProfScope {
   } while (0)
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+// ---- programmatic dependent launch (griddepcontrol) -------------------------------------
+// A kernel launched through launch_after() with overlap = true may start while the kernel before it
+// on the stream is still running, as soon as every CTA of that kernel has called pdl_trigger() (or
+// exited); what it reads of the earlier kernel's results it reads after pdl_wait(), which returns
+// once the earlier kernel has finished and its writes are visible.  Without the launch attribute
+// both instructions do nothing, so kernels that carry them can be launched either way.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_after(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                       cudaStream_t st, bool overlap, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at, cfg.numAttrs = overlap ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 
 static inline long long cdiv(long long a, long long b) { return (a + b - 1) / b; }
 

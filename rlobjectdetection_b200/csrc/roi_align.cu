@@ -309,6 +309,7 @@ __device__ __forceinline__ int tap_order_natural(const int *L, const int *R, int
 __global__ void __launch_bounds__(128, 6)
     k_roi_plan8_walk(const float *__restrict__ rois, int R, int B, int H, int W, int P, float scale,
                      int bwd, AlignWs ws) {
+  pdl_trigger();  // k_roi_lists_finish may be set up behind this grid (it waits for our results itself)
   const int r = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (r >= R) return;
   int *e = ws.ext + (size_t)r * 32;
@@ -816,7 +817,8 @@ template <int POOL>
 __global__ void __launch_bounds__(kWalkThreads, 2)
     k_align8_fwd_walk2(const float *__restrict__ feat, const int *__restrict__ ext,
                        const int *__restrict__ order, const int *__restrict__ img_off, int C,
-                       int H, int W, int P, int n_chunks, int tma_fill, float *__restrict__ out) {
+                       int H, int W, int P, int n_chunks, int tma_fill, int split_from, int split,
+                       float *__restrict__ out) {
   constexpr int OW = POOL == RLOD_POOL_NONE ? 8 : 7;
   constexpr int OHW = OW * OW;                            // 64 | 49
   constexpr int STG = 4 * OHW;                            // floats per (roi, 4 channels)
@@ -827,9 +829,20 @@ __global__ void __launch_bounds__(kWalkThreads, 2)
   const int HW = H * W;
   float *stage = reinterpret_cast<float *>(planes4 + (H + 2) * P);
 
-  const int b = blockIdx.x / n_chunks, chunk = blockIdx.x - b * n_chunks;
-  const int r0 = img_off[b], r1 = img_off[b + 1];
-  if (r0 >= r1) return;
+  // CTA = (image, 4 channels) for the first split_from blocks (whole waves of the grid); the items of the
+  // last, partial wave are served by `split` CTAs each, every one with its own copy of the planes and a
+  // contiguous share of the image's roi groups, so that the tail of the launch fills the SMs it would
+  // leave idle (align_fwd_run picks split)
+  unsigned item = blockIdx.x, part = 0, parts = 1;
+  if ((int)blockIdx.x >= split_from) {
+    const unsigned t = blockIdx.x - (unsigned)split_from;
+    item = (unsigned)split_from + t / (unsigned)split, part = t % (unsigned)split, parts = (unsigned)split;
+  }
+  const int b = (int)item / n_chunks, chunk = (int)item - b * n_chunks;
+  // The fill below reads the feature map only: it may run while the roi plan (k_roi_plan8_walk +
+  // k_roi_lists_finish, launched just before on the stream) is still being written -- pdl_wait()
+  // after the fill is where this grid meets the plan (rlod_roi_align_forward launches it as a
+  // programmatic dependent of the list kernel).
   const float *src = feat + ((size_t)b * C + (size_t)chunk * 4) * HW;
   uint64_t *fill_bar = reinterpret_cast<uint64_t *>(stage + kWalkWarps * 2 * 4 * SLOT);
   // ---- fill (see k_align8_fwd_walk): bulk copies land the planes planar, threads interleave ----
@@ -867,7 +880,7 @@ __global__ void __launch_bounds__(kWalkThreads, 2)
     // next planes of this SM slot into L2 while the copies are in flight
     {
       const unsigned nb2 = blockIdx.x + 2u * (unsigned)kSmCount;
-      if (nb2 < gridDim.x) {
+      if (nb2 < (unsigned)split_from) {
         const unsigned b2 = nb2 / (unsigned)n_chunks, c2 = nb2 - b2 * (unsigned)n_chunks;
         const char *nx = reinterpret_cast<const char *>(feat + ((size_t)b2 * C + (size_t)c2 * 4) * HW);
         for (int i = threadIdx.x * 128; i < 4 * HW * 4; i += kWalkThreads * 128)
@@ -902,7 +915,7 @@ __global__ void __launch_bounds__(kWalkThreads, 2)
   } else {
     fill_planes4_async<kWalkThreads>(planes4, src, H, W, P, HW);
     const unsigned nb2 = blockIdx.x + 2u * (unsigned)kSmCount;
-    if (nb2 < gridDim.x) {
+    if (nb2 < (unsigned)split_from) {
       const unsigned b2 = nb2 / (unsigned)n_chunks, c2 = nb2 - b2 * (unsigned)n_chunks;
       const char *nx = reinterpret_cast<const char *>(feat + ((size_t)b2 * C + (size_t)c2 * 4) * HW);
       for (int i = threadIdx.x * 128; i < 4 * HW * 4; i += kWalkThreads * 128)
@@ -926,11 +939,20 @@ __global__ void __launch_bounds__(kWalkThreads, 2)
     for (int p = threadIdx.x; p < 2 * P; p += kWalkThreads) planes4[H * P + p] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 
+  pdl_wait();  // the roi plan is complete and visible from here on
+  const int r0 = img_off[b], r1 = img_off[b + 1];
+  if (r0 >= r1) {  // an image without rois (uniform over the CTA)
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    return;
+  }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k = lane & 7, slot = lane >> 3;
   const uint32_t pbase = smem_u32(planes4);
   float *stg = stage + (warp * 2) * (4 * SLOT) + slot * SLOT;  // + parity * 4 * SLOT
-  const int n_groups = (r1 - r0 + 3) >> 2;
+  const int n_groups_all = (r1 - r0 + 3) >> 2;
+  // this CTA's share of the image's groups: [g_lo, n_groups)
+  const int g_lo = (int)(((long long)n_groups_all * part) / parts);
+  const int n_groups = (int)(((long long)n_groups_all * (part + 1)) / parts);
   const bool kst = POOL == RLOD_POOL_NONE || k < 7;  // this lane stores (lane 7 only pools for lane 6)
   float *out_chunk = out + (size_t)chunk * 4 * OHW;
   const size_t roi_pitch = (size_t)C * OHW;
@@ -943,9 +965,9 @@ __global__ void __launch_bounds__(kWalkThreads, 2)
   // two record register sets: one is computed while the other is loaded
   WalkRec recA, recB;
   walk_rec_clear(recA);
-  int ra = roi_of(warp);
+  int ra = roi_of(g_lo + warp);
   if (ra >= 0) walk_rec_load(ext, ra, k, recA);
-  int rb = roi_of(warp + kWalkWarps);
+  int rb = roi_of(g_lo + warp + kWalkWarps);
   WalkTaps2 taps;
   taps.x0 = taps.x1 = taps.y0 = taps.y1 = taps.z0 = taps.z1 = taps.w0 = taps.w1 = 0ull;
   asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -1035,7 +1057,7 @@ __global__ void __launch_bounds__(kWalkThreads, 2)
   };
   using P0 = std::integral_constant<int, 0>;
   using P1 = std::integral_constant<int, 1>;
-  for (int g = warp, it = 0; g < n_groups;) {
+  for (int g = g_lo + warp, it = 0; g < n_groups;) {
     const int rc = roi_of(g + 2 * kWalkWarps);
     body(recA, ra, recB, rb, it, P0{});
     g += kWalkWarps, ++it;
@@ -1423,6 +1445,28 @@ static bool align_fwd_geometry_fast(int B, int C, int H, int W, int R, int GH, i
          R >= 2 * B;
 }
 
+// A/B switches: RLOD_NO_PDL=1 launches the list and pooling kernels of the forward strictly one after the
+// other; RLOD_NO_SPLIT=1 keeps one CTA per (image, 4 channels) in the last wave of the pooling launch.
+static bool pdl_enabled() {
+  static const bool on = getenv("RLOD_NO_PDL") == nullptr;
+  return on;
+}
+
+// How the pooling launch ends: `items` CTAs of equal cost on `slots` resident CTAs leave the last wave
+// partly empty; when at most half of it is used, every item of that wave is served by S CTAs (S <= 4,
+// at least ~16 roi groups each).  Returns S (1 = no split) and the first split item.
+static int fwd_tail_split(int items, int slots, int rois_per_image, int *split_from) {
+  static const bool off = getenv("RLOD_NO_SPLIT") != nullptr;
+  const int full = items / slots * slots, rem = items - full;
+  *split_from = items;
+  if (off || rem == 0) return 1;
+  int S = slots / rem;
+  if (S > 4) S = 4;
+  while (S > 1 && rois_per_image / (4 * S) < 16) --S;
+  if (S > 1) *split_from = full;
+  return S;
+}
+
 static int align_fwd_plan(const float *rois, int B, int H, int W, int R, int GH, int GW, float spatial_scale,
                           bool fast, const AlignWs &ws, cudaStream_t st) {
   if (!fast) return build_plan(rois, B, H, W, R, GH, GW, spatial_scale, ws, st);
@@ -1436,21 +1480,31 @@ static int align_fwd_plan(const float *rois, int B, int H, int W, int R, int GH,
   } else {
     // group fix-up + partition of every image's list by walk mode (the four rois of a warp then stage alike)
     // in one launch
-    RLOD_LAUNCH(RLOD_KERNEL_ROI_PLAN, st, k_roi_lists_finish<<<B, kOrderThreads, 0, st>>>(ws.ext, 0, 30, R, B, ws));
+    // (set up behind the plan kernel as its programmatic dependent: its CTAs are resident and past their
+    // prologue when the plan completes)
+    RLOD_LAUNCH(RLOD_KERNEL_ROI_PLAN, st,
+                launch_after(k_roi_lists_finish, dim3((unsigned)B), dim3(kOrderThreads), 0, st, pdl_enabled(),
+                             (const int *)ws.ext, 0, 30, R, B, ws));
   }
   return launch_status();
 }
 
 static int align_fwd_run(const float *feat, int B, int C, int H, int W, int R, int ah, int aw, int GH, int GW,
-                         int pool_mode, int channels_last, bool fast, float *out, const AlignWs &ws, cudaStream_t st) {
+                         int pool_mode, int channels_last, bool fast, float *out, const AlignWs &ws, cudaStream_t st,
+                         bool behind_plan) {
+  // behind_plan: the plan kernels are the launches just before this one on st (rlod_roi_align_forward); the
+  // pooling kernel is then set up behind them and fills its planes while they run
   if (fast) {
     static const bool v1 = getenv("RLOD_FWD_V1") != nullptr;
     if (channels_last && v1) return RLOD_EUNSUPPORTED;
     const size_t smem = fwd_walk_smem(H, W, pool_mode) + 16;
     const int tma_fill = channels_last ? 2 : (fwd_tma_fill_ok(feat, H, W, pool_mode) ? 1 : 0);
     const int n_chunks = C / 4;
-    const unsigned grid = (unsigned)(B * n_chunks);
     const int P = walk_pitch(W);
+    int split_from = B * n_chunks;
+    const int split = v1 ? 1 : fwd_tail_split(B * n_chunks, (2 * smem + 2048 <= (size_t)kMaxSmemPerCta ? 2 : 1) * kSmCount,
+                                              R / B, &split_from);
+    const unsigned grid = (unsigned)(split_from + (B * n_chunks - split_from) * split);
 #define RLOD_LAUNCH_FWD(POOL)                                                                  \
   do {                                                                                         \
     static bool attr_set = false;                                                              \
@@ -1467,9 +1521,10 @@ static int align_fwd_run(const float *feat, int B, int C, int H, int W, int R, i
                                                                 ws.img_off, C, H, W, P,        \
                                                                 n_chunks, tma_fill, out);      \
     else                                                                                       \
-      k_align8_fwd_walk2<POOL><<<grid, kWalkThreads, smem, st>>>(feat, ws.ext, ws.order2,      \
-                                                                 ws.img_off, C, H, W, P,       \
-                                                                 n_chunks, tma_fill, out);     \
+      launch_after(k_align8_fwd_walk2<POOL>, dim3(grid), dim3(kWalkThreads), smem, st,        \
+                   behind_plan && pdl_enabled(), feat, (const int *)ws.ext,                    \
+                   (const int *)ws.order2, (const int *)ws.img_off, C, H, W, P, n_chunks,      \
+                   tma_fill, split_from, split, out);                                          \
   } while (0)
     if (pool_mode == RLOD_POOL_NONE)
       RLOD_LAUNCH_FWD(RLOD_POOL_NONE);
@@ -1515,7 +1570,7 @@ RLOD_API int rlod_roi_align_forward(const float *feat, const float *rois, int B,
   if (channels_last && (!fast || ((uintptr_t)feat % 16) != 0)) return RLOD_EUNSUPPORTED;
   rc = align_fwd_plan(rois, B, H, W, R, GH, GW, spatial_scale, fast, ws, st);
   if (rc) return rc;
-  return align_fwd_run(feat, B, C, H, W, R, ah, aw, GH, GW, pool_mode, channels_last, fast, out, ws, st);
+  return align_fwd_run(feat, B, C, H, W, R, ah, aw, GH, GW, pool_mode, channels_last, fast, out, ws, st, true);
 }
 
 RLOD_API int rlod_roi_align_plan(const float *rois, int B, int C, int H, int W, int R, int ah, int aw,
@@ -1549,7 +1604,8 @@ RLOD_API int rlod_roi_align_forward_planned(const float *feat, int B, int C, int
   // the plan in the workspace is the plane kernel's: it needs a 16-byte aligned output (and map, when channels-last)
   if (fast && ((uintptr_t)out % 16) != 0) return RLOD_EINVAL;
   if (channels_last && (!fast || ((uintptr_t)feat % 16) != 0)) return RLOD_EUNSUPPORTED;
-  return align_fwd_run(feat, B, C, H, W, R, ah, aw, GH, GW, pool_mode, channels_last, fast, out, ws, (cudaStream_t)stream);
+  return align_fwd_run(feat, B, C, H, W, R, ah, aw, GH, GW, pool_mode, channels_last, fast, out, ws, (cudaStream_t)stream,
+                       false);
 }
 
 RLOD_API int rlod_roi_align_backward(const float *grad_out, const float *rois, const float *feat,

@@ -193,6 +193,10 @@ static __global__ void __launch_bounds__(kOrderThreads)
   const unsigned full = 0xffffffffu, below = (1u << lane) - 1u;
   constexpr int NW = kOrderThreads / 32;
   int n, first;
+  // launched as a programmatic dependent of the plan kernel (the forward RoIAlign): the kernel after this
+  // one may be set up now, and the plan is complete and visible after the wait (both do nothing otherwise)
+  pdl_trigger();
+  pdl_wait();
   const bool grouped = ws.flag[0] == 0;
   if (grouped) {
     first = ws.img_off[b];

@@ -268,6 +268,30 @@ def test_roi_align_long_roi_lists(orc, grouped):
     close(gin.cpu().numpy(), gref, what="long roi lists bwd")
 
 
+@pytest.mark.parametrize("mode", [be.POOL_NONE, be.POOL_AVG, be.POOL_MAX])
+@pytest.mark.parametrize("shuffle", [False, True])
+def test_roi_align_forward_split_tail(orc, mode, shuffle):
+    """Few (image, 4-channel) items and long roi lists: the pooling launch serves every item of its last wave
+    with up to four CTAs, each with a contiguous share of the image's roi groups (fwd_tail_split).  Ragged
+    lists: an image with fewer groups than CTAs (empty shares), an image without rois, shares of unequal size."""
+    B, C, H, W = 4, 8, 30, 41
+    counts = [3, 0, 1021, 517]
+    g = torch.Generator().manual_seed(77)
+    feat = torch.randn(B, C, H, W, generator=g)
+    parts = []
+    for b, n in enumerate(counts):
+        r = syn.rois_for_batch(100 + b, 1, max(n, 1), H * 16.0, W * 16.0)[:n]
+        r[:, 0] = b
+        parts.append(r)
+    rois = torch.cat(parts).contiguous()
+    if shuffle:
+        rois = rois[torch.randperm(rois.size(0), generator=g)].contiguous()
+    ah = 8 if mode == be.POOL_NONE else 7
+    ref = orc.roi_align(feat.numpy(), rois.numpy(), ah, ah, 1 / 16.0, pool_mode=mode)
+    out = be.roi_align_forward(cu(feat), cu(rois), ah, ah, 1 / 16.0, mode)
+    close(out.cpu().numpy(), ref, what=f"split tail mode {mode} shuffle {shuffle}")
+
+
 def test_roi_align_c2_full_size(orc):
     # config 2: Res-101 C4 at 600x1000 -> (4,1024,38,63), 4 x 256 rois, 7x7
     feat, rois = _align_case(1, 4, 1024, 38, 63, 256)

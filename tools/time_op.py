@@ -46,4 +46,4 @@ for _ in range(iters):
     e1.synchronize()
     ts.append(e0.elapsed_time(e1) * 1e3)
 alg = 4 * (B * C * H * W + 5 * rois.size(0) + rois.size(0) * C * 49) * (2 if op.startswith("pool") else 1) - (4 * B * C * H * W if op.startswith("pool") else 0)
-print(f"{op} {cfg} env={os.environ.get('RLOD_FWD_NO_STREAM', '')}: median {statistics.median(ts):.1f} us  min {min(ts):.1f} us (whole call incl. plan launches)")
+print(f"{op} {cfg} env={' '.join(k + '=' + v for k, v in sorted(os.environ.items()) if k.startswith('RLOD_'))}: median {statistics.median(ts):.1f} us  min {min(ts):.1f} us (whole call incl. plan launches)")
