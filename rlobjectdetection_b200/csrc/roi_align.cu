@@ -1445,12 +1445,8 @@ static bool align_fwd_geometry_fast(int B, int C, int H, int W, int R, int GH, i
          R >= 2 * B;
 }
 
-// A/B switches: RLOD_NO_PDL=1 launches the list and pooling kernels of the forward strictly one after the
-// other; RLOD_NO_SPLIT=1 keeps one CTA per (image, 4 channels) in the last wave of the pooling launch.
-static bool pdl_enabled() {
-  static const bool on = getenv("RLOD_NO_PDL") == nullptr;
-  return on;
-}
+// A/B switches: RLOD_NO_PDL=1 (roi_lists.cuh) launches the list and pooling kernels of the forward strictly one
+// after the other; RLOD_NO_SPLIT=1 keeps one CTA per (image, 4 channels) in the last wave of the pooling launch.
 
 // How the pooling launch ends: `items` CTAs of equal cost on `slots` resident CTAs leave the last wave
 // partly empty; when at most half of it is used, every item of that wave is served by S CTAs (S <= 4,

@@ -116,6 +116,7 @@ __device__ __forceinline__ void axis8(float c0, float c1, float scale, int dim, 
 __global__ void __launch_bounds__(128)
     k_roi_plan_own(const float *__restrict__ rois, int R, int B, int H, int W, float scale, int avg,
                    AlignWs ws) {
+  pdl_trigger();  // the kernels behind this one are set up now; they wait for the plan themselves
   const int r = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (r >= R) return;
   const int lane = threadIdx.x & 31;
@@ -282,7 +283,6 @@ __global__ void __launch_bounds__(NW * 32, B16 ? (18 / NW > 0 ? 18 / NW : 1) : 2
   const size_t planes_bytes = (size_t)(HW + W) * 16;
   float *tiles = reinterpret_cast<float *>(smem_raw + planes_bytes) + (size_t)warp * NS * STG;
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + planes_bytes + (size_t)NW * NS * STG * 4) + warp * NS;
-  const int r0 = img_off[b], n = img_off[b + 1] - r0;
   float *dst = gin + ((size_t)b * C + (size_t)quad * 4) * HW;
   const float *gsrc = gout + (size_t)quad * 4 * OHW;
 
@@ -299,6 +299,10 @@ __global__ void __launch_bounds__(NW * 32, B16 ? (18 / NW > 0 ? 18 / NW : 1) : 2
   if (lane == 0)
     for (int s = 0; s < NS; ++s) mbar_init(bars + s, 1);
   __syncthreads();
+  // launched behind the plan kernels as their programmatic dependent: the planes above were set up while
+  // those ran, the plan and the roi lists are complete and visible from here on
+  pdl_wait();
+  const int r0 = img_off[b], n = img_off[b + 1] - r0;
 
   // warp w serves rois w, w + NW, ... of the image (every roi costs the same: no work queue)
   auto roi_at = [&](int k) {  // k-th roi of this warp
@@ -465,7 +469,11 @@ int launch_bwd_own(const float *grad_out, const float *rois, int B, int C, int H
   RLOD_LAUNCH(RLOD_KERNEL_ROI_PLAN, st,
               k_roi_plan_own<<<(unsigned)cdiv(R, 4), 128, 0, st>>>(rois, R, B, H, W, spatial_scale,
                                                                   pool_mode == RLOD_POOL_AVG ? 1 : 0, ws));
-  RLOD_LAUNCH(RLOD_KERNEL_ROI_PLAN, st, k_roi_group_fixup<<<1, 32, 0, st>>>(R, B, ws));
+  // Programmatic dependent launch of the two kernels below (as in the forward) is wired but left off: measured
+  // 220 against 207 us at C2 and 1349 against 1352 us at C4 (RLOD_BWD_PDL=1 turns it on) -- the early CTAs of the
+  // backward land unevenly on the SMs the plan kernel still occupies, and the 1.7 waves of C2 end later for it.
+  static const bool pdl = getenv("RLOD_BWD_PDL") != nullptr && pdl_enabled();
+  RLOD_LAUNCH(RLOD_KERNEL_ROI_PLAN, st, launch_after(k_roi_group_fixup, dim3(1), dim3(32), 0, st, pdl, R, B, ws));
   // warps per CTA and tile ring depth per warp: 6-warp CTAs when at least two fit an SM (measured best at
   // C2 and C4: tools/time_op.py with RLOD_BWD_NW), else whatever puts the most warps on an SM; then the
   // deepest ring (8 / 4 / 2 tiles) that does not cost a resident CTA
@@ -506,9 +514,9 @@ int launch_bwd_own(const float *grad_out, const float *rois, int B, int C, int H
       attr_set = true;                                                                           \
     }                                                                                            \
     ProfScope _ps(RLOD_KERNEL_ALIGN_BWD, st);                                                    \
-    k_align8_bwd_own<POOL, NWW, BB><<<grid, NWW * 32, smem, st>>>(grad_out, ws.own, ws.order, ws.img_off, \
-                                                                  C, H, W, n_quads, ns_log2, accumulate, \
-                                                                  grad_in);                      \
+    launch_after(k_align8_bwd_own<POOL, NWW, BB>, dim3(grid), dim3(NWW * 32), smem, st, pdl,     \
+                 grad_out, (const int *)ws.own, (const int *)ws.order, (const int *)ws.img_off,  \
+                 C, H, W, n_quads, ns_log2, accumulate, grad_in);                                \
   } while (0)
 #define RLOD_LAUNCH_OWN_NW(POOL, BB)                    \
   do {                                                  \

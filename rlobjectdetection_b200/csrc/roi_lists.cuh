@@ -66,8 +66,16 @@ __device__ __forceinline__ void roi_list_mark(const float *__restrict__ rois, in
     for (int q = b + 1; q <= B; ++q) ws.img_off[q] = R;
 }
 
+// A/B switch: RLOD_NO_PDL=1 launches the plan / list / pooling kernels of a call strictly one after the other
+static inline bool pdl_enabled() {
+  static const bool on = getenv("RLOD_NO_PDL") == nullptr;
+  return on;
+}
+
 // one warp: stable counting sort of roi ids by image, only when the rois were not grouped
 static __global__ void k_roi_group_fixup(int R, int B, AlignWs ws) {
+  pdl_trigger();  // (see k_roi_lists_finish)
+  pdl_wait();
   if (ws.flag[0] == 0) return;
   const int lane = threadIdx.x;
   const unsigned full = 0xffffffffu;
@@ -132,6 +140,8 @@ static __global__ void __launch_bounds__(kOrderThreads)
   __shared__ unsigned short s_key[kOrderMaxRois];
   __shared__ int s_tot[kOrderMaxKeys], s_base[kOrderMaxKeys];
   const int b = blockIdx.x, t = threadIdx.x, lane = t & 31;
+  pdl_trigger();  // (see k_roi_lists_finish)
+  pdl_wait();
   const int r0 = img_off[b], r1 = img_off[b + 1], n = r1 - r0;
   const unsigned full = 0xffffffffu;
   if (n > kOrderMaxRois) {

@@ -32,6 +32,7 @@ constexpr int kPoolSlot = 200;  // floats per staged tile slot (196 used), = 8 (
 
 __global__ void k_pool_plan(const float *__restrict__ rois, int R, int B, int H, int W, float scale,
                             AlignWs ws) {
+  pdl_trigger();  // the list kernels behind this one are set up now; they wait for the plan themselves
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= R) return;
   const float *roi = rois + (size_t)r * 5;
@@ -84,8 +85,8 @@ __global__ void __launch_bounds__(kPoolThreads, 2)
   const int HW = H * W;
   float *stage = reinterpret_cast<float *>(planes4 + H * P);  // [warps][4 slots][2 tiles][kPoolSlot]
   const int b = blockIdx.x / n_chunks, chunk = blockIdx.x - b * n_chunks;
-  const int r0 = img_off[b], r1 = img_off[b + 1];
-  if (r0 >= r1) return;
+  // the fill reads the feature map only and runs while the plan / list kernels launched just before are still
+  // at work (programmatic dependent launch); pdl_wait() below is where this grid meets their results
   if (channels_last) {
     fill_planes4_nhwc_async<kPoolThreads>(planes4, feat + (size_t)b * HW * C + (size_t)chunk * 4, H, W, P, C);
   } else {
@@ -97,9 +98,12 @@ __global__ void __launch_bounds__(kPoolThreads, 2)
   const uint32_t pbase = smem_u32(planes4);
   float *tile_v = stage + ((warp * 4 + slot) * 2) * kPoolSlot;
   int *tile_i = reinterpret_cast<int *>(tile_v + kPoolSlot);
-  const int n_groups = (r1 - r0 + 3) >> 2;
   const int chan_base = (b * C + chunk * 4) * HW;  // flat NCHW index of this CTA's first plane
   asm volatile("cp.async.wait_group 0;" ::: "memory");
+  pdl_wait();
+  const int r0 = img_off[b], r1 = img_off[b + 1];
+  if (r0 >= r1) return;  // an image without rois (uniform over the CTA)
+  const int n_groups = (r1 - r0 + 3) >> 2;
   __syncthreads();
 
   for (int g = warp, it = 0; g < n_groups; g += kPoolWarps, ++it) {
@@ -361,20 +365,24 @@ RLOD_API int rlod_roi_pool_forward(const float *feat, const float *rois, int B, 
   if (fast) {
     cudaMemsetAsync(ws.flag, 0, 4 * sizeof(int), st);
     RLOD_LAUNCH(RLOD_KERNEL_ROI_PLAN, st, k_pool_plan<<<(unsigned)cdiv(R, 128), 128, 0, st>>>(rois, R, B, H, W, spatial_scale, ws));
-    RLOD_LAUNCH(RLOD_KERNEL_ROI_PLAN, st, k_roi_group_fixup<<<1, 32, 0, st>>>(R, B, ws));
+    const bool pdl = pdl_enabled();
+    RLOD_LAUNCH(RLOD_KERNEL_ROI_PLAN, st, launch_after(k_roi_group_fixup, dim3(1), dim3(32), 0, st, pdl, R, B, ws));
     RLOD_LAUNCH(RLOD_KERNEL_ROI_PLAN, st,
-                k_roi_order_by_key<<<B, kOrderThreads, 0, st>>>(ws.plan, ws.order, ws.img_off, 31, 0, 64, ws.order2));
+                launch_after(k_roi_order_by_key, dim3((unsigned)B), dim3(kOrderThreads), 0, st, pdl, (const int *)ws.plan,
+                             (const int *)ws.order, (const int *)ws.img_off, 31, 0, 64, ws.order2));
     const int n_chunks = C / 4;
     if (argmax) {
       cudaFuncSetAttribute(k_roi_pool7_fwd_planes<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       RLOD_LAUNCH(RLOD_KERNEL_POOL_FWD, st,
-                  k_roi_pool7_fwd_planes<true><<<(unsigned)(B * n_chunks), kPoolThreads, smem, st>>>(
-                      feat, ws.plan, ws.order2, ws.img_off, C, H, W, P, n_chunks, channels_last, out, argmax));
+                  launch_after(k_roi_pool7_fwd_planes<true>, dim3((unsigned)(B * n_chunks)), dim3(kPoolThreads), smem, st, pdl,
+                               feat, (const int *)ws.plan, (const int *)ws.order2, (const int *)ws.img_off, C, H, W, P,
+                               n_chunks, channels_last, out, argmax));
     } else {
       cudaFuncSetAttribute(k_roi_pool7_fwd_planes<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       RLOD_LAUNCH(RLOD_KERNEL_POOL_FWD, st,
-                  k_roi_pool7_fwd_planes<false><<<(unsigned)(B * n_chunks), kPoolThreads, smem, st>>>(
-                      feat, ws.plan, ws.order2, ws.img_off, C, H, W, P, n_chunks, channels_last, out, argmax));
+                  launch_after(k_roi_pool7_fwd_planes<false>, dim3((unsigned)(B * n_chunks)), dim3(kPoolThreads), smem, st, pdl,
+                               feat, (const int *)ws.plan, (const int *)ws.order2, (const int *)ws.img_off, C, H, W, P,
+                               n_chunks, channels_last, out, argmax));
     }
     return launch_status();
   }
