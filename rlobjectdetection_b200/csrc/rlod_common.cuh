@@ -181,6 +181,24 @@ __device__ __forceinline__ void fill_planes4_async(float4 *planes4, const float 
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
+// The same fill from a window of a larger map: rows x cols pixels whose first is src, rows row_stride floats
+// apart, channel planes chan_stride floats apart.
+template <int THREADS>
+__device__ __forceinline__ void fill_planes4_window_async(float4 *planes4, const float *__restrict__ src, int rows,
+                                                          int cols, int P, int row_stride, size_t chan_stride) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int px = lane >> 2, c = lane & 3;
+  const float *sc = src + (size_t)c * chan_stride + px;
+  const uint32_t d0 = smem_u32(planes4) + 16u * (uint32_t)px + 4u * (uint32_t)c;
+  for (int y = warp; y < rows; y += THREADS / 32) {
+    const float *s = sc + (size_t)y * row_stride;
+    uint32_t d = d0 + 16u * (uint32_t)(y * P);
+    for (int x = px; x < cols; x += 8, s += 8, d += 128u)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(s) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
 // The same fill from a channels-last (NHWC) feature map: the 4 channels of a pixel are already one
 // contiguous, 16-byte aligned float4 (C % 4 == 0), C floats from the next pixel -- one 16-byte async
 // copy per pixel, no interleave at all.  A 32-byte DRAM sector holds two chunks' worth, so the CTAs

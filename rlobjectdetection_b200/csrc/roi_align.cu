@@ -117,7 +117,8 @@ template <int POOL>
 __global__ void __launch_bounds__(256)
     k_align_fwd_generic(const float *__restrict__ feat, const int *__restrict__ plan,
                         const int *__restrict__ roi_b, int C, int H, int W, int GH, int GW,
-                        long long total, float *__restrict__ out) {
+                        long long total, float *__restrict__ out, const int *__restrict__ only = nullptr,
+                        const int *__restrict__ only_count = nullptr) {
   const int ah = POOL == RLOD_POOL_NONE ? GH : GH - 1, aw = POOL == RLOD_POOL_NONE ? GW : GW - 1;
   const int words = 2 * GH + 2 * GW;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -125,9 +126,18 @@ __global__ void __launch_bounds__(256)
     const int ow = (int)(idx % aw);
     const int oh = (int)((idx / aw) % ah);
     const int c = (int)((idx / ((long long)aw * ah)) % C);
-    const int r = (int)(idx / ((long long)aw * ah * C));
+    int r = (int)(idx / ((long long)aw * ah * C));
+    int b;
+    if (only) {
+      // only the rois the tiled plane kernel left out: only[0 .. *only_count) = their ids, roi_b = -1 - image
+      if (r >= *only_count) break;
+      r = only[r];
+      b = -1 - roi_b[r];
+    } else {
+      b = roi_b[r];
+    }
     const int *pl = plan + (size_t)r * words;
-    const float *plane = feat + ((size_t)roi_b[r] * C + c) * ((size_t)H * W);
+    const float *plane = feat + ((size_t)b * C + c) * ((size_t)H * W);
     const int h0 = pl[oh], w0 = pl[2 * GH + 2 * ow];
     const float hr0 = __int_as_float(pl[GH + oh]), wr0 = __int_as_float(pl[2 * GH + 2 * ow + 1]);
     float v;
@@ -143,7 +153,7 @@ __global__ void __launch_bounds__(256)
       const float d = sample_plane(plane, W, h1, hr1, w1, wr1);
       v = pool4<POOL>(a, b, cc, d);
     }
-    out[idx] = v;
+    out[only ? ((long long)r * C + c) * (ah * aw) + oh * aw + ow : idx] = v;
   }
 }
 
@@ -308,7 +318,7 @@ __device__ __forceinline__ int tap_order_natural(const int *L, const int *R, int
 // one warp per roi
 __global__ void __launch_bounds__(128, 6)
     k_roi_plan8_walk(const float *__restrict__ rois, int R, int B, int H, int W, int P, float scale,
-                     int bwd, AlignWs ws) {
+                     int bwd, TileGrid tg, AlignWs ws) {
   pdl_trigger();  // k_roi_lists_finish may be set up behind this grid (it waits for our results itself)
   const int r = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (r >= R) return;
@@ -334,7 +344,43 @@ __global__ void __launch_bounds__(128, 6)
       my_idx = (int)fminf(floorf(pos), (float)(dim - 2));
       my_ratio = __float_as_int(__fsub_rn(pos, (float)my_idx));
     }
-    if (lane == 0) roi_list_mark(rois, r, R, B, bvalid ? bi : 0, ws);
+    if (tg.ny * tg.nx == 1) {
+      if (lane == 0) roi_list_mark(rois, r, R, B, bvalid ? bi : 0, ws);
+    } else {
+      // Tiled map: the roi goes to the tile that holds all of its taps (rows lo .. hi + 1, columns likewise);
+      // tile origins are tg.sy / tg.sx apart, so the tile whose origin is the last one at or before the first
+      // tap is the only candidate that can hold a roi of up to th - sy + 1 rows wherever it lies.  From here on
+      // the indices are tile-local and the zero rows / column are the tile's (H, W become th, tw).  A roi
+      // that fits no tile is planned as all-zero here and pooled by the generic kernel afterwards, from the
+      // k_roi_plan record written below (its id is appended to a list in ws.own; ws.roi_b keeps its image).
+      const unsigned full = 0xffffffffu;
+      const bool v = my_idx >= 0;
+      const int rlo = __reduce_min_sync(full, (v && lane < 8) ? my_idx : (1 << 30));
+      const int rhi = __reduce_max_sync(full, (v && lane < 8) ? my_idx + 1 : -1);
+      const int clo = __reduce_min_sync(full, (v && lane >= 8) ? my_idx : (1 << 30));
+      const int chi = __reduce_max_sync(full, (v && lane >= 8) ? my_idx + 1 : -1);
+      const int ty = rhi < 0 ? 0 : min(rlo / tg.sy, tg.ny - 1), tx = chi < 0 ? 0 : min(clo / tg.sx, tg.nx - 1);
+      const int oy = ty * tg.sy, ox = tx * tg.sx;
+      const bool fits = (rhi < 0 || rhi - oy < tg.th) && (chi < 0 || chi - ox < tg.tw);
+      if (!fits && lane < 16) {
+        int *pl = ws.plan + (size_t)r * 32;
+        if (lane < 8) pl[lane] = my_idx, pl[8 + lane] = my_ratio;
+        else pl[16 + 2 * (lane - 8)] = my_idx, pl[17 + 2 * (lane - 8)] = my_ratio;
+      }
+      if (lane == 0) {
+        // the rois left to the generic kernel: ws.own[0 .. count) = their ids, count = ws.flag[2] (zeroed with
+        // the flags before this launch); (a roi of an image out of range has no valid sample: it fits)
+        if (!fits) ws.own[atomicAdd(ws.flag + 2, 1)] = r;
+        // list key: the virtual image of the tile; a roi beyond the tiles carries -1 - image, which matches no
+        // list (the plane kernel never sees it) and tells the generic kernel its image
+        ws.roi_b[r] = !bvalid ? 0 : (fits ? (bi * tg.ny + ty) * tg.nx + tx : -1 - bi);
+        ws.order[r] = r;
+        if (r == 0) atomicOr(ws.flag, 1);  // lists by virtual image: always collected, never "grouped"
+      }
+      if (!fits) my_idx = -1, my_ratio = 0;
+      else if (v) my_idx -= lane < 8 ? oy : ox;
+      H = tg.th, W = tg.tw;
+    }
   }
   int row[8], col[8];
   bool colv[8];
@@ -813,12 +859,14 @@ __device__ __forceinline__ void walk_load2(WalkTaps2 &q, uint32_t pa, uint32_t p
       : "r"(pa), "r"(pb), "r"(pa2), "r"(pb2), "r"(flags));
 }
 
-template <int POOL>
+// TILED: the lists are per tile of a larger map (TileGrid, roi_lists.cuh): H, W are the tile's size, Hf, Wf
+// the map's; the planes are filled from the tile's window of the map (4-byte async copies, row stride Wf).
+template <int POOL, bool TILED>
 __global__ void __launch_bounds__(kWalkThreads, 2)
     k_align8_fwd_walk2(const float *__restrict__ feat, const int *__restrict__ ext,
                        const int *__restrict__ order, const int *__restrict__ img_off, int C,
                        int H, int W, int P, int n_chunks, int tma_fill, int split_from, int split,
-                       float *__restrict__ out) {
+                       TileGrid tg, int Hf, int Wf, float *__restrict__ out) {
   constexpr int OW = POOL == RLOD_POOL_NONE ? 8 : 7;
   constexpr int OHW = OW * OW;                            // 64 | 49
   constexpr int STG = 4 * OHW;                            // floats per (roi, 4 channels)
@@ -845,6 +893,31 @@ __global__ void __launch_bounds__(kWalkThreads, 2)
   // programmatic dependent of the list kernel).
   const float *src = feat + ((size_t)b * C + (size_t)chunk * 4) * HW;
   uint64_t *fill_bar = reinterpret_cast<uint64_t *>(stage + kWalkWarps * 2 * 4 * SLOT);
+  if constexpr (TILED) {
+    // most tiles of a large map hold no roi: look at the list before paying for the fill
+    pdl_wait();
+    if (img_off[b] >= img_off[b + 1]) return;
+    const int tiles = tg.ny * tg.nx;
+    const int bi = b / tiles, t = b - bi * tiles, ty = t / tg.nx, tx = t - ty * tg.nx;
+    const int oy = ty * tg.sy, ox = tx * tg.sx;
+    const int rows = min(H, Hf - oy), cols = min(W, Wf - ox);
+    if (rows < H || cols < W) {  // a tile that hangs over the edge: no tap lands there, but keep it finite
+      for (int p = threadIdx.x; p < H * P; p += kWalkThreads) planes4[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+      __syncthreads();
+    }
+    const size_t HWf = (size_t)Hf * Wf;
+    fill_planes4_window_async<kWalkThreads>(planes4, feat + ((size_t)bi * C + (size_t)chunk * 4) * HWf + (size_t)oy * Wf + ox,
+                                            rows, cols, P, Wf, HWf);
+    if (POOL == RLOD_POOL_AVG) {  // prescale in place once the async copies have landed
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();
+      for (int p = threadIdx.x; p < H * P; p += kWalkThreads) {
+        float4 v = planes4[p];
+        planes4[p] = make_float4(kPre * v.x, kPre * v.y, kPre * v.z, kPre * v.w);
+      }
+      __syncthreads();  // the pass touched the pad columns too: they are zeroed below, by other threads
+    }
+  } else
   // ---- fill (see k_align8_fwd_walk): bulk copies land the planes planar, threads interleave ----
   // tma_fill: 1 = NCHW by bulk copies, 0 = NCHW by 4-byte async copies, 2 = channels-last input
   if (tma_fill == 2) {
@@ -856,6 +929,7 @@ __global__ void __launch_bounds__(kWalkThreads, 2)
         float4 v = planes4[p];
         planes4[p] = make_float4(kPre * v.x, kPre * v.y, kPre * v.z, kPre * v.w);
       }
+      __syncthreads();  // the pass touched the pad columns too: they are zeroed below, by other threads
     }
   } else if (tma_fill) {
     const uint32_t plane_copy = (uint32_t)((HW * 4 + 8 + 15) & ~15);
@@ -928,6 +1002,7 @@ __global__ void __launch_bounds__(kWalkThreads, 2)
         float4 v = planes4[p];
         planes4[p] = make_float4(kPre * v.x, kPre * v.y, kPre * v.z, kPre * v.w);
       }
+      __syncthreads();  // the pass touched the pad columns too: they are zeroed below, by other threads
     }
   }
   {
@@ -1445,6 +1520,39 @@ static bool align_fwd_geometry_fast(int B, int C, int H, int W, int R, int GH, i
          R >= 2 * B;
 }
 
+// A map too large for the plane kernel (FPN-sized levels, images beyond ~1400 pixels at stride 16) is covered by
+// overlapping tiles of at most kTilePixels padded pixels (two CTAs per SM, like the 50 x 75 map of C4), origins
+// half a tile apart: a roi of up to half a tile per side fits one tile wherever it lies, larger ones are left to
+// the generic kernel.  Returns false when the map needs no tiles, cannot be tiled (more than kMaxTilesPerImage
+// tiles), has too few rois per tile to pay for the tiles' planes, or the call is not the plane kernel's anyway.
+constexpr int kTilePixels = 4030;
+static bool align_fwd_tiles(int B, int C, int H, int W, int R, int GH, int GW, int pool_mode, int channels_last,
+                            TileGrid *tg) {
+  static const bool off = getenv("RLOD_NO_TILES") != nullptr;  // A/B switch: the generic kernel for large maps
+  if (off || channels_last || GH != 8 || GW != 8 || (C % 4) != 0 || R < 2 * B) return false;
+  if (align_fwd_geometry_fast(B, C, H, W, R, GH, GW, pool_mode)) return false;
+  // as square as the map allows: an axis shorter than the square's side is not tiled
+  int tw = W < 61 ? W : 61, th = kTilePixels / walk_pitch(tw) - 2;
+  if (th >= H) {
+    th = H;
+    while (tw < W && (th + 2) * walk_pitch(tw + 1) <= kTilePixels) ++tw;
+  }
+  if (th < 8 || tw < 8) return false;
+  tg->th = th, tg->tw = tw;
+  tg->sy = th >= H ? th : th / 2, tg->sx = tw >= W ? tw : tw / 2;
+  tg->ny = th >= H ? 1 : (H - th + tg->sy - 1) / tg->sy + 1;
+  tg->nx = tw >= W ? 1 : (W - tw + tg->sx - 1) / tg->sx + 1;
+  if (tg->ny * tg->nx > kMaxTilesPerImage || tg->ny * tg->nx < 2) return false;
+  // A (tile, 4 channels) CTA costs ~9.3 us + 0.06 us per roi (the planes arrive by 4-byte async copies), the
+  // generic kernel ~0.72 us per (roi, 4 channels); measured with tools/time_op.py: an FPN P2 level (2 x 256 x 200 x
+  // 304, 8.5 rois per tile) 253 us tiled against 172 us generic, 2 x 1024 x 100 x 150 with 25 rois per tile 216
+  // against 371 us, with 166 per tile 398 against 2 353 us.  Tiles from 16 rois per tile on.
+  static const bool force = getenv("RLOD_FORCE_TILES") != nullptr;
+  if (!force && (long long)R < 16LL * B * tg->ny * tg->nx) return false;
+  if ((long long)B * tg->ny * tg->nx * (C / 4) >= (1LL << 31)) return false;
+  return fwd_walk_smem(th, tw, pool_mode) + 16 <= (size_t)kMaxSmemPerCta;
+}
+
 // A/B switches: RLOD_NO_PDL=1 (roi_lists.cuh) launches the list and pooling kernels of the forward strictly one
 // after the other; RLOD_NO_SPLIT=1 keeps one CTA per (image, 4 channels) in the last wave of the pooling launch.
 
@@ -1463,13 +1571,28 @@ static int fwd_tail_split(int items, int slots, int rois_per_image, int *split_f
   return S;
 }
 
+static const TileGrid kNoTiles = {1, 1, 0, 0, 0, 0};
+
+// tiles: the map is tiled (align_fwd_tiles); fast then means "plane kernel over the tiles"
 static int align_fwd_plan(const float *rois, int B, int H, int W, int R, int GH, int GW, float spatial_scale,
-                          bool fast, const AlignWs &ws, cudaStream_t st) {
+                          bool fast, const TileGrid *tiles, const AlignWs &ws, cudaStream_t st) {
   if (!fast) return build_plan(rois, B, H, W, R, GH, GW, spatial_scale, ws, st);
   // one launch: sample grid + orientation / tap-order search + walk record + roi lists
   cudaMemsetAsync(ws.flag, 0, 4 * sizeof(int), st);
+  if (tiles) {
+    // lists per (image, tile); rois that fit no tile get a k_roi_plan record for the generic kernel
+    RLOD_LAUNCH(RLOD_KERNEL_ROI_PLAN, st,
+                k_roi_plan8_walk<<<(unsigned)cdiv(R, 4), 128, 0, st>>>(rois, R, B, H, W, walk_pitch(tiles->tw), spatial_scale,
+                                                                      0, *tiles, ws));
+    const int V = B * tiles->ny * tiles->nx;
+    RLOD_LAUNCH(RLOD_KERNEL_ROI_PLAN, st,
+                launch_after(k_roi_lists_finish, dim3((unsigned)V), dim3(kOrderThreads), 0, st, pdl_enabled(),
+                             (const int *)ws.ext, 0, 30, R, V, ws));
+    return launch_status();
+  }
   RLOD_LAUNCH(RLOD_KERNEL_ROI_PLAN, st,
-              k_roi_plan8_walk<<<(unsigned)cdiv(R, 4), 128, 0, st>>>(rois, R, B, H, W, walk_pitch(W), spatial_scale, 0, ws));
+              k_roi_plan8_walk<<<(unsigned)cdiv(R, 4), 128, 0, st>>>(rois, R, B, H, W, walk_pitch(W), spatial_scale, 0,
+                                                                    kNoTiles, ws));
   static const bool v1 = getenv("RLOD_FWD_V1") != nullptr;  // A/B switch: the scalar walk of round 1
   if (v1) {
     RLOD_LAUNCH(RLOD_KERNEL_ROI_PLAN, st, k_roi_group_fixup<<<1, 32, 0, st>>>(R, B, ws));
@@ -1486,10 +1609,51 @@ static int align_fwd_plan(const float *rois, int B, int H, int W, int R, int GH,
 }
 
 static int align_fwd_run(const float *feat, int B, int C, int H, int W, int R, int ah, int aw, int GH, int GW,
-                         int pool_mode, int channels_last, bool fast, float *out, const AlignWs &ws, cudaStream_t st,
-                         bool behind_plan) {
+                         int pool_mode, int channels_last, bool fast, const TileGrid *tiles, float *out,
+                         const AlignWs &ws, cudaStream_t st, bool behind_plan) {
   // behind_plan: the plan kernels are the launches just before this one on st (rlod_roi_align_forward); the
   // pooling kernel is then set up behind them and fills its planes while they run
+  if (fast && tiles) {
+    // plane kernel over the tiles (every (image, tile) is a virtual image with its own roi list), then the rois
+    // that fit no tile through the generic kernel
+    const int th = tiles->th, tw = tiles->tw, V = B * tiles->ny * tiles->nx, n_chunks = C / 4;
+    const size_t smem = fwd_walk_smem(th, tw, pool_mode) + 16;
+    const unsigned grid = (unsigned)(V * n_chunks);
+#define RLOD_LAUNCH_FWD_TILED(POOL)                                                                          \
+  do {                                                                                                       \
+    static bool attr_set = false;                                                                            \
+    if (!attr_set) {                                                                                         \
+      cudaFuncSetAttribute(k_align8_fwd_walk2<POOL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                           kMaxSmemPerCta);                                                                  \
+      attr_set = true;                                                                                       \
+    }                                                                                                        \
+    ProfScope _ps(RLOD_KERNEL_ALIGN_FWD, st);                                                                \
+    launch_after(k_align8_fwd_walk2<POOL, true>, dim3(grid), dim3(kWalkThreads), smem, st,                   \
+                 behind_plan && pdl_enabled(), feat, (const int *)ws.ext, (const int *)ws.order2,            \
+                 (const int *)ws.img_off, C, th, tw, walk_pitch(tw), n_chunks, 0, (int)grid, 1, *tiles, H, W, out); \
+  } while (0)
+    if (pool_mode == RLOD_POOL_NONE)
+      RLOD_LAUNCH_FWD_TILED(RLOD_POOL_NONE);
+    else if (pool_mode == RLOD_POOL_AVG)
+      RLOD_LAUNCH_FWD_TILED(RLOD_POOL_AVG);
+    else
+      RLOD_LAUNCH_FWD_TILED(RLOD_POOL_MAX);
+#undef RLOD_LAUNCH_FWD_TILED
+    // the rois beyond a tile (their number is only known on the device): a fixed grid strides over the list
+    const long long total = (long long)R * C * ah * aw;
+    const long long want = cdiv(total, 256);
+    const unsigned ggrid = (unsigned)(want < 16LL * kSmCount ? want : 16LL * kSmCount);
+    if (pool_mode == RLOD_POOL_NONE)
+      RLOD_LAUNCH(RLOD_KERNEL_ALIGN_FWD_GENERIC, st, k_align_fwd_generic<RLOD_POOL_NONE>
+          <<<ggrid, 256, 0, st>>>(feat, ws.plan, ws.roi_b, C, H, W, GH, GW, total, out, ws.own, ws.flag + 2));
+    else if (pool_mode == RLOD_POOL_AVG)
+      RLOD_LAUNCH(RLOD_KERNEL_ALIGN_FWD_GENERIC, st, k_align_fwd_generic<RLOD_POOL_AVG>
+          <<<ggrid, 256, 0, st>>>(feat, ws.plan, ws.roi_b, C, H, W, GH, GW, total, out, ws.own, ws.flag + 2));
+    else
+      RLOD_LAUNCH(RLOD_KERNEL_ALIGN_FWD_GENERIC, st, k_align_fwd_generic<RLOD_POOL_MAX>
+          <<<ggrid, 256, 0, st>>>(feat, ws.plan, ws.roi_b, C, H, W, GH, GW, total, out, ws.own, ws.flag + 2));
+    return launch_status();
+  }
   if (fast) {
     static const bool v1 = getenv("RLOD_FWD_V1") != nullptr;
     if (channels_last && v1) return RLOD_EUNSUPPORTED;
@@ -1507,7 +1671,7 @@ static int align_fwd_run(const float *feat, int B, int C, int H, int W, int R, i
     if (!attr_set) {                                                                           \
       cudaFuncSetAttribute(k_align8_fwd_walk<POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                            kMaxSmemPerCta);                                                    \
-      cudaFuncSetAttribute(k_align8_fwd_walk2<POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+      cudaFuncSetAttribute(k_align8_fwd_walk2<POOL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                            kMaxSmemPerCta);                                                    \
       attr_set = true;                                                                         \
     }                                                                                          \
@@ -1517,10 +1681,10 @@ static int align_fwd_run(const float *feat, int B, int C, int H, int W, int R, i
                                                                 ws.img_off, C, H, W, P,        \
                                                                 n_chunks, tma_fill, out);      \
     else                                                                                       \
-      launch_after(k_align8_fwd_walk2<POOL>, dim3(grid), dim3(kWalkThreads), smem, st,        \
+      launch_after(k_align8_fwd_walk2<POOL, false>, dim3(grid), dim3(kWalkThreads), smem, st, \
                    behind_plan && pdl_enabled(), feat, (const int *)ws.ext,                    \
                    (const int *)ws.order2, (const int *)ws.img_off, C, H, W, P, n_chunks,      \
-                   tma_fill, split_from, split, out);                                          \
+                   tma_fill, split_from, split, kNoTiles, H, W, out);                          \
   } while (0)
     if (pool_mode == RLOD_POOL_NONE)
       RLOD_LAUNCH_FWD(RLOD_POOL_NONE);
@@ -1560,13 +1724,17 @@ RLOD_API int rlod_roi_align_forward(const float *feat, const float *rois, int B,
   AlignWs ws = carve_align_ws(workspace, B, R, GH, GW);
   if (workspace_bytes < ws.bytes) return RLOD_ENOSPC;
   cudaStream_t st = (cudaStream_t)stream;
-  const bool fast = align_fwd_geometry_fast(B, C, H, W, R, GH, GW, pool_mode) && ((uintptr_t)out % 16) == 0;
+  bool fast = align_fwd_geometry_fast(B, C, H, W, R, GH, GW, pool_mode) && ((uintptr_t)out % 16) == 0;
   // a channels-last map is only read by the plane kernel (its taps are contiguous float4s there); the
   // generic kernels index NCHW planes
   if (channels_last && (!fast || ((uintptr_t)feat % 16) != 0)) return RLOD_EUNSUPPORTED;
-  rc = align_fwd_plan(rois, B, H, W, R, GH, GW, spatial_scale, fast, ws, st);
+  TileGrid tg;
+  const bool tiled = ((uintptr_t)out % 16) == 0 && align_fwd_tiles(B, C, H, W, R, GH, GW, pool_mode, channels_last, &tg);
+  fast = fast || tiled;
+  rc = align_fwd_plan(rois, B, H, W, R, GH, GW, spatial_scale, fast, tiled ? &tg : nullptr, ws, st);
   if (rc) return rc;
-  return align_fwd_run(feat, B, C, H, W, R, ah, aw, GH, GW, pool_mode, channels_last, fast, out, ws, st, true);
+  return align_fwd_run(feat, B, C, H, W, R, ah, aw, GH, GW, pool_mode, channels_last, fast, tiled ? &tg : nullptr, out, ws,
+                       st, true);
 }
 
 RLOD_API int rlod_roi_align_plan(const float *rois, int B, int C, int H, int W, int R, int ah, int aw,
@@ -1580,8 +1748,11 @@ RLOD_API int rlod_roi_align_plan(const float *rois, int B, int C, int H, int W, 
   const int GW = pool_mode == RLOD_POOL_NONE ? aw : aw + 1;
   AlignWs ws = carve_align_ws(workspace, B, R, GH, GW);
   if (workspace_bytes < ws.bytes) return RLOD_ENOSPC;
-  return align_fwd_plan(rois, B, H, W, R, GH, GW, spatial_scale, align_fwd_geometry_fast(B, C, H, W, R, GH, GW, pool_mode),
-                        ws, (cudaStream_t)stream);
+  TileGrid tg;
+  const bool tiled = align_fwd_tiles(B, C, H, W, R, GH, GW, pool_mode, 0, &tg);
+  return align_fwd_plan(rois, B, H, W, R, GH, GW, spatial_scale,
+                        tiled || align_fwd_geometry_fast(B, C, H, W, R, GH, GW, pool_mode), tiled ? &tg : nullptr, ws,
+                        (cudaStream_t)stream);
 }
 
 RLOD_API int rlod_roi_align_forward_planned(const float *feat, int B, int C, int H, int W, int R, int ah, int aw,
@@ -1596,12 +1767,16 @@ RLOD_API int rlod_roi_align_forward_planned(const float *feat, int B, int C, int
   const int GW = pool_mode == RLOD_POOL_NONE ? aw : aw + 1;
   AlignWs ws = carve_align_ws(workspace, B, R, GH, GW);
   if (workspace_bytes < ws.bytes) return RLOD_ENOSPC;
-  const bool fast = align_fwd_geometry_fast(B, C, H, W, R, GH, GW, pool_mode);
+  bool fast = align_fwd_geometry_fast(B, C, H, W, R, GH, GW, pool_mode);
+  if (channels_last && (!fast || ((uintptr_t)feat % 16) != 0)) return RLOD_EUNSUPPORTED;
+  TileGrid tg;
+  const bool tiled = align_fwd_tiles(B, C, H, W, R, GH, GW, pool_mode, 0, &tg);  // (the plan call saw no layout flag)
+  fast = fast || tiled;
   // the plan in the workspace is the plane kernel's: it needs a 16-byte aligned output (and map, when channels-last)
   if (fast && ((uintptr_t)out % 16) != 0) return RLOD_EINVAL;
-  if (channels_last && (!fast || ((uintptr_t)feat % 16) != 0)) return RLOD_EUNSUPPORTED;
-  return align_fwd_run(feat, B, C, H, W, R, ah, aw, GH, GW, pool_mode, channels_last, fast, out, ws, (cudaStream_t)stream,
-                       false);
+  if (tiled && channels_last) return RLOD_EUNSUPPORTED;
+  return align_fwd_run(feat, B, C, H, W, R, ah, aw, GH, GW, pool_mode, channels_last, fast, tiled ? &tg : nullptr, out, ws,
+                       (cudaStream_t)stream, false);
 }
 
 RLOD_API int rlod_roi_align_backward(const float *grad_out, const float *rois, const float *feat,
@@ -1639,7 +1814,7 @@ RLOD_API int rlod_roi_align_backward(const float *grad_out, const float *rois, c
   if (fast) {
     cudaMemsetAsync(ws.flag, 0, 4 * sizeof(int), st);
     RLOD_LAUNCH(RLOD_KERNEL_ROI_PLAN, st,
-                k_roi_plan8_walk<<<(unsigned)cdiv(R, 4), 128, 0, st>>>(rois, R, B, H, W, P, spatial_scale, 1, ws));
+                k_roi_plan8_walk<<<(unsigned)cdiv(R, 4), 128, 0, st>>>(rois, R, B, H, W, P, spatial_scale, 1, kNoTiles, ws));
     RLOD_LAUNCH(RLOD_KERNEL_ROI_PLAN, st, k_roi_group_fixup<<<1, 32, 0, st>>>(R, B, ws));
     RLOD_LAUNCH(RLOD_KERNEL_ROI_PLAN, st,
                 k_roi_order_by_key<<<B, kOrderThreads, 0, st>>>(ws.ext, ws.order, ws.img_off, 16, 20, 8, ws.order2));

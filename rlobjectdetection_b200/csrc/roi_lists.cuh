@@ -9,10 +9,21 @@ namespace rlod {
 // ----------------------------------------------------------------------------------------
 // workspace layout
 // ----------------------------------------------------------------------------------------
+// Forward RoIAlign over a map that does not fit one CTA's shared memory: the map is covered by overlapping
+// tiles, every tile is a virtual image of the plane kernel (image b, tile (ty, tx) -> list b * ny * nx +
+// ty * nx + tx), and a roi goes to the tile that holds all of its taps (roi_align.cu).  ny = nx = 1: the
+// whole map is the tile.
+constexpr int kMaxTilesPerImage = 128;
+struct TileGrid {
+  int ny, nx;  // tiles per image
+  int th, tw;  // tile size in pixels (rows, columns); the last tile of an axis may hang over the map's edge
+  int sy, sx;  // distance between tile origins
+};
+
 struct AlignWs {
   int *flag;     // [4]   flag[0] != 0: rois are not grouped by image
-  int *img_off;  // [B+1] roi list offsets per image
-  int *cursor;   // [B]
+  int *img_off;  // [B * kMaxTilesPerImage + 1] roi list offsets per (virtual) image
+  int *cursor;   // [B * kMaxTilesPerImage]
   int *order;    // [R]   roi ids grouped by image (stable)
   int *roi_b;    // [R]   batch index (0 when out of range: the plan is all-invalid then)
   int *plan;     // [R * words]
@@ -32,8 +43,9 @@ static inline AlignWs carve_align_ws(void *base, int B, int R, int GH, int GW) {
     return q;
   };
   w.flag = (int *)take(4 * sizeof(int));
-  w.img_off = (int *)take((size_t)(B + 1) * sizeof(int));
-  w.cursor = (int *)take((size_t)(B > 0 ? B : 1) * sizeof(int));
+  // (lists per virtual image when the forward tiles a large map)
+  w.img_off = (int *)take(((size_t)(B > 0 ? B : 0) * kMaxTilesPerImage + 1) * sizeof(int));
+  w.cursor = (int *)take((size_t)(B > 0 ? B : 1) * kMaxTilesPerImage * sizeof(int));
   w.order = (int *)take((size_t)(R > 0 ? R : 1) * sizeof(int));
   w.roi_b = (int *)take((size_t)(R > 0 ? R : 1) * sizeof(int));
   w.plan = (int *)take((size_t)(R > 0 ? R : 1) * (size_t)(2 * GH + 2 * GW) * sizeof(int));

@@ -292,6 +292,51 @@ def test_roi_align_forward_split_tail(orc, mode, shuffle):
     close(out.cpu().numpy(), ref, what=f"split tail mode {mode} shuffle {shuffle}")
 
 
+@pytest.mark.parametrize("mode", [be.POOL_NONE, be.POOL_AVG, be.POOL_MAX])
+@pytest.mark.parametrize("case", [
+    dict(B=2, C=8, H=200, W=304, n_per=1500, stride=4.0),               # FPN P2 of 800 x 1216: 6 x 10 tiles
+    dict(B=3, C=4, H=50, W=200, n_per=130, stride=16.0, shuffle=True),  # tiled along x only, rois not grouped
+    dict(B=1, C=12, H=260, W=40, n_per=130, stride=8.0),                # tiled along y only, last tile hangs over
+    dict(B=2, C=4, H=100, W=167, n_per=380, stride=8.0, small=True),    # every roi fits a tile
+    dict(B=2, C=4, H=100, W=167, n_per=40, stride=8.0),                 # too few rois per tile: generic kernel
+])
+def test_roi_align_forward_tiled_large_maps(orc, case, mode):
+    """Maps beyond one CTA's shared memory: the plane kernel runs over overlapping tiles of the map (every roi in
+    the tile that holds all of its taps), rois larger than half a tile go through the generic kernel; the result is
+    the oracle's whatever the route.  Rois touch the borders, lie outside, are inverted (rois_for_batch)."""
+    B, C, H, W, stride = case["B"], case["C"], case["H"], case["W"], case["stride"]
+    g = torch.Generator().manual_seed(41)
+    feat = torch.randn(B, C, H, W, generator=g)
+    rois = syn.rois_for_batch(42, B, case["n_per"], H * stride, W * stride)
+    if case.get("small"):
+        ctr = 0.5 * (rois[:, 1:3] + rois[:, 3:5])
+        half = (0.5 * (rois[:, 3:5] - rois[:, 1:3])).clamp(-12 * stride, 12 * stride)
+        rois[:, 1:3], rois[:, 3:5] = ctr - half, ctr + half
+    if case.get("shuffle"):
+        rois = rois[torch.randperm(rois.size(0), generator=g)].contiguous()
+    ah = 8 if mode == be.POOL_NONE else 7
+    ref = orc.roi_align(feat.numpy(), rois.numpy(), ah, ah, 1 / stride, pool_mode=mode)
+    f, r = cu(feat), cu(rois)
+    n0 = be.lib().rlod_launch_count()
+    out = be.roi_align_forward(f, r, ah, ah, 1 / stride, mode)
+    # tiled: plan + lists + plane kernel + generic kernel for the rois beyond a tile; else plan + fix-up + generic
+    assert be.lib().rlod_launch_count() - n0 == (3 if case["n_per"] == 40 else 4)
+    close(out.cpu().numpy(), ref, what=f"tiled {case} mode {mode}")
+
+
+def test_roi_align_tiled_planned_forward_equals_forward():
+    from rlobjectdetection_b200.model.roi_align.modules.roi_align import RoIAlignAvg
+    g = torch.Generator().manual_seed(43)
+    feat = cu(torch.randn(2, 8, 120, 150, generator=g))
+    rois = cu(syn.rois_for_batch(44, 2, 320, 120 * 8.0, 150 * 8.0))  # 3 x 4 tiles, 26 rois per tile
+    layer = RoIAlignAvg(7, 7, 1 / 8.0)
+    ref = layer(feat, rois)
+    plan = layer.plan(rois, tuple(feat.shape))
+    with torch.no_grad():
+        out = layer.forward_planned(feat, plan)
+    assert torch.equal(out, ref)
+
+
 def test_roi_align_c2_full_size(orc):
     # config 2: Res-101 C4 at 600x1000 -> (4,1024,38,63), 4 x 256 rois, 7x7
     feat, rois = _align_case(1, 4, 1024, 38, 63, 256)

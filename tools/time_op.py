@@ -13,10 +13,17 @@ from rlobjectdetection_b200.model import _backend as be  # noqa: E402
 op, cfg = sys.argv[1], (sys.argv[2] if len(sys.argv) > 2 else "C4")
 iters = int(sys.argv[3]) if len(sys.argv) > 3 else 20
 dev = torch.device("cuda", 0)
-B, C, H, W, n_per = (4, 1024, 38, 63, 256) if cfg == "C2" else (24, 1024, 50, 75, 300)
+# P2: an FPN P2 level of 800 x 1216 (stride 4, rois of 16-112 pixels); BIG / BIGD: a stride-16 map of 1600 x 2400 with 300 / 2000 rois per image
+B, C, H, W, n_per = {"C2": (4, 1024, 38, 63, 256), "C4": (24, 1024, 50, 75, 300), "P2": (2, 256, 200, 304, 512),
+                     "BIG": (2, 1024, 100, 150, 300), "BIGD": (2, 1024, 100, 150, 2000)}[cfg]
+stride = 4.0 if cfg == "P2" else 16.0
 g = torch.Generator().manual_seed(1)
 feat = torch.randn(B, C, H, W, generator=g).to(dev)
-rois = syn.rois_for_batch(2, B, n_per, H * 16.0, W * 16.0).to(dev)
+if cfg == "P2":
+    rois = torch.cat([torch.cat([torch.full((n_per, 1), float(b)), syn.random_boxes(g, n_per, H * stride, W * stride, 16.0, 112.0)], 1)
+                      for b in range(B)]).to(dev)
+else:
+    rois = syn.rois_for_batch(2, B, n_per, H * stride, W * stride).to(dev)
 gout = torch.randn(rois.size(0), C, 7, 7, generator=g).to(dev)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 if op == "pool_bwd":
@@ -28,7 +35,7 @@ if op.startswith("crop"):
 fns = {
     "crop_fwd": lambda: be.roi_crop_forward(feat, gyx),
     "crop_bwd": lambda: be.roi_crop_backward(gout14, gyx, (B, C, H, W)),
-    "align_fwd": lambda: be.roi_align_forward(feat, rois, 7, 7, 1 / 16.0, be.POOL_AVG),
+    "align_fwd": lambda: be.roi_align_forward(feat, rois, 7, 7, 1 / stride, be.POOL_AVG),
     "align_bwd": lambda: be.roi_align_backward(gout, rois, None, (B, C, H, W), 7, 7, 1 / 16.0, be.POOL_AVG),
     "pool_fwd": lambda: be.roi_pool_forward(feat, rois, 7, 7, 1 / 16.0),
     "pool_bwd": lambda: be.roi_pool_backward(gout, am, rois, (B, C, H, W), 7, 7, 1 / 16.0),
