@@ -702,7 +702,7 @@ def measure_ops(iters=20, legacy_iters=8):
         rows.append(r)
         print(json.dumps(r), file=sys.stderr, flush=True)
 
-    def align_case(tag, B, C, H, W, n_per, seed):
+    def align_case(tag, B, C, H, W, n_per, seed, fwd_only=False):
         g = torch.Generator().manual_seed(seed)
         feat = torch.randn(B, C, H, W, generator=g).to(dev)
         rois = syn.rois_for_batch(seed + 1, B, n_per, H * 16.0, W * 16.0).to(dev)
@@ -722,6 +722,8 @@ def measure_ops(iters=20, legacy_iters=8):
                 return torch.nn.functional.avg_pool2d(top, kernel_size=2, stride=1)  # modules/roi_align.py:29
             lg = time_us(legacy_fwd, iters=legacy_iters, warm=2)
         add(f"RoIAlignAvg fwd {tag}", fb, ours, lg, f"B={B} C={C} {H}x{W} R={R}")
+        if fwd_only:
+            return None
         # backward
         ours = time_us(lambda: be.roi_align_backward(gout, rois, None, (B, C, H, W), 7, 7, 1 / 16.0, be.POOL_AVG))
         lg = None
@@ -799,6 +801,10 @@ def measure_ops(iters=20, legacy_iters=8):
     add("RoICrop 14x14 bwd C2", cb, ours_b, lgb2)
     del feat, rois, gout, out, am, gout14, gxy, gyx
     align_case("C4", 24, 1024, 50, 75, 300, 3)
+    torch.cuda.empty_cache()
+    # a map beyond one CTA's shared memory (1600 x 2400 image at stride 16): the plane kernel over overlapping tiles
+    align_case("large map 100x150, 2000 rois/image (tiled planes)", 2, 1024, 100, 150, 2000, 7, fwd_only=True)
+    torch.cuda.empty_cache()
 
     # NMS, C1 size: 12000 sorted boxes, thr 0.7
     g = torch.Generator().manual_seed(0)
