@@ -602,7 +602,7 @@ def run_ours(args, rank, local_rank, world):
     if world == 1 and not args.no_ops:
         dev_in = None
         torch.cuda.empty_cache()
-        ops = ops_summary(measure_ops(iters=10, legacy_iters=4))
+        ops = ops_summary(measure_ops(iters=20, legacy_iters=4))
 
     # ---- CPU baseline, bounded sample ---------------------------------------------------------
     cpu = None
@@ -675,8 +675,19 @@ def measure_ops(iters=20, legacy_iters=8):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def time_us(fn, iters=iters, warm=3):
-        for _ in range(warm):
+        # warm-up by TIME as well as by count: this leg follows seconds of host-only work (the CPU baseline), the SM
+        # clock ramps up over the first milliseconds of load, and the issue-bound ops (RoIAlign backward, RoIPool
+        # forward) read 15-25 % slow in a median of 10 samples taken right after three calls
+        t_end = time.perf_counter() + 0.03
+        n = 0
+        while n < warm or time.perf_counter() < t_end:
             fn()
+            n += 1
+            if n % 4 == 0:
+                torch.cuda.synchronize()
+            if n >= 200:
+                break
+        torch.cuda.synchronize()
         ts = []
         for _ in range(iters):
             flush.zero_()  # cold L2 for every sample
