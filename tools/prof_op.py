@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Run one op of the path a few times (for ncu): python tools/prof_op.py {align_fwd|align_bwd|pool_fwd|pool_bwd|nms|proposal} {C2|C4}"""
+"""Run one op of the path a few times (for ncu): python tools/prof_op.py {align_fwd|align_bwd|pool_fwd|pool_bwd|nms|proposal} {C2|C4|BIGD}"""  # BIGD: 2 x 1024 x 100 x 150, 2000 rois per image (tiled planes)
 import os
 import sys
 
@@ -11,7 +11,7 @@ from rlobjectdetection_b200.model import _backend as be  # noqa: E402
 
 op, cfg = sys.argv[1], (sys.argv[2] if len(sys.argv) > 2 else "C4")
 dev = torch.device("cuda", 0)
-B, C, H, W, n_per = (4, 1024, 38, 63, 256) if cfg == "C2" else (24, 1024, 50, 75, 300)
+B, C, H, W, n_per = {"C2": (4, 1024, 38, 63, 256), "BIGD": (2, 1024, 100, 150, 2000)}.get(cfg, (24, 1024, 50, 75, 300))
 g = torch.Generator().manual_seed(1)
 if op.startswith("align") or op.startswith("pool"):
     feat = torch.randn(B, C, H, W, generator=g).to(dev)
