@@ -10,6 +10,8 @@
 // ALL R rois (O(B*C*H*W*R)); here the saved argmax turns it into a single pass over the
 // R*C*ph*pw gradients with at most one fp32 RED each -- the only work that exists -- while
 // keeping the gather's visiting rules, so malformed rois lose their gradient exactly as there.
+#include <type_traits>
+
 #include "roi_lists.cuh"
 
 namespace rlod {
@@ -67,7 +69,9 @@ __global__ void k_pool_plan(const float *__restrict__ rois, int R, int B, int H,
   // shape key (8 x 8 classes: bin rows, bin column steps of 4) so that the four rois a warp serves
   // together scan the same window: the kernel's loops run to the LONGEST bin of the four in each
   // direction, a tall-thin and a wide-short roi of equal area would cost their product
-  const int kr = bvalid ? min(mr, 8) : 0, kc = bvalid ? min((mc + 3) >> 2, 7) : 0;
+  // (columns: the widths the kernel's scan loop distinguishes -- 1, 2, up to 4, then steps of 4)
+  const int kr = bvalid ? min(mr, 8) : 0;
+  const int kc = !bvalid ? 0 : (mc <= 1 ? 0 : (mc == 2 ? 1 : min(((mc + 3) >> 2) + 1, 7)));
   e[31] = (kr > 0 ? kr - 1 : 0) * 8 + kc;
   roi_list_mark(rois, r, R, B, bvalid ? bi : 0, ws);
 }
@@ -109,16 +113,11 @@ __global__ void __launch_bounds__(kPoolThreads, 2)
   for (int g = warp, it = 0; g < n_groups; g += kPoolWarps, ++it) {
     const int kk = r0 + 4 * g + slot;
     const int r = kk < r1 ? __ldg(order + kk) : -1;
-    // this lane's column bin, the roi's row bins
-    int hs[7], he[7], ws = 0, we = 0, mr = 0, mc = 0;
-#pragma unroll
-    for (int p = 0; p < 7; ++p) hs[p] = 0, he[p] = 0;
+    // this lane's column bin; the roi's row bins are read from the record bin by bin (L1 hits: the loop over
+    // the row bins below is NOT unrolled -- three scan widths x seven unrolled bins were 112 KB of code)
+    int ws = 0, we = 0, mr = 0, mc = 0;
+    const int *e = rec + (size_t)(r >= 0 ? r : 0) * 32;
     if (r >= 0) {
-      const int *e = rec + (size_t)r * 32;
-      const int4 a0 = __ldg(reinterpret_cast<const int4 *>(e)), a1 = __ldg(reinterpret_cast<const int4 *>(e) + 1);
-      const int4 a2 = __ldg(reinterpret_cast<const int4 *>(e) + 2), a3 = __ldg(reinterpret_cast<const int4 *>(e) + 3);
-      hs[0] = a0.x, hs[1] = a0.y, hs[2] = a0.z, hs[3] = a0.w, hs[4] = a1.x, hs[5] = a1.y, hs[6] = a1.z;
-      he[0] = a1.w, he[1] = a2.x, he[2] = a2.y, he[3] = a2.z, he[4] = a2.w, he[5] = a3.x, he[6] = a3.y;
       if (k < 7) ws = __ldg(e + 14 + k), we = __ldg(e + 21 + k);
       if (__ldg(e + 28) >= 0) mr = __ldg(e + 29), mc = __ldg(e + 30);
       else we = ws;  // batch index out of range: every bin empty
@@ -129,28 +128,32 @@ __global__ void __launch_bounds__(kPoolThreads, 2)
       if (k == 0) bulk_wait_read<0>();
       __syncwarp();
     }
-#pragma unroll
+    // STEP pixels of a bin row per step (1, 2 or 4: the widest bin of the four rois decides, and the lists are
+    // ordered by that class -- a masked pixel costs as much as a real one, and half of the rois of a detector
+    // have bins of one or two columns): the loads are independent (predicated, a pixel outside the bin keeps
+    // the -FLT_MAX sentinel and can never win a strict '>'), then the compare chain in scan order
+    auto scan_bins = [&](auto stepc, auto loopc) {
+    constexpr int STEP = decltype(stepc)::value;
+    constexpr bool LOOP = decltype(loopc)::value;  // false: the widest bin fits one step
+#pragma unroll 1
     for (int ph = 0; ph < 7; ++ph) {
       float4 mv = make_float4(-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f);
       int4 mi = make_int4(-1, -1, -1, -1);
-      const int h0 = hs[ph], h1 = he[ph];
-      // four pixels of a bin row per step: the loads are independent (predicated, a pixel outside
-      // the bin keeps the -FLT_MAX sentinel and can never win a strict '>'), then the compare
-      // chain in scan order
+      const int h0 = r >= 0 ? __ldg(e + ph) : 0, h1 = r >= 0 ? __ldg(e + 7 + ph) : 0;
       for (int dh = 0; dh < mrw; ++dh) {
         const int h = h0 + dh;
         const bool rowok = h < h1;
         const int rowpix = h * W + ws;
         const uint32_t rowaddr = pbase + 16u * (uint32_t)(h * P + ws);
-        for (int dw = 0; dw < mcw; dw += 4) {
-          float4 v[4];
+        for (int dw = 0; LOOP ? dw < mcw : dw < 1; dw += STEP) {
+          float4 v[STEP];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < STEP; ++j) {
             v[j] = make_float4(-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f);
             if (rowok && ws + dw + j < we) v[j] = lds128(rowaddr + 16u * (uint32_t)(dw + j));
           }
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < STEP; ++j) {
             if (AM) {
               const int pix = rowpix + dw + j;
               if (v[j].x > mv.x) mv.x = v[j].x, mi.x = pix;
@@ -176,6 +179,11 @@ __global__ void __launch_bounds__(kPoolThreads, 2)
         }
       }
     }
+    };
+    if (mcw <= 1) scan_bins(std::integral_constant<int, 1>{}, std::false_type{});  // warp-uniform
+    else if (mcw == 2) scan_bins(std::integral_constant<int, 2>{}, std::false_type{});
+    else if (mcw <= 4) scan_bins(std::integral_constant<int, 4>{}, std::false_type{});
+    else scan_bins(std::integral_constant<int, 4>{}, std::true_type{});
     fence_async_smem();
     __syncwarp();
     if (k == 0) {
