@@ -199,6 +199,43 @@ __device__ __forceinline__ void fill_planes4_window_async(float4 *planes4, const
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
+// The window fill with 128-bit loads, for windows whose rows start 16-byte aligned in every channel plane (map
+// width, window origin and the map's base all multiples of 4 floats): a warp takes blocks of 8 rows x 16 pixels,
+// a lane 4 consecutive pixels of a row in all 4 channels (four coalesced LDG.128, 64 contiguous bytes per row and
+// channel over 4 lanes), transposes them in registers and stores one float4 (4 channels) per pixel, scaled by
+// `pre`.  4-byte async copies move one element per thread and instruction: ~9 us for a 61 x 61 x 4 window,
+// against ~3.5 us for the bulk-copy fill of a whole plane set of that size.  Synchronous: the caller needs a
+// __syncthreads() before reading, no cp.async wait.
+template <int THREADS>
+__device__ __forceinline__ void fill_planes4_window_vec(float4 *planes4, const float *__restrict__ src, int rows,
+                                                        int cols, int P, int row_stride, size_t chan_stride,
+                                                        float pre) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ly = lane >> 2, lx = (lane & 3) * 4;
+  const int rblks = (rows + 7) >> 3, cblks = (cols + 15) >> 4;
+  for (int blk = warp; blk < rblks * cblks; blk += THREADS / 32) {
+    const int rb = blk / cblks, cb = blk - rb * cblks;
+    const int y = rb * 8 + ly, x = cb * 16 + lx;
+    if (y >= rows || x >= cols) continue;
+    const float *s = src + (size_t)y * row_stride + x;
+    float4 *d = planes4 + y * P + x;
+    if (x + 3 < cols) {
+      const float4 a = __ldg(reinterpret_cast<const float4 *>(s));
+      const float4 b = __ldg(reinterpret_cast<const float4 *>(s + chan_stride));
+      const float4 c = __ldg(reinterpret_cast<const float4 *>(s + 2 * chan_stride));
+      const float4 e = __ldg(reinterpret_cast<const float4 *>(s + 3 * chan_stride));
+      d[0] = make_float4(pre * a.x, pre * b.x, pre * c.x, pre * e.x);
+      d[1] = make_float4(pre * a.y, pre * b.y, pre * c.y, pre * e.y);
+      d[2] = make_float4(pre * a.z, pre * b.z, pre * c.z, pre * e.z);
+      d[3] = make_float4(pre * a.w, pre * b.w, pre * c.w, pre * e.w);
+    } else {
+      for (int j = 0; x + j < cols; ++j)
+        d[j] = make_float4(pre * __ldg(s + j), pre * __ldg(s + chan_stride + j), pre * __ldg(s + 2 * chan_stride + j),
+                           pre * __ldg(s + 3 * chan_stride + j));
+    }
+  }
+}
+
 // The same fill from a channels-last (NHWC) feature map: the 4 channels of a pixel are already one
 // contiguous, 16-byte aligned float4 (C % 4 == 0), C floats from the next pixel -- one 16-byte async
 // copy per pixel, no interleave at all.  A 32-byte DRAM sector holds two chunks' worth, so the CTAs
