@@ -1564,17 +1564,26 @@ static bool align_fwd_tiles(int B, int C, int H, int W, int R, int GH, int GW, i
 // A/B switches: RLOD_NO_PDL=1 (roi_lists.cuh) launches the list and pooling kernels of the forward strictly one
 // after the other; RLOD_NO_SPLIT=1 keeps one CTA per (image, 4 channels) in the last wave of the pooling launch.
 
-// How the pooling launch ends: `items` CTAs of equal cost on `slots` resident CTAs leave the last wave
-// partly empty; when at most half of it is used, every item of that wave is served by S CTAs (S <= 4,
-// at least ~16 roi groups each).  Returns S (1 = no split) and the first split item.
-static int fwd_tail_split(int items, int slots, int rois_per_image, int *split_from) {
+// How the pooling launch ends: the CTAs have equal cost, so the launch ends with a partial wave.  Each item of
+// that wave can be served by S CTAs instead, every one with its own copy of the planes and a contiguous share of
+// the image's roi groups.  Measured on the merged pooling call of the C4 step (tools/ab_split.sh; S = 1 / 2 / 3,
+// a wave counted as one CTA per SM = 148 | as the 296 resident CTAs): 3 images per rank 130.0 / 121.8 / 119.8 |
+// 130.0 / 123.9 / 123.9 us, 6 images 224.3 / 216.0 / 220.1 us (both), 12 images 405.5 / 406.5 / 406.5 us (both);
+// C2 78.6 / 76.8 us.  Only the very end of the launch matters (the smaller wave is the better unit), and a wave
+// model with the fill as a fixed cost does not predict the table -- an unsplit tail runs one CTA per SM, faster
+// than two co-resident ones -- so the rule is the measured one: thirds up to 5 waves of 148, halves up to 12,
+// while the parts keep ~16 roi groups.  Returns S (1 = no split) and the first split item.
+static int fwd_tail_split(int items, int rois_per_image, int *split_from) {
   static const bool off = getenv("RLOD_NO_SPLIT") != nullptr;
-  const int full = items / slots * slots, rem = items - full;
+  static const int force = getenv("RLOD_SPLIT") ? atoi(getenv("RLOD_SPLIT")) : 0;  // A/B: this S whenever rem > 0
+  static const int env_slots = getenv("RLOD_SPLIT_SLOTS") ? atoi(getenv("RLOD_SPLIT_SLOTS")) : 0;  // A/B: the wave
+  const int slots = env_slots > 0 ? env_slots : kSmCount;
+  const int waves = items / slots, full = waves * slots, rem = items - full;
   *split_from = items;
   if (off || rem == 0) return 1;
-  int S = slots / rem;
-  if (S > 4) S = 4;
+  int S = waves <= 5 ? 3 : (waves <= 12 ? 2 : 1);
   while (S > 1 && rois_per_image / (4 * S) < 16) --S;
+  if (force >= 1 && force <= 4) S = force;
   if (S > 1) *split_from = full;
   return S;
 }
@@ -1672,8 +1681,7 @@ static int align_fwd_run(const float *feat, int B, int C, int H, int W, int R, i
     const int n_chunks = C / 4;
     const int P = walk_pitch(W);
     int split_from = B * n_chunks;
-    const int split = v1 ? 1 : fwd_tail_split(B * n_chunks, (2 * smem + 2048 <= (size_t)kMaxSmemPerCta ? 2 : 1) * kSmCount,
-                                              R / B, &split_from);
+    const int split = v1 ? 1 : fwd_tail_split(B * n_chunks, R / B, &split_from);
     const unsigned grid = (unsigned)(split_from + (B * n_chunks - split_from) * split);
 #define RLOD_LAUNCH_FWD(POOL)                                                                  \
   do {                                                                                         \

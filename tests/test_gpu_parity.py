@@ -272,7 +272,7 @@ def test_roi_align_long_roi_lists(orc, grouped):
 @pytest.mark.parametrize("shuffle", [False, True])
 def test_roi_align_forward_split_tail(orc, mode, shuffle):
     """Few (image, 4-channel) items and long roi lists: the pooling launch serves every item of its last wave
-    with up to four CTAs, each with a contiguous share of the image's roi groups (fwd_tail_split).  Ragged
+    with two or three CTAs, each with a contiguous share of the image's roi groups (fwd_tail_split).  Ragged
     lists: an image with fewer groups than CTAs (empty shares), an image without rois, shares of unequal size."""
     B, C, H, W = 4, 8, 30, 41
     counts = [3, 0, 1021, 517]

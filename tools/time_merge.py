@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Two RoIAlignAvg forward calls on the same feature map against ONE call on the concatenated roi sets
-(python tools/time_merge.py {C4|C4x3}): what sharing the plane fill and the plan launches is worth."""
+(python tools/time_merge.py {C4|C4xN}): what sharing the plane fill and the plan launches is worth."""
 import os, statistics, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -9,7 +9,8 @@ from rlobjectdetection_b200.model import _backend as be  # noqa: E402
 
 cfg = sys.argv[1] if len(sys.argv) > 1 else "C4"
 dev = torch.device("cuda", 0)
-B, C, H, W, n_per = (24, 1024, 50, 75, 300) if cfg == "C4" else (3, 1024, 50, 75, 300)
+# C4xN: N images of the C4 shape (what a rank holds when the batch of 24 is sharded: C4x3 at 8 GPUs, C4x6 at 4)
+B, C, H, W, n_per = (24, 1024, 50, 75, 300) if cfg == "C4" else (int(cfg[3:]), 1024, 50, 75, 300)
 g = torch.Generator().manual_seed(1)
 feat = torch.randn(B, C, H, W, generator=g).to(dev)
 ra = syn.rois_for_batch(2, B, n_per, H * 16.0, W * 16.0, edge_cases=False).to(dev)
