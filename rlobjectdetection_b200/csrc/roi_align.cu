@@ -1755,6 +1755,29 @@ RLOD_API int rlod_roi_align_forward(const float *feat, const float *rois, int B,
                        st, true);
 }
 
+// Pure host arithmetic (no CUDA call): which kernels rlod_roi_align_forward would launch for this geometry.
+RLOD_API int rlod_roi_align_forward_route(int B, int C, int H, int W, int R, int ah, int aw, int pool_mode,
+                                          int channels_last, int *info) {
+  if (!info) return RLOD_EINVAL;
+  for (int i = 0; i < 8; ++i) info[i] = 0;
+  if (check_align_args(reinterpret_cast<const float *>(info), B, C, H, W, R, ah, aw, pool_mode) != RLOD_OK || B < 1)
+    return RLOD_EINVAL;
+  const int GH = pool_mode == RLOD_POOL_NONE ? ah : ah + 1;
+  const int GW = pool_mode == RLOD_POOL_NONE ? aw : aw + 1;
+  TileGrid tg;
+  if (align_fwd_geometry_fast(B, C, H, W, R, GH, GW, pool_mode)) {
+    int split_from = B * (C / 4);
+    info[0] = 1;
+    info[7] = fwd_tail_split(B * (C / 4), R / B, &split_from);
+    info[1] = info[2] = 1, info[3] = H, info[4] = W, info[5] = H, info[6] = W;
+  } else if (align_fwd_tiles(B, C, H, W, R, GH, GW, pool_mode, channels_last, &tg)) {
+    info[0] = 2, info[1] = tg.ny, info[2] = tg.nx, info[3] = tg.th, info[4] = tg.tw, info[5] = tg.sy, info[6] = tg.sx;
+    info[7] = 1;
+  }
+  if (channels_last && info[0] != 1) return RLOD_EUNSUPPORTED;
+  return RLOD_OK;
+}
+
 RLOD_API int rlod_roi_align_plan(const float *rois, int B, int C, int H, int W, int R, int ah, int aw,
                                  float spatial_scale, int pool_mode, void *workspace, size_t workspace_bytes,
                                  rlod_stream_t stream) {

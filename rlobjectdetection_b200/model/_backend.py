@@ -40,6 +40,7 @@ SIGNATURES = {
     "rlod_debug_nms_force_large": (_I, [_I]),
     "rlod_nms_batched": (_I, [_P, _I, _P, _I, _I, _F, _I, _P, _P, _P, _Z, _P]),
     "rlod_roi_align_workspace_bytes": (_Z, [_I, _I, _I, _I, _I]),
+    "rlod_roi_align_forward_route": (_I, [_I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "rlod_roi_align_forward": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _I, _I, _P, _P, _Z, _P]),
     "rlod_roi_align_plan": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _F, _I, _P, _Z, _P]),
     "rlod_roi_align_forward_planned": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _Z, _P]),

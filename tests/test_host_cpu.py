@@ -42,6 +42,47 @@ def test_workspace_queries_are_pure_host_arithmetic():
     assert lib.rlod_proposal_workspace_bytes(1, 9, 37, 62, 12000, 2000) >= 12000 * 16 + 188 * 188 * 512
 
 
+def _route(lib, B, C, H, W, R, pool_mode, channels_last=0):
+    import ctypes
+    info = (ctypes.c_int * 8)()
+    rc = lib.rlod_roi_align_forward_route(B, C, H, W, R, 7, 7, pool_mode, channels_last, ctypes.cast(info, ctypes.c_void_p))
+    return rc, list(info)
+
+
+def test_roi_align_forward_route_is_host_arithmetic():
+    """Which kernels the RoIAlign forward takes: plane kernel for the reference's maps, tiles for dense roi sets on
+    maps beyond one CTA's shared memory (tiles cover the map, overlap by half, stay within the plane kernel's limits),
+    the gather kernel for sparse ones; the last wave of a short launch is split."""
+    from rlobjectdetection_b200.model import _backend as be
+    lib = be.lib()
+    AVG = be.POOL_AVG
+    # the reference's configurations: plane kernel, whole map
+    for (B, C, H, W, R, split) in ((24, 1024, 50, 75, 14400, 1), (4, 1024, 38, 63, 1024, 2), (3, 1024, 50, 75, 1800, 3),
+                                  (6, 1024, 50, 75, 3600, 2), (12, 1024, 50, 75, 7200, 1)):
+        rc, info = _route(lib, B, C, H, W, R, AVG)
+        assert rc == 0 and info[0] == 1 and info[1:3] == [1, 1] and info[7] == split, (B, C, H, W, R, info)
+    assert _route(lib, 2, 6, 20, 30, 64, AVG)[1][0] == 0          # C % 4 != 0: gather kernel
+    # large maps: tiles for dense roi sets
+    for (B, C, H, W, R) in ((2, 1024, 100, 150, 4000), (2, 256, 200, 304, 2 * 60 * 16), (1, 12, 260, 40, 130),
+                            (3, 4, 50, 200, 390), (2, 256, 200, 336, 2 * 128 * 16), (1, 64, 300, 90, 4000)):
+        rc, info = _route(lib, B, C, H, W, R, AVG)
+        kind, ny, nx, th, tw, sy, sx, _ = info
+        assert rc == 0 and kind == 2, (B, C, H, W, R, info)
+        assert ny * nx >= 2 and ny * nx <= 128 and R >= 16 * B * ny * nx
+        assert (ny - 1) * sy + th >= H and (nx - 1) * sx + tw >= W        # the tiles cover the map
+        assert (ny == 1 and th == H) or (sy <= th // 2 and (ny - 2) * sy + th < H)   # half-tile overlap, no spare tile
+        assert (nx == 1 and tw == W) or (sx <= tw // 2 and (nx - 2) * sx + tw < W)
+        assert (th + 2) * ((tw + 1) | 1) <= 4030                          # two CTAs per SM
+        assert W % 4 != 0 or nx == 1 or sx % 4 == 0                       # 16-byte aligned window rows
+    # sparse roi sets and maps beyond 128 tiles: gather kernel
+    assert _route(lib, 2, 256, 200, 304, 1024, AVG)[1][0] == 0
+    assert _route(lib, 1, 64, 600, 600, 100000, AVG)[1][0] == 0
+    # channels-last is the plane kernel's only
+    assert _route(lib, 2, 64, 25, 38, 64, AVG, channels_last=1)[0] == 0
+    assert _route(lib, 2, 1024, 100, 150, 4000, AVG, channels_last=1)[0] == -3   # RLOD_EUNSUPPORTED
+    assert _route(lib, 0, 64, 25, 38, 64, AVG)[0] == -1
+
+
 def test_invalid_arguments_are_rejected_without_a_gpu():
     from rlobjectdetection_b200.model import _backend as be
     lib = be.lib()
