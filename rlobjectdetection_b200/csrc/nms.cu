@@ -731,6 +731,9 @@ __device__ __forceinline__ void lz_cluster_sync() {
 
 __global__ void __launch_bounds__(kLazyThreads)
     k_nms_lazy(NmsSegs segs, float thresh, int max_keep, NmsOut o) {
+  // launched as a programmatic dependent of whatever kernel precedes it on the stream (in the proposal layer:
+  // k_proposal_decode): the boxes and the segment table are complete and visible after the wait
+  pdl_wait();
   extern __shared__ __align__(16) unsigned char lz_raw[];
   float4 *kbox = reinterpret_cast<float4 *>(lz_raw);
   float *kSa = reinterpret_cast<float *>(kbox + max_keep);
@@ -924,11 +927,13 @@ int nms_launch(const NmsSegs &segs, int nseg, int max_seg, float thresh, int max
     cfg.blockDim = dim3(kLazyThreads, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = (unsigned)cs, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     const cudaError_t e = cudaLaunchKernelEx(&cfg, k_nms_lazy, segs, thresh, max_keep, out);
     return e != cudaSuccess ? (int)e : launch_status();
   }

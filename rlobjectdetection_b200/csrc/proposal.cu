@@ -334,6 +334,7 @@ static __host__ __device__ inline ClLayout cl_layout(int A, int HW, int M) {
 
 __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kClThreads)
     k_proposal_cluster(PropArgs a, int mp) {
+  pdl_trigger();  // k_proposal_decode is set up behind this grid (it waits for the selection itself)
   extern __shared__ __align__(16) unsigned char cl_raw[];
   const int HW = a.H * a.W, KA = HW * a.A, M = a.pre;
   const ClLayout L = cl_layout(a.A, HW, M);
@@ -550,6 +551,10 @@ __global__ void __cluster_dims__(kClusterSize, 1, 1) __launch_bounds__(kClThread
 
 // decode + clip the selected anchors in sorted order: one thread per (image, rank)
 __global__ void __launch_bounds__(256) k_proposal_decode(PropArgs a, int mp) {
+  // a programmatic dependent of the select / sort kernel, and the NMS kernel is one of this: set up early,
+  // the sorted selection is complete and visible after the wait
+  pdl_trigger();
+  pdl_wait();
   const int M = a.pre, HW = a.H * a.W;
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= (long long)a.B * M) return;
@@ -678,7 +683,8 @@ RLOD_API int rlod_proposal_forward(const float *scores, const float *deltas, con
     RLOD_LAUNCH(RLOD_KERNEL_PROPOSAL_SORT, st, k_proposal_sort_decode<<<B, kSortThreads, smem, st>>>(pa, mp));
   }
   RLOD_LAUNCH(RLOD_KERNEL_PROPOSAL_SORT, st,
-              k_proposal_decode<<<(unsigned)cdiv((long long)B * pre, 256), 256, 0, st>>>(pa, mp));
+              launch_after(k_proposal_decode, dim3((unsigned)cdiv((long long)B * pre, 256)), dim3(256), 0, st, pdl_enabled(), pa,
+                           mp));
   int rc = launch_status();
   if (rc) return rc;
 

@@ -1,6 +1,7 @@
 // Shared helpers for the sm_100a kernels of librlod_sm100a.so.
 #pragma once
 #include <cuda_runtime.h>
+#include <cstdlib>
 #include <stdint.h>
 
 #include "rlod.h"
@@ -45,6 +46,12 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 // both instructions do nothing, so kernels that carry them can be launched either way.
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// A/B switch: RLOD_NO_PDL=1 launches the kernels of a call strictly one after the other
+static inline bool pdl_enabled() {
+  static const bool on = getenv("RLOD_NO_PDL") == nullptr;
+  return on;
+}
 
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_after(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,

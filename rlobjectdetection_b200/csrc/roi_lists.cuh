@@ -78,12 +78,6 @@ __device__ __forceinline__ void roi_list_mark(const float *__restrict__ rois, in
     for (int q = b + 1; q <= B; ++q) ws.img_off[q] = R;
 }
 
-// A/B switch: RLOD_NO_PDL=1 launches the plan / list / pooling kernels of a call strictly one after the other
-static inline bool pdl_enabled() {
-  static const bool on = getenv("RLOD_NO_PDL") == nullptr;
-  return on;
-}
-
 // one warp: stable counting sort of roi ids by image, only when the rois were not grouped
 static __global__ void k_roi_group_fixup(int R, int B, AlignWs ws) {
   pdl_trigger();  // (see k_roi_lists_finish)
