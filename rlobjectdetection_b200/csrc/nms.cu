@@ -933,7 +933,7 @@ int nms_launch(const NmsSegs &segs, int nseg, int max_seg, float thresh, int max
     at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    cfg.numAttrs = proposal_pdl_enabled() ? 2 : 1;
     const cudaError_t e = cudaLaunchKernelEx(&cfg, k_nms_lazy, segs, thresh, max_keep, out);
     return e != cudaSuccess ? (int)e : launch_status();
   }

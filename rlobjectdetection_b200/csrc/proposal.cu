@@ -683,7 +683,7 @@ RLOD_API int rlod_proposal_forward(const float *scores, const float *deltas, con
     RLOD_LAUNCH(RLOD_KERNEL_PROPOSAL_SORT, st, k_proposal_sort_decode<<<B, kSortThreads, smem, st>>>(pa, mp));
   }
   RLOD_LAUNCH(RLOD_KERNEL_PROPOSAL_SORT, st,
-              launch_after(k_proposal_decode, dim3((unsigned)cdiv((long long)B * pre, 256)), dim3(256), 0, st, pdl_enabled(), pa,
+              launch_after(k_proposal_decode, dim3((unsigned)cdiv((long long)B * pre, 256)), dim3(256), 0, st, proposal_pdl_enabled(), pa,
                            mp));
   int rc = launch_status();
   if (rc) return rc;
